@@ -1,0 +1,8 @@
+"""smc_jl_b200 -- B200-native SMC particle engine behind SMC.jl's `smc(...)` / `Cloud` API.
+
+The compute path is the CUDA library `libsmcb200.so` (C ABI in include/smcb200.h); this package
+is the host-side mirror of the reference's Julia interface.  There is no CPU fallback.
+"""
+from .model import (Beta, CAPMLogLik, Gamma, GaussRegLogLik, InverseGamma, LinearEquationsLogLik,  # noqa: F401
+                    LinearGaussianLogLik, ModelSpec, Normal, Parameter, RootInverseGamma, Uniform, make_spec,
+                    parameter)

@@ -1,0 +1,211 @@
+// detmath.cuh -- deterministic binary64 elementary functions + Philox4x32-10 for the SMC engine.
+//
+// Every operation is an explicit IEEE-754 binary64 +,-,*,/,sqrt or fma, so host code, device
+// code and the CPU oracle (oracle/smc_oracle.c, written independently against the same
+// algorithm description in DESIGN.md "Numerical contract") produce identical bits.  The library
+// is compiled with -fmad=false (device) and -ffp-contract=off (host): the ONLY fused operations
+// are the fma() calls written here.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define SMC_HD __host__ __device__ __forceinline__
+#else
+#define SMC_HD inline
+#endif
+
+namespace smc {
+
+SMC_HD double bits_to_double(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x; std::memcpy(&x, &u, 8); return x;
+#endif
+}
+SMC_HD uint64_t double_to_bits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; std::memcpy(&u, &x, 8); return u;
+#endif
+}
+SMC_HD double dinf()
+{
+    return bits_to_double(0x7ff0000000000000ull);
+}
+SMC_HD double dnan()
+{
+    return bits_to_double(0x7ff8000000000000ull);
+}
+
+// exp(x): k = rint(x*log2(e)); r = x - k*ln2 (Cody-Waite, 2 fma); degree-13 Taylor in Horner
+// form; scale by 2^k with at most one rounding.
+SMC_HD double det_exp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.782712893384) return dinf();
+    if (x < -745.1332191019412) return 0.0;
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const double kd = t - 6755399441055744.0;
+    int k = (int)kd;
+    double r = fma(-kd, 6.93147180369123816490e-01, x);
+    r = fma(-kd, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    if (k > 1023) { p *= 0x1p1023; k -= 1023; }
+    if (k < -1021) { p *= 0x1p-1000; k += 1000; }
+    return p * bits_to_double((uint64_t)(k + 1023) << 52);
+}
+
+// log(x): fdlibm-style reduction x = 2^k (1+f), s = f/(2+f), degree-14 odd series in s.
+SMC_HD double det_log(double x)
+{
+    uint64_t ix = double_to_bits(x);
+    int32_t hx = (int32_t)(ix >> 32);
+    const uint32_t lx = (uint32_t)ix;
+    int k = 0;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -dinf();
+        if (hx < 0) return dnan();
+        k -= 54; x *= 0x1p54; ix = double_to_bits(x); hx = (int32_t)(ix >> 32);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int32_t i = (hx + 0x95f64) & 0x100000;
+    ix = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (ix & 0xffffffffull);
+    x = bits_to_double(ix);
+    k += (i >> 20);
+    const double dk = (double)k;
+    const double f = x - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
+                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double u = fma(s, hfsq + R, dk * 1.90821492927058770002e-10);
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - u) - f));
+}
+
+// sin(2*pi*u), cos(2*pi*u) for u in [0,1): exact octant split, fdlibm kernels on [0, pi/4].
+SMC_HD void det_sincos2pi(double u, double& sn, double& cs)
+{
+    const double t = u * 8.0;
+    const int o = (int)t;
+    const double f = t - (double)o;
+    const double g = (o & 1) ? (1.0 - f) : f;
+    const double x = g * 7.85398163397448278999e-01;
+    const double z = x * x;
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
+                                               2.75573137070700676789e-06), -1.98412698298579493134e-04),
+                                 8.33333333332248946124e-03), -1.66666666666666324348e-01);
+    const double s = fma(x * z, ps, x);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
+                                               -2.75573143513906633035e-07), 2.48015872894767294178e-05),
+                                 -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double sp = (o & 1) ? c : s;
+    const double cp = (o & 1) ? s : c;
+    const int q = o >> 1;
+    sn = (q == 0) ? sp : (q == 1) ? cp : (q == 2) ? -sp : -cp;
+    cs = (q == 0) ? cp : (q == 1) ? -sp : (q == 2) ? -cp : sp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (particle, stage, slot, purpose), key = seed
+// ---------------------------------------------------------------------------------------------
+struct u32x4 { uint32_t x, y, z, w; };
+
+SMC_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
+{
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umulhi(a, b);
+#else
+    const uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
+
+SMC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c.x, h0, l0);
+        mulhilo(0xCD9E8D57u, c.z, h1, l1);
+        u32x4 n;
+        n.x = h1 ^ c.y ^ k0; n.y = l1; n.z = h0 ^ c.w ^ k1; n.w = l0;
+        c = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+enum : uint32_t { PURP_STEP = 1, PURP_NORMAL = 2, PURP_RESAMPLE = 3, PURP_BLOCKS = 4, PURP_INIT = 5 };
+
+SMC_HD u32x4 rng4(uint64_t seed, uint32_t particle, uint32_t stage, uint32_t slot, uint32_t purpose)
+{
+    u32x4 c; c.x = particle; c.y = stage; c.z = slot; c.w = purpose;
+    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+// 53-bit uniforms: [0,1) and (0,1]
+SMC_HD double u01(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1p-53; }
+SMC_HD double u01_open0(uint32_t hi, uint32_t lo) { return (double)(((((uint64_t)hi << 32) | lo) >> 11) + 1) * 0x1p-53; }
+
+// Box-Muller pair from one Philox block
+SMC_HD void normal_pair(u32x4 r, double& z0, double& z1)
+{
+    const double u1 = u01_open0(r.x, r.y);
+    const double u2 = u01(r.z, r.w);
+    const double rad = sqrt(-2.0 * det_log(u1));
+    double sn, cs;
+    det_sincos2pi(u2, sn, cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// Lower Cholesky, row by row, explicit fma order.  Returns 0 or 1 + failing row.
+SMC_HD int cholesky_lower(const double* A, int n, double* L)
+{
+    for (int i = 0; i < n * n; ++i) L[i] = 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i * n + j];
+            for (int k = 0; k < j; ++k) s = fma(-L[i * n + k], L[j * n + k], s);
+            if (i == j) {
+                if (!(s > 0.0)) return 1 + i;
+                L[i * n + i] = sqrt(s);
+            } else {
+                L[i * n + j] = s / L[j * n + j];
+            }
+        }
+    return 0;
+}
+
+// c <- c * (0.95 + 0.10 e^{16(a-t)} / (1 + e^{16(a-t)}))      (src/smc_main.jl:453-455)
+SMC_HD double update_step_size(double c, double accept, double target)
+{
+    const double e = det_exp(16.0 * (accept - target));
+    return c * (0.95 + 0.10 * e / (1.0 + e));
+}
+
+}  // namespace smc

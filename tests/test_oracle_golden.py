@@ -1,0 +1,254 @@
+"""Pin the CPU oracle against the reference's own known-answer vectors (tests/golden/*.npz,
+extracted from /root/reference/test/reference by tests/golden/make_golden.py).
+
+Reference tests mirrored: test/helpers.jl:15-53,101-127,133-175; test/mutation.jl:1-59;
+test/initialization.jl:26-129; test/smc.jl:13-87 (its stored w/W/ESS history).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from smc_jl_b200 import model as M
+
+
+def linear_test_model(data, X, old_data=None):
+    """test/modelsetup.jl:9-30: (alpha_i, beta_i, sigma_i) x 3, Normal(0,1e3)/Uniform(0,1e3)."""
+    ps = []
+    for i in (1, 2, 3):
+        ps.append(M.parameter("α%d" % i, 0.0, (-1e5, 1e5), (-1e5, 1e5), None, M.Normal(0, 1e3)))
+        ps.append(M.parameter("β%d" % i, 0.0, (-1e5, 1e5), (-1e5, 1e5), None, M.Normal(0, 1e3)))
+        ps.append(M.parameter("σ%d" % i, 1.0, (1e-5, 1e5), (1e-5, 1e5), None, M.Uniform(0, 1e3)))
+    lk = M.LinearEquationsLogLik(data, X)
+    old = M.LinearEquationsLogLik(old_data, X) if old_data is not None else None
+    return M.make_spec(ps, lk, old)
+
+
+def test_proposal_densities_golden(golden):
+    """test/helpers.jl:101-127 -> q0 = 4.714243032395692, q1 = 4.714241545508865."""
+    g = golden("proposal_densities.npz")
+    L = O.lib()
+    n = len(g["mu"])
+    Sig = np.ascontiguousarray(g["Sigma"])
+    Lo = np.zeros((n, n))
+    assert L.orc_cholesky(Sig, n, Lo) == 0
+    np.testing.assert_allclose(Lo, g["chol_lower"], rtol=1e-12, atol=1e-15)  # reference-stored LAPACK factor
+    c = float(g["c"])
+    Lc = np.ascontiguousarray(c * Lo)
+    sd = np.sqrt(np.diag(Sig)).copy()
+    logdet = 2.0 * np.sum(np.log(np.diag(Lc)))
+    q0, q1 = C.c_double(), C.c_double()
+    L.orc_proposal_densities(Lc, sd, np.ascontiguousarray(g["mu"]), n, logdet,
+                             np.ascontiguousarray(g["para_draw"]), np.ascontiguousarray(g["para_subset"]),
+                             float(g["alpha"]), C.byref(q0), C.byref(q1))
+    assert q0.value == pytest.approx(float(g["q0"]), rel=1e-13)
+    assert q1.value == pytest.approx(float(g["q1"]), rel=1e-13)
+
+
+def test_compute_ess_golden(golden):
+    """test/helpers.jl:133-175 -> 391.79648393931234."""
+    g = golden("compute_ess.npz")
+    n = len(g["loglh"])
+    ess = O.lib().orc_compute_ess(np.ascontiguousarray(g["loglh"]), np.ascontiguousarray(g["current_weights"]),
+                                  np.ascontiguousarray(g["old_loglh"]), n, float(g["phi_n"]), float(g["phi_n1"]),
+                                  np.zeros(n))
+    assert ess == pytest.approx(float(g["ess"]), rel=1e-13)
+
+
+def test_solve_adaptive_phi_golden(golden):
+    """test/helpers.jl:15-53 -> phi_n = 1.212927219006027e-05, j = 3, phi_prop = sched[2]."""
+    g = golden("solve_adaptive_phi.npz")
+    P = g["particles"]
+    N, cols = P.shape
+    d = cols - 5
+    j = C.c_int64(int(g["j"]))
+    phi_prop = C.c_double(float(g["phi_prop"]))
+    phi_n = C.c_double()
+    evals = C.c_int64()
+    i = int(g["i"])
+    ess_prev = float(g["cloud_ESS"][i - 2])  # cloud.ESS[i-1], 1-based
+    O.lib().orc_solve_adaptive_phi(O.cloud_f(P), N, d, np.ascontiguousarray(g["proposed_fixed_schedule"]),
+                                   len(g["proposed_fixed_schedule"]), C.byref(j), C.byref(phi_prop),
+                                   float(g["phi_n1"]), float(g["tempering_target"]), ess_prev,
+                                   int(g["resampled_last_period"]), C.byref(phi_n), C.byref(evals))
+    assert phi_n.value == pytest.approx(float(g["out_phi_n"]), rel=1e-12)
+    assert j.value == int(g["out_j"])
+    assert phi_prop.value == float(g["out_phi_prop"])
+    assert evals.value < 100
+
+
+def test_linear_model_rows_golden(golden):
+    """400 (theta -> loglh, logprior) rows produced by the reference's initial_draw! (test/initialization.jl)."""
+    g = golden("linear_model_rows.npz")
+    data, X, P = g["data"], g["X"], g["particles"]
+    spec = linear_test_model(data, X)
+    mod = O.Model(spec)
+    L = O.lib()
+    dflat = np.ascontiguousarray(data.T).ravel()   # column-major n_eq x T
+    xflat = np.ascontiguousarray(X.T).ravel()
+    for r in range(P.shape[0]):
+        th = np.ascontiguousarray(P[r, :9])
+        direct = L.orc_loglik_lineq_direct(th, dflat, xflat, 3, data.shape[1])
+        assert direct == pytest.approx(P[r, 9], rel=2e-14, abs=1e-12)
+        assert mod.loglik(th) == pytest.approx(P[r, 9], rel=1e-11)         # sufficient-statistic form
+        assert mod.logprior(th) == pytest.approx(P[r, 10], rel=1e-14, abs=1e-13)
+
+
+def test_initialize_likelihoods_golden(golden):
+    """initialize_likelihoods! (src/initialization.jl:153-186): old_loglh <- loglh, loglh recomputed, weights kept."""
+    g = golden("linear_model_rows.npz")
+    out = golden("init_likelihoods.npz")["particles"]
+    spec = linear_test_model(g["data"], g["X"])
+    mod = O.Model(spec)
+    P = g["particles"]
+    buf = O.cloud_f(P)
+    O.lib().orc_initialize_likelihoods(mod.h, buf, P.shape[0])
+    got = O.cloud_m(buf, P.shape[0], 9)
+    if out.shape == got.shape and np.array_equal(out[:, :9], P[:, :9]):
+        np.testing.assert_array_equal(got[:, 11], P[:, 9])
+        np.testing.assert_allclose(got[:, 9], out[:, 9], rtol=1e-11)
+        np.testing.assert_allclose(got[:, 11], out[:, 11], rtol=0, atol=0)
+        np.testing.assert_array_equal(got[:, 13], out[:, 13])
+
+
+def test_correction_history_golden(golden):
+    """W[:,n] = N (W[:,n-1] .* w[:,n]) / sum, ESS[n] = N^2 / sum W^2, resample iff ESS < N/2
+    for stored stages of the reference's full run (test/smc.jl:26-29)."""
+    g = golden("correction_history.npz")
+    N = int(g["n_parts"])
+    ESS = g["ESS"]
+    L = O.lib()
+    d = 1
+    for col, n in enumerate(g["stages"]):
+        W_prev, w_inc, W_new = g["W_prev"][:, col], g["w_inc"][:, col], g["W_new"][:, col]
+        cloud = np.zeros((N, d + 5))
+        cloud[:, d + 4] = W_prev
+        with np.errstate(divide="ignore"):
+            cloud[:, d] = np.log(w_inc)            # phi: 0 -> 1 so that inc = exp(loglh) = w_inc (to 1 ulp)
+        buf = O.cloud_f(cloud)
+        out = np.zeros(3)
+        inc = np.zeros(N)
+        st = L.orc_correct(buf, N, d, 0.0, 1.0, 0.0, 0.0, inc.ctypes.data_as(C.c_void_p), None, out)
+        assert st == 0
+        np.testing.assert_allclose(inc, w_inc, rtol=4e-16 * 800, atol=0)   # |log w| up to ~700 amplifies 1 ulp
+        assert out[1] == pytest.approx(ESS[n], rel=1e-11)
+        got_W = O.cloud_m(buf, N, d)[:, d + 4]
+        resampled = ESS[n] < 0.5 * N
+        if resampled:
+            assert np.all(W_new == 1.0)
+        else:
+            np.testing.assert_allclose(got_W, W_new, rtol=1e-11, atol=1e-300)
+    # resample decisions over the full run: 34 resamples (cloud.resamples)
+    assert int((ESS[1:] < 0.5 * N).sum()) == int(g["resamples"])
+    # the stored schedule is ((0:119)/119)^2.1
+    k = np.arange(120)
+    np.testing.assert_allclose(g["tempering_schedule"], (k / 119.0) ** 2.1, rtol=4e-16)
+
+
+def test_mutation_golden(golden):
+    """test/mutation.jl:1-59.  The stored case is degenerate (input loglh column is 0, so every
+    proposal loses): output == input except accept := 0.  Pins pass-through layout + accept."""
+    g = golden("mutation.npz")
+    lm = golden("linear_model_rows.npz")
+    spec = linear_test_model(lm["data"], lm["X"], old_data=g["old_data"])
+    mod = O.Model(spec)
+    L = O.lib()
+    P = g["particles_in"]
+    N = P.shape[0]
+    bf = (g["blocks_free"] - 1).astype(np.int32)
+    ba = (g["blocks_all"] - 1).astype(np.int32)
+    st = C.c_int()
+    pr = L.orc_proposal_create(9, 9, np.ascontiguousarray(g["mu"]), np.ascontiguousarray(g["Sigma"]), 1,
+                               np.array([9], np.int32), bf, ba, float(g["c"]), C.byref(st))
+    assert pr and st.value == 0
+    buf = O.cloud_f(P)
+    L.orc_mutate(mod.h, pr, buf, N, 0, float(g["phi_n"]), float(g["phi_n1"]), float(g["alpha"]), 1, 9, 1, 42, 2, 1)
+    L.orc_proposal_free(pr)
+    got = O.cloud_m(buf, N, 9)
+    want = g["particles_out"]
+    np.testing.assert_array_equal(got[:, :12], want[:, :12])
+    np.testing.assert_array_equal(got[:, 12], want[:, 12])       # accept column: all 0.0
+    np.testing.assert_array_equal(got[:, 13], want[:, 13])
+
+
+def test_as_priors_golden(golden):
+    """logprior column of the saved An-Schorfheide clouds pins Gamma / Normal / Uniform /
+    RootInverseGamma log-densities."""
+    g = golden("as_clouds.npz")
+    ps = []
+    for i in range(16):
+        kind = int(g["prior_kind"][i]); a, b = float(g["prior_p1"][i]), float(g["prior_p2"][i])
+        prior = [M.Normal, M.Uniform, M.Gamma, M.RootInverseGamma][kind](a, b)
+        ps.append(M.parameter(str(g["keys"][i]), float(g["value"][i]), (float(g["lo"][i]), float(g["hi"][i])),
+                              None, None, prior, fixed=bool(g["fixed"][i])))
+    mod = O.Model(M.make_spec(ps))
+    for name in ("cloud1000", "cloud600", "prior_draws"):
+        P = g[name]
+        for r in range(P.shape[0]):
+            assert mod.logprior(np.ascontiguousarray(P[r, :16])) == pytest.approx(P[r, 17], rel=1e-13, abs=2e-13)
+
+
+def test_detmath_vs_libm():
+    """The fixed-polynomial exp/log/sincos agree with libm to <= 1 ulp / 1e-15 abs."""
+    L = O.lib()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-745, 709, 20000), rng.normal(0, 3, 20000)])
+    mine = np.array([L.orc_exp(v) for v in x])
+    ref = np.exp(x)
+    assert np.max(np.abs(mine - ref) / np.spacing(ref)) <= 1.0
+    x = np.concatenate([rng.uniform(0, 2, 20000), 10.0 ** rng.uniform(-300, 300, 20000)])
+    mine = np.array([L.orc_log(v) for v in x])
+    ref = np.log(x)
+    assert np.max(np.abs(mine - ref) / np.spacing(np.abs(ref))) <= 1.0
+    assert L.orc_exp(-np.inf) == 0.0 and L.orc_exp(np.inf) == np.inf and np.isnan(L.orc_exp(np.nan))
+    assert L.orc_log(0.0) == -np.inf and np.isnan(L.orc_log(-1.0))
+    out = np.zeros(2)
+    for u in rng.uniform(0, 1, 20000):
+        L.orc_sincos2pi_v(u, out)
+        assert abs(out[0] - np.sin(2 * np.pi * u)) < 1e-15 and abs(out[1] - np.cos(2 * np.pi * u)) < 1e-15
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    L = O.lib()
+
+    def ph(c, k):
+        o = np.zeros(4, np.uint32)
+        L.orc_philox4x32_10(np.array(c, np.uint32), np.array(k, np.uint32), o)
+        return [int(v) for v in o]
+    assert ph([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_normals_are_standard():
+    L = O.lib()
+    out = np.zeros(2)
+    zs = []
+    for p in range(20000):
+        L.orc_normal_pair(7, p, 3, 0, out)
+        zs.extend(out)
+    z = np.array(zs)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    assert abs(np.mean(z ** 3)) < 0.06 and abs(np.mean(z ** 4) - 3) < 0.15
+
+
+def test_resample_structure(golden):
+    """Properties the reference's stored systematic indices have (test/resample.jl): non-decreasing,
+    1-based, in range; our resampler shares them, and offspring counts track N*w within 1."""
+    g = golden("resample_structural.npz")
+    sys_idx = g["sys"]
+    assert np.all(np.diff(sys_idx) >= 0) and sys_idx.min() >= 1 and sys_idx.max() <= 400
+    rng = np.random.default_rng(42)
+    w = rng.uniform(size=400); w /= w.sum()
+    idx = np.zeros(400, np.int64)
+    O.lib().orc_resample(w, 400, 0, 1, 2, 0.37, idx, None)
+    assert np.all(np.diff(idx) >= 0) and idx.min() >= 1 and idx.max() <= 400
+    counts = np.bincount(idx - 1, minlength=400)
+    assert np.all(np.abs(counts - 400 * w) < 1.0 + 1e-9)
+    # literal restatement of src/resample.jl:45-71 in numpy on numpy's cumsum: same indices except at ulp ties
+    cum = np.cumsum(w / w.sum())
+    ref = np.array([np.searchsorted(cum, (i + 0.37) / 400, side="right") + 1 for i in range(400)])
+    assert np.mean(ref == idx) > 0.99
