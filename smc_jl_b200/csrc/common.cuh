@@ -1,0 +1,130 @@
+// common.cuh -- internal declarations of libsmcb200 (context, constants of the canonical orders).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/smcb200.h"
+#include "detmath.cuh"
+
+namespace smc {
+
+// ---- canonical reduction orders (DESIGN.md "Numerical contract"; mirrored by the oracle) --------
+constexpr int W_LANES = 256, W_R = 4, W_TILE = W_LANES * W_R;      // weight-type sums
+constexpr int M_LANES = 32, M_R = 64, M_TILE = M_LANES * M_R;      // moment-type sums
+constexpr int LEAF = 64;                                           // cumsum leaf (sequential)
+constexpr int SCAN_THREADS = 128, SCAN_TILE = SCAN_THREADS * LEAF; // cumsum block tile
+
+constexpr int DMAX = 32;               // max n_para with a device mutation kernel
+constexpr int NBMAX = 8;               // max n_blocks
+constexpr int PACKMAX = DMAX * (DMAX + 1) / 2;
+constexpr int EQMAX = 8;
+
+// device scalar slots (ctx->scal)
+enum { SC_S = 0, SC_Q = 1, SC_S2 = 2, SC_SRES = 3, SC_ACC = 4, SC_COUNT = 16 };
+
+struct PhiState {           // adaptive-phi state machine, lives in device memory
+    double lo, hi, phi_prop, ess_bar, phi_cur, phi_n1, phi_n, g_last;
+    long long j;
+    int phase;              // 0 walk schedule, 1 bisect
+    int done;
+    int evals;
+    int n_phi;
+};
+
+struct PriorConst {
+    double lo[DMAX], hi[DMAX], p1[DMAX], p2[DMAX], cst[DMAX], a1[DMAX], a2[DMAX];
+    int32_t kind[DMAX], fixed[DMAX];
+};
+struct LikSlot {
+    double T[EQMAX], qscale[EQMAX], rss[EQMAX], cT[EQMAX], logs[EQMAX], inv_s2[EQMAX];
+    double bhat[2 * DMAX];
+    double U[PACKMAX];
+};
+struct MutConst {
+    double L[NBMAX][PACKMAX];   // c * L_b embedded in parameter order, packed lower: [i(i+1)/2 + j]
+    double csd[NBMAX][DMAX];    // c * sqrt(Sigma_ii)
+    double mu[DMAX];            // theta_bar
+    uint32_t mask[NBMAX];
+    int32_t bsize[NBMAX];
+    int32_t n_blocks, status;
+};
+struct BlockSpec {              // host-built, passed by value to the proposal-preparation kernel
+    int32_t n_blocks, d, n_free, pad;
+    int32_t bsize[NBMAX];
+    int8_t member[NBMAX][DMAX]; // ascending parameter indices of block b
+};
+struct LikDesc {                // host copy of a likelihood slot's shape
+    int kind = 0, neq = 0, k = 0, stride = 0, coef_off = 0, sig_off = -1;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // sharding
+    int rank = 0, world = 1;
+    void* nccl_comm = nullptr;
+    int64_t N_global = 0, N = 0, index0 = 0;
+    int d = 0;
+    // device buffers
+    double* cloud[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* tmp = nullptr;         // N
+    double* rmax = nullptr;        // N   running max of the cumsum
+    int64_t* idx = nullptr;        // N
+    double* partials = nullptr;    // tile partial sums, weight-type orders  [6][P_w]
+    double* mpartials = nullptr;   // tile partial sums, moment-type orders  [max(1+d, E)][P_m]
+    size_t partials_len = 0;
+    unsigned* counters = nullptr;  // last-block counters
+    double* scal = nullptr;        // SC_COUNT device scalars
+    double* h_scal = nullptr;      // pinned mirror
+    PhiState* phi_state = nullptr;
+    PhiState* h_phi_state = nullptr;
+    double* sched_dev = nullptr; int sched_cap = 0;
+    double* scan_blocktot = nullptr; double* scan_blockoff = nullptr; double* scan_levels = nullptr; double* scan_bmax = nullptr;
+    int64_t scan_nb_cap = 0;
+    double* msum = nullptr;        // [1 + d] Sw, sum w x_k
+    double* csum = nullptr;        // [d(d+1)/2] packed lower scatter sums
+    double* h_moments = nullptr;   // pinned
+    MutConst* mutc_dev = nullptr;  // staging copy in global memory
+    MutConst* mutc_host = nullptr; // pinned
+    int* status_dev = nullptr; int* h_status = nullptr;
+    // model
+    bool have_params = false;
+    PriorConst prior{};
+    LikDesc lik[2];
+    LikSlot lik_host[2]{};
+    int n_free = 0;
+    int free_idx[DMAX]{};
+    // bookkeeping
+    long long launches = 0;
+    float last_ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[8]{};
+    std::string err;
+};
+
+#define SMC_CUDA(ctx, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return SMCB200_ERR_CUDA;                                                               \
+        }                                                                                          \
+    } while (0)
+
+inline int64_t next_pow2(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return p; }
+inline int ilog2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; return k; }
+
+// column pointers of the struct-of-arrays cloud
+__host__ __device__ inline size_t col_off(int64_t N, int j) { return (size_t)j * (size_t)N; }
+
+// ---- mutation dispatch (mutate.cu) ---------------------------------------------------------------
+int mutate_upload_model(Ctx* ctx);                      // priors + likelihood slots -> __constant__
+int mutate_upload_proposal(Ctx* ctx, bool from_device); // MutConst -> __constant__
+bool mutate_supported(const Ctx* ctx, bool has_old);
+int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage);
+int evaluate_launch(Ctx* ctx, int mode);
+
+}  // namespace smc

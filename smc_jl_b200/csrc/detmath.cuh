@@ -147,7 +147,9 @@ SMC_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
 
 SMC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
 {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
     for (int r = 0; r < 10; ++r) {
         uint32_t h0, l0, h1, l1;
         mulhilo(0xD2511F53u, c.x, h0, l0);

@@ -1,0 +1,782 @@
+// engine.cu -- the C ABI of libsmcb200 (include/smcb200.h) and the host-side orchestration of one
+// SMC stage on one GPU shard.  Host code here only sequences kernels and moves scalars; all
+// per-particle arithmetic runs in the kernels of kernels.cuh / mutate.cu.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace smc;
+
+struct smcb200_ctx : public smc::Ctx {};
+
+namespace {
+
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+int fail(Ctx* c, int code, const char* msg)
+{
+    c->err = msg;
+    return code;
+}
+
+void free_cloud(Ctx* c)
+{
+    cudaFree(c->cloud[0]); cudaFree(c->cloud[1]); cudaFree(c->tmp); cudaFree(c->rmax); cudaFree(c->idx);
+    cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
+    cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
+    c->cloud[0] = c->cloud[1] = c->tmp = c->rmax = nullptr; c->idx = nullptr; c->partials = c->mpartials = nullptr;
+    c->scan_blocktot = c->scan_blockoff = c->scan_levels = c->scan_bmax = nullptr; c->msum = c->csum = nullptr;
+    c->N = c->N_global = 0;
+}
+
+// tile geometry of the canonical orders for this shard
+struct Tiles { int ntiles, P; };
+Tiles weight_tiles(int64_t n) { int nt = (int)((n + W_TILE - 1) / W_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+Tiles moment_tiles(int64_t n) { int nt = (int)((n + M_TILE - 1) / M_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+
+int sync(Ctx* c)
+{
+    SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SMCB200_OK;
+}
+
+// ---- correction ---------------------------------------------------------------------------------
+int launch_correct(Ctx* c, double phi_n1, double phi_n, double pw, double lpod, double* inc_dev, double* normw_dev)
+{
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    CorrArgs a;
+    a.phi_n1 = phi_n1; a.phi_n = phi_n; a.pw = pw; a.lpod = lpod;
+    a.mode = (pw == 0.0) ? 0 : (pw == 1.0 ? 1 : 2);
+    a.log_1m_pw = (a.mode == 2) ? det_log(1.0 - pw) : 0.0;
+    const Tiles t = weight_tiles(c->N);
+    double* w = cl + col_off(c->N, d + 4);
+    k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), w, w, inc_dev, c->N, a,
+                                                 nullptr, c->partials, t.ntiles, t.P, c->counters, c->scal);
+    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(w, normw_dev, c->N, (double)c->N_global, 1, nullptr, nullptr,
+                                                 c->partials, t.ntiles, t.P, c->counters, c->scal);
+    c->launches += 2;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+// ---- resampling on explicit buffers -----------------------------------------------------------------
+struct ScanGeom { int64_t P; int B, nb; };
+ScanGeom scan_geom(int64_t n)
+{
+    ScanGeom g;
+    g.P = next_pow2(n < LEAF ? LEAF : n);
+    g.B = (g.P < SCAN_TILE) ? (int)g.P : SCAN_TILE;
+    g.nb = (int)(g.P / g.B);
+    return g;
+}
+constexpr size_t SCAN_SMEM = (size_t)(SCAN_THREADS * 65 + 2 * SCAN_THREADS + SCAN_THREADS) * sizeof(double);
+
+int ensure_scan_buffers(Ctx* c, int nb)
+{
+    if (nb <= c->scan_nb_cap) return SMCB200_OK;
+    cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels); cudaFree(c->scan_bmax);
+    SMC_CUDA(c, cudaMalloc(&c->scan_blocktot, sizeof(double) * nb));
+    SMC_CUDA(c, cudaMalloc(&c->scan_blockoff, sizeof(double) * nb));
+    SMC_CUDA(c, cudaMalloc(&c->scan_levels, sizeof(double) * 2 * nb));
+    SMC_CUDA(c, cudaMalloc(&c->scan_bmax, sizeof(double) * nb));
+    c->scan_nb_cap = nb;
+    return SMCB200_OK;
+}
+
+// src: n weights on the device (div_n: use src/n_parts, the `normalized_weights/n_parts` of smc_main.jl:438);
+// rmax/craw/idx: device outputs.  `sres` = device slot receiving sum(weights) ("weights ./ sum(weights)").
+int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int method, uint64_t seed, uint32_t stage,
+                            double u_override, double* rmax, double* craw, int64_t* idx, double* partials,
+                            unsigned* counter, double* sres)
+{
+    if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
+        return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
+    const ScanGeom g = scan_geom(n);
+    if (g.nb > (1 << 15)) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_parts too large for the device scan (max 2^28)");
+    int st = ensure_scan_buffers(c, g.nb);
+    if (st) return st;
+    const Tiles t = weight_tiles(n);
+    const double nd = (double)n;
+    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, n, nd, div_n, partials, t.ntiles, t.P, counter, sres);
+    k_scan<false><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, c->scan_blocktot, nullptr,
+                                                              nullptr, nullptr, nullptr);
+    k_scan_upper<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scan_blockoff);
+    k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
+                                                             craw, c->scan_bmax);
+    k_prefix_max<<<1, 32, 0, c->stream>>>(c->scan_bmax, g.nb);
+    double u = u_override;
+    if (!(u >= 0.0)) {
+        const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
+        u = u01(r.x, r.y);
+    }
+    k_search<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(rmax, c->scan_bmax, g.nb, g.B, n, n, 0, method, seed, stage,
+                                                                 u, nd, idx);
+    c->launches += 6;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override)
+{
+    if (c->world > 1) return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU resampling is not available in this build");
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    const Tiles t = weight_tiles(c->N);
+    int st = launch_resample_indices(c, cl + col_off(c->N, d + 4), 1, c->N, method, seed, stage, u_override, c->rmax, nullptr,
+                                     c->idx, c->partials + (size_t)3 * t.P, c->counters + 2, c->scal + SC_SRES);
+    if (st) return st;
+    k_gather<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(cl, c->cloud[c->cur ^ 1], c->idx, c->N, d + 4, d + 4);
+    c->launches += 1;
+    SMC_CUDA(c, cudaGetLastError());
+    c->cur ^= 1;
+    return SMCB200_OK;
+}
+
+// ---- moments ------------------------------------------------------------------------------------------
+template <int D>
+void launch_m2(Ctx* c, const double* cl, double* partials, const Tiles& t)
+{
+    constexpr int E = D * (D + 1) / 2;
+    constexpr int SLABS = (E + 55) / 56 > 8 ? 8 : (E + 55) / 56;
+    k_moments2<D, SLABS><<<t.ntiles, 32 * SLABS, 0, c->stream>>>(cl, c->N, c->msum, partials, t.P);
+}
+
+int launch_moments(Ctx* c)
+{
+    const int d = c->d;
+    const double* cl = c->cloud[c->cur];
+    const Tiles t = moment_tiles(c->N);
+    const int E = d * (d + 1) / 2;
+    double* part = c->mpartials;  // [max(1+d, E)][P] -- sized at cloud creation
+    k_moments1<<<t.ntiles, 32, 0, c->stream>>>(cl, c->N, d, part, t.P);
+    k_tree_finalize<<<1 + d, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->msum);
+    switch (d) {
+    case 2: launch_m2<2>(c, cl, part, t); break;
+    case 9: launch_m2<9>(c, cl, part, t); break;
+    case 16: launch_m2<16>(c, cl, part, t); break;
+    case 20: launch_m2<20>(c, cl, part, t); break;
+    default: k_moments2_generic<<<t.ntiles, 32, 0, c->stream>>>(cl, c->N, d, c->msum, part, t.P); break;
+    }
+    k_tree_finalize<<<E, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->csum);
+    c->launches += 4;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+// ---- blocks -------------------------------------------------------------------------------------------
+// generate_free_blocks (src/helpers.jl:215-231): Fisher-Yates on the Philox stream, then cld-sized blocks
+void generate_blocks(int n_free, int n_blocks, uint64_t seed, uint32_t stage, int* perm, int* sizes)
+{
+    for (int i = 0; i < n_free; ++i) perm[i] = i;
+    for (int i = n_free - 1; i >= 1; --i) {
+        const u32x4 r = rng4(seed, (uint32_t)i, stage, 0u, PURP_BLOCKS);
+        const double u = u01(r.x, r.y);
+        const int j = (int)(u * (double)(i + 1));
+        const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+    const int sub = (n_free + n_blocks - 1) / n_blocks;
+    const int last = n_free - sub * (n_blocks - 1);
+    for (int b = 0; b < n_blocks; ++b) sizes[b] = (b < n_blocks - 1) ? sub : last;
+}
+
+int make_blockspec(Ctx* c, int n_blocks, const int32_t* sizes, const int32_t* blocks_all, BlockSpec* bs)
+{
+    if (n_blocks < 1 || n_blocks > NBMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_blocks must be in 1..8");
+    std::memset(bs, 0, sizeof(*bs));
+    bs->n_blocks = n_blocks; bs->d = c->d; bs->n_free = c->n_free;
+    int pos = 0, total = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const int n = sizes[b];
+        if (n < 1 || n > DMAX) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad block size");
+        bs->bsize[b] = n;
+        int tmp[DMAX];
+        for (int i = 0; i < n; ++i) {
+            const int a = blocks_all[pos + i];
+            if (a < 0 || a >= c->d || c->prior.fixed[a]) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "block index is not a free parameter");
+            tmp[i] = a;
+        }
+        for (int i = 1; i < n; ++i) {   // ascending parameter order inside a block
+            const int x = tmp[i]; int j = i - 1;
+            while (j >= 0 && tmp[j] > x) { tmp[j + 1] = tmp[j]; --j; }
+            tmp[j + 1] = x;
+        }
+        for (int i = 0; i < n; ++i) bs->member[b][i] = (int8_t)tmp[i];
+        pos += n; total += n;
+    }
+    if (total != c->n_free) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "blocks do not partition the free parameters");
+    return SMCB200_OK;
+}
+
+int check_ready(Ctx* c, bool need_lik)
+{
+    if (!c->cloud[0]) return fail(c, SMCB200_ERR_NOT_READY, "no cloud: call smcb200_cloud_create first");
+    if (need_lik) {
+        if (!c->have_params) return fail(c, SMCB200_ERR_NOT_READY, "no parameters: call smcb200_set_parameters first");
+        if (c->lik[0].kind == SMCB200_LIK_NONE) return fail(c, SMCB200_ERR_NOT_READY, "no likelihood: call smcb200_set_likelihood first");
+    }
+    return SMCB200_OK;
+}
+
+int mean_accept(Ctx* c)
+{
+    const Tiles t = weight_tiles(c->N);
+    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(c->cloud[c->cur] + col_off(c->N, c->d + 3), c->N, 1.0, 0,
+                                              c->partials + (size_t)4 * t.P, t.ntiles, t.P, c->counters + 3, c->scal + SC_ACC);
+    c->launches += 1;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int32_t smcb200_abi_version(void) { return SMCB200_ABI_VERSION; }
+
+const char* smcb200_status_string(int32_t s)
+{
+    switch (s) {
+    case SMCB200_OK: return "ok";
+    case SMCB200_ERR_NAN_ESS: return "No particles have non-zero weight (ESS is NaN)";
+    case SMCB200_ERR_BAD_RESAMPLER: return "Invalid resampler in SMC. Options are :systematic, :multinomial";
+    case SMCB200_ERR_BAD_ARGUMENT: return "bad argument";
+    case SMCB200_ERR_NOT_POSDEF: return "proposal covariance is not positive definite";
+    case SMCB200_ERR_CUDA: return "CUDA error";
+    case SMCB200_ERR_NCCL: return "NCCL error";
+    case SMCB200_ERR_UNSUPPORTED: return "unsupported likelihood / prior / dimension (no device kernel)";
+    case SMCB200_ERR_NOT_READY: return "call order: cloud / parameters / likelihood not set";
+    }
+    return "unknown status";
+}
+
+int32_t smcb200_create(smcb200_ctx** out, int32_t device)
+{
+    if (!out) return SMCB200_ERR_BAD_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SMCB200_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return SMCB200_ERR_CUDA;
+    smcb200_ctx* c = new (std::nothrow) smcb200_ctx();
+    if (!c) return SMCB200_ERR_BAD_ARGUMENT;
+    c->device = device;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->counters, sizeof(unsigned) * 16) == cudaSuccess;
+    ok = ok && cudaMemset(c->counters, 0, sizeof(unsigned) * 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->scal, sizeof(double) * SC_COUNT) == cudaSuccess;
+    ok = ok && cudaMemset(c->scal, 0, sizeof(double) * SC_COUNT) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * SC_COUNT) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->phi_state, sizeof(PhiState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_phi_state, sizeof(PhiState)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->mutc_dev, sizeof(MutConst) + sizeof(double) * (DMAX + 3 * DMAX * DMAX)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->mutc_host, sizeof(MutConst)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->status_dev, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->status_dev, 0, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_status, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_moments, sizeof(double) * (1 + DMAX + PACKMAX)) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
+    if (!ok) { smcb200_destroy(c); return SMCB200_ERR_CUDA; }
+    std::memset(c->mutc_host, 0, sizeof(MutConst));
+    *out = c;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_destroy(smcb200_ctx* c)
+{
+    if (!c) return SMCB200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_cloud(c);
+    cudaFree(c->counters); cudaFree(c->scal); cudaFreeHost(c->h_scal); cudaFree(c->phi_state); cudaFreeHost(c->h_phi_state);
+    cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
+    cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
+    for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SMCB200_OK;
+}
+
+const char* smcb200_last_error(const smcb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int32_t smcb200_comm_unique_id(void* id) { (void)id; return SMCB200_ERR_UNSUPPORTED; }
+int32_t smcb200_comm_init(smcb200_ctx* c, int32_t rank, int32_t world, const void* id)
+{
+    (void)id;
+    if (!c) return SMCB200_ERR_BAD_ARGUMENT;
+    if (world == 1 && rank == 0) return SMCB200_OK;
+    return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU communicator is not available in this build");
+}
+
+// ---- cloud --------------------------------------------------------------------------------------------
+int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
+{
+    if (!c || n_parts < 1 || n_para < 1) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_parts, n_para must be positive") : SMCB200_ERR_BAD_ARGUMENT;
+    if (n_para > DMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_para > 32 has no device kernels");
+    if (n_parts > ((int64_t)1 << 28)) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_parts > 2^28");
+    cudaSetDevice(c->device);
+    free_cloud(c);
+    c->N_global = n_parts; c->d = n_para;
+    // contiguous shard of the zero-padded power-of-two index space (keeps every canonical tree shard-aligned)
+    const int64_t P2 = next_pow2(n_parts);
+    const int64_t per = P2 / c->world;
+    int64_t first = per * c->rank, last = first + per;
+    if (first > n_parts) first = n_parts;
+    if (last > n_parts) last = n_parts;
+    c->index0 = first; c->N = last - first;
+    if (c->N < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "empty shard: fewer particles than ranks");
+    const size_t cols = (size_t)n_para + 5;
+    SMC_CUDA(c, cudaMalloc(&c->cloud[0], sizeof(double) * cols * c->N));
+    SMC_CUDA(c, cudaMalloc(&c->cloud[1], sizeof(double) * cols * c->N));
+    SMC_CUDA(c, cudaMalloc(&c->tmp, sizeof(double) * c->N));
+    SMC_CUDA(c, cudaMalloc(&c->rmax, sizeof(double) * c->N));
+    SMC_CUDA(c, cudaMalloc(&c->idx, sizeof(int64_t) * c->N));
+    const Tiles tw = weight_tiles(c->N), tm = moment_tiles(c->N);
+    const int E = n_para * (n_para + 1) / 2;
+    const size_t len = (size_t)6 * tw.P;
+    const size_t lm = (size_t)((E > n_para + 1) ? E : n_para + 1) * tm.P;
+    c->partials_len = len;
+    SMC_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * len));
+    SMC_CUDA(c, cudaMemset(c->partials, 0, sizeof(double) * len));
+    SMC_CUDA(c, cudaMalloc(&c->mpartials, sizeof(double) * lm));
+    SMC_CUDA(c, cudaMemset(c->mpartials, 0, sizeof(double) * lm));
+    SMC_CUDA(c, cudaMalloc(&c->msum, sizeof(double) * (1 + DMAX)));
+    SMC_CUDA(c, cudaMalloc(&c->csum, sizeof(double) * PACKMAX));
+    SMC_CUDA(c, cudaMemset(c->cloud[0], 0, sizeof(double) * cols * c->N));
+    c->cur = 0;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_cloud_shard(const smcb200_ctx* c, int64_t* first, int64_t* count)
+{
+    if (!c || !c->cloud[0]) return SMCB200_ERR_NOT_READY;
+    if (first) *first = c->index0;
+    if (count) *count = c->N;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_cloud_upload(smcb200_ctx* c, const double* p, int64_t ld, int64_t row0)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (!p || ld < row0 + c->N) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "update_cloud!: host matrix is too small");
+    cudaSetDevice(c->device);
+    SMC_CUDA(c, cudaMemcpy2DAsync(c->cloud[c->cur], sizeof(double) * c->N, p + row0, sizeof(double) * ld, sizeof(double) * c->N,
+                                  (size_t)c->d + 5, cudaMemcpyHostToDevice, c->stream));
+    return sync(c);
+}
+
+int32_t smcb200_cloud_download(smcb200_ctx* c, double* p, int64_t ld, int64_t row0)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (!p || ld < row0 + c->N) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "host matrix is too small");
+    cudaSetDevice(c->device);
+    SMC_CUDA(c, cudaMemcpy2DAsync(p + row0, sizeof(double) * ld, c->cloud[c->cur], sizeof(double) * c->N, sizeof(double) * c->N,
+                                  (size_t)c->d + 5, cudaMemcpyDeviceToHost, c->stream));
+    return sync(c);
+}
+
+int32_t smcb200_cloud_read_column(smcb200_ctx* c, int32_t col, double* out)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (col < 0 || col >= c->d + 5 || !out) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad column");
+    SMC_CUDA(c, cudaMemcpyAsync(out, c->cloud[c->cur] + col_off(c->N, col), sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    return sync(c);
+}
+
+int32_t smcb200_cloud_write_column(smcb200_ctx* c, int32_t col, const double* in)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (col < 0 || col >= c->d + 5 || !in) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad column");
+    SMC_CUDA(c, cudaMemcpyAsync(c->cloud[c->cur] + col_off(c->N, col), in, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+    return sync(c);
+}
+
+// ---- model --------------------------------------------------------------------------------------------
+int32_t smcb200_set_parameters(smcb200_ctx* c, int32_t d, const int32_t* fixed, const double* lo, const double* hi,
+                               const int32_t* kind, const double* p1, const double* p2)
+{
+    if (!c) return SMCB200_ERR_BAD_ARGUMENT;
+    if (d < 1 || d > DMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_para must be in 1..32");
+    if (c->cloud[0] && d != c->d) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_para does not match the cloud");
+    PriorConst& P = c->prior;
+    std::memset(&P, 0, sizeof(P));
+    c->n_free = 0;
+    for (int k = 0; k < DMAX; ++k) P.fixed[k] = 1;
+    for (int k = 0; k < d; ++k) {
+        P.fixed[k] = fixed[k] ? 1 : 0;
+        P.lo[k] = lo[k]; P.hi[k] = hi[k]; P.kind[k] = kind[k]; P.p1[k] = p1[k]; P.p2[k] = p2[k];
+        if (!P.fixed[k]) c->free_idx[c->n_free++] = k;
+        const double a = p1[k], b = p2[k];
+        if (P.fixed[k]) continue;
+        // per-parameter constants with the host libm (the oracle does the same with the same glibc)
+        switch (kind[k]) {
+        case SMCB200_PRIOR_NORMAL: P.cst[k] = -std::log(b) - HALF_LOG_2PI; P.a1[k] = 1.0 / b; break;
+        case SMCB200_PRIOR_UNIFORM: P.cst[k] = -std::log(b - a); break;
+        case SMCB200_PRIOR_GAMMA: P.cst[k] = -std::lgamma(a) - a * std::log(b); P.a1[k] = a - 1.0; P.a2[k] = 1.0 / b; break;
+        case SMCB200_PRIOR_ROOT_INV_GAMMA:
+            P.cst[k] = std::log(2.0) - std::lgamma(0.5 * a) + 0.5 * a * std::log(0.5 * a * b * b);
+            P.a1[k] = 0.5 * (a + 1.0); P.a2[k] = 0.5 * a * b * b; break;
+        case SMCB200_PRIOR_BETA: P.cst[k] = std::lgamma(a + b) - std::lgamma(a) - std::lgamma(b); P.a1[k] = a - 1.0; P.a2[k] = b - 1.0; break;
+        case SMCB200_PRIOR_INV_GAMMA: P.cst[k] = a * std::log(b) - std::lgamma(a); P.a1[k] = a + 1.0; P.a2[k] = b; break;
+        default: return fail(c, SMCB200_ERR_UNSUPPORTED, "unknown prior family");
+        }
+    }
+    if (c->n_free == 0) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "All model parameters are fixed!");   // smc_main.jl:237
+    if (!c->cloud[0]) c->d = d;
+    c->have_params = true;
+    cudaSetDevice(c->device);
+    return mutate_upload_model(c);
+}
+
+int32_t smcb200_set_likelihood(smcb200_ctx* c, int32_t slot, int32_t kind, const int32_t* ip, int32_t n_ip, const double* dp,
+                               int64_t n_dp)
+{
+    if (!c || slot < 0 || slot > 1) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "slot must be 0 or 1") : SMCB200_ERR_BAD_ARGUMENT;
+    if (kind != SMCB200_LIK_GAUSSREG) return fail(c, SMCB200_ERR_UNSUPPORTED, "likelihood family has no device functor");
+    if (n_ip < 5 || !ip || !dp) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "GAUSSREG needs 5 iparams");
+    LikDesc L; L.kind = kind; L.neq = ip[0]; L.k = ip[1]; L.stride = ip[2]; L.coef_off = ip[3]; L.sig_off = ip[4];
+    const int k = L.k, kp = k * (k + 1) / 2;
+    if (L.neq < 1 || L.neq > EQMAX || k < 1 || k > DMAX || L.neq * k > 2 * DMAX || L.neq * kp > PACKMAX)
+        return fail(c, SMCB200_ERR_UNSUPPORTED, "GAUSSREG shape out of range");
+    const int64_t per = 4 + k + (int64_t)k * k;
+    if (n_dp != per * L.neq) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "GAUSSREG dparams length mismatch");
+    LikSlot& S = c->lik_host[slot];
+    std::memset(&S, 0, sizeof(S));
+    for (int e = 0; e < L.neq; ++e) {
+        const double* p = dp + per * e;
+        S.T[e] = p[0]; S.qscale[e] = p[1]; S.rss[e] = p[2];
+        S.cT[e] = -p[0] * HALF_LOG_2PI;
+        if (L.sig_off < 0) { S.logs[e] = std::log(p[3]); S.inv_s2[e] = 1.0 / (p[3] * p[3]); }
+        for (int j = 0; j < k; ++j) S.bhat[e * k + j] = p[4 + j];
+        const double* U = p + 4 + k;
+        for (int i = 0; i < k; ++i)
+            for (int j = i; j < k; ++j) S.U[e * kp + i * k - (i * (i - 1)) / 2 + (j - i)] = U[i * k + j];
+    }
+    c->lik[slot] = L;
+    cudaSetDevice(c->device);
+    return mutate_upload_model(c);
+}
+
+int32_t smcb200_evaluate(smcb200_ctx* c, int32_t mode)
+{
+    int st = check_ready(c, true); if (st) return st;
+    cudaSetDevice(c->device);
+    st = evaluate_launch(c, mode); if (st) return st;
+    return sync(c);
+}
+
+int32_t smcb200_initial_draw(smcb200_ctx* c, const double* fixed_values, uint64_t seed, int32_t max_tries)
+{
+    (void)fixed_values; (void)seed; (void)max_tries;
+    return fail(c, SMCB200_ERR_UNSUPPORTED, "initial_draw! on the device is not available in this build");
+}
+
+// ---- stage operations -----------------------------------------------------------------------------------
+int32_t smcb200_correct(smcb200_ctx* c, double phi_n1, double phi_n, double pw, double lpod, double* inc_out, double* normw_out,
+                        double out[3])
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (!(pw >= 0.0 && pw <= 1.0))
+        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
+    cudaSetDevice(c->device);
+    double* inc_dev = inc_out ? c->tmp : nullptr;
+    double* nw_dev = normw_out ? c->rmax : nullptr;
+    SMC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    st = launch_correct(c, phi_n1, phi_n, pw, lpod, inc_dev, nw_dev); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, inc_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, nw_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+    const double n = (double)c->N_global;
+    const double ess = (n * n) / c->h_scal[SC_Q];
+    if (out) { out[0] = c->h_scal[SC_S]; out[1] = ess; out[2] = c->h_scal[SC_S2]; }
+    if (ess != ess) return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight.");
+    return SMCB200_OK;
+}
+
+int32_t smcb200_ess_at(smcb200_ctx* c, const double* phi, int32_t K, double phi_n1, double* ess_out)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (K < 0 || (K > 0 && (!phi || !ess_out))) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad phi vector");
+    cudaSetDevice(c->device);
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    const Tiles t = weight_tiles(c->N);
+    const double n = (double)c->N_global;
+    for (int k = 0; k < K; ++k) {
+        CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = phi[k]; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
+        k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
+                                                     c->tmp, nullptr, c->N, a, nullptr, c->partials, t.ntiles, t.P, c->counters, c->scal);
+        k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, nullptr, nullptr, c->partials, t.ntiles, t.P,
+                                                     c->counters, c->scal);
+        c->launches += 2;
+        SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+        st = sync(c); if (st) return st;
+        ess_out[k] = (n * n) / c->h_scal[SC_Q];
+    }
+    return SMCB200_OK;
+}
+
+int32_t smcb200_solve_adaptive_phi(smcb200_ctx* c, const double* sched, int32_t n_phi, int64_t* j_io, double* phi_prop_io,
+                                   double phi_n1, double tempering_target, double ess_prev, int32_t resampled_last, double* phi_n_out)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (!sched || n_phi < 1 || !j_io || !phi_prop_io || !phi_n_out) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
+    cudaSetDevice(c->device);
+    if (c->sched_cap < n_phi) {
+        cudaFree(c->sched_dev);
+        SMC_CUDA(c, cudaMalloc(&c->sched_dev, sizeof(double) * n_phi));
+        c->sched_cap = n_phi;
+    }
+    SMC_CUDA(c, cudaMemcpyAsync(c->sched_dev, sched, sizeof(double) * n_phi, cudaMemcpyHostToDevice, c->stream));
+    PhiState* h = c->h_phi_state;
+    std::memset(h, 0, sizeof(*h));
+    const double n = (double)c->N_global;
+    h->ess_bar = resampled_last ? tempering_target * n : tempering_target * ess_prev;   // helpers.jl:14-20
+    h->phi_prop = *phi_prop_io; h->phi_cur = *phi_prop_io; h->phi_n1 = phi_n1; h->j = *j_io; h->n_phi = n_phi;
+    SMC_CUDA(c, cudaMemcpyAsync(c->phi_state, h, sizeof(PhiState), cudaMemcpyHostToDevice, c->stream));
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    const Tiles t = weight_tiles(c->N);
+    CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = 0.0; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
+    // every evaluation of g() = two kernels; the bracket walk and the bisection advance on the device, the host
+    // only polls the `done` flag between batches
+    for (int round = 0; round < 64; ++round) {
+        for (int e = 0; e < 72; ++e) {
+            k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
+                                                         c->tmp, nullptr, c->N, a, c->phi_state, c->partials, t.ntiles, t.P,
+                                                         c->counters, c->scal);
+            k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, c->phi_state, c->sched_dev, c->partials,
+                                                         t.ntiles, t.P, c->counters, c->scal);
+        }
+        c->launches += 144;
+        SMC_CUDA(c, cudaGetLastError());
+        SMC_CUDA(c, cudaMemcpyAsync(h, c->phi_state, sizeof(PhiState), cudaMemcpyDeviceToHost, c->stream));
+        st = sync(c); if (st) return st;
+        if (h->done) break;
+    }
+    if (!h->done) return fail(c, SMCB200_ERR_NAN_ESS, "solve_adaptive_phi did not converge (NaN ESS?)");
+    *j_io = h->j; *phi_prop_io = h->phi_prop; *phi_n_out = h->phi_n;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_resample(smcb200_ctx* c, int32_t method, uint64_t seed, uint32_t stage, double u_override, int64_t* idx_out)
+{
+    int st = check_ready(c, false); if (st) return st;
+    cudaSetDevice(c->device);
+    SMC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    st = launch_resample_cloud(c, method, seed, stage, u_override); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    if (idx_out) SMC_CUDA(c, cudaMemcpyAsync(idx_out, c->idx, sizeof(int64_t) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    cudaEventElapsedTime(&c->last_ms[1], c->ev[2], c->ev[3]);
+    return SMCB200_OK;
+}
+
+int32_t smcb200_resample_weights(smcb200_ctx* c, const double* weights, int64_t n, int32_t method, uint64_t seed, uint32_t stage,
+                                 double u_override, int64_t* idx_out, double* cum_out)
+{
+    if (!c || !weights || n < 1 || !idx_out) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument") : SMCB200_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    double *w = nullptr, *r = nullptr, *cr = nullptr, *part = nullptr;
+    int64_t* idx = nullptr;
+    const Tiles t = weight_tiles(n);
+    SMC_CUDA(c, cudaMalloc(&w, sizeof(double) * n));
+    SMC_CUDA(c, cudaMalloc(&r, sizeof(double) * n));
+    SMC_CUDA(c, cudaMalloc(&cr, sizeof(double) * n));
+    SMC_CUDA(c, cudaMalloc(&idx, sizeof(int64_t) * n));
+    SMC_CUDA(c, cudaMalloc(&part, sizeof(double) * t.P));
+    SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * t.P, c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    int st = launch_resample_indices(c, w, 0, n, method, seed, stage, u_override, r, cr, idx, part, c->counters + 4, c->scal + SC_SRES);
+    if (st == SMCB200_OK) {
+        cudaMemcpyAsync(idx_out, idx, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c->stream);
+        if (cum_out) cudaMemcpyAsync(cum_out, cr, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+        st = sync(c);
+    }
+    cudaFree(w); cudaFree(r); cudaFree(cr); cudaFree(idx); cudaFree(part);
+    return st;
+}
+
+int32_t smcb200_moments(smcb200_ctx* c, double* mean, double* cov)
+{
+    int st = check_ready(c, false); if (st) return st;
+    cudaSetDevice(c->device);
+    const int d = c->d, E = d * (d + 1) / 2;
+    SMC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    st = launch_moments(c); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_moments, c->msum, sizeof(double) * (1 + d), cudaMemcpyDeviceToHost, c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_moments + 1 + DMAX, c->csum, sizeof(double) * E, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    cudaEventElapsedTime(&c->last_ms[2], c->ev[4], c->ev[5]);
+    const double sw = c->h_moments[0];
+    if (mean) for (int k = 0; k < d; ++k) mean[k] = c->h_moments[1 + k] / sw;
+    if (cov)
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b <= a; ++b) {
+                const double v = c->h_moments[1 + DMAX + a * (a + 1) / 2 + b] / sw;
+                cov[a * d + b] = v; cov[b * d + a] = v;
+            }
+    return SMCB200_OK;
+}
+
+int32_t smcb200_mutate(smcb200_ctx* c, const double* mean_fr, const double* cov_fr, int32_t n_free, int32_t n_blocks,
+                       const int32_t* block_sizes, const int32_t* blocks_free, const int32_t* blocks_all, double phi_n,
+                       double phi_n1, double cc, double alpha, int32_t n_mh_steps, int32_t has_old, uint64_t seed, uint32_t stage,
+                       double* mean_accept_out)
+{
+    (void)phi_n1; (void)blocks_free;
+    int st = check_ready(c, true); if (st) return st;
+    if (!mean_fr || !cov_fr || !block_sizes || !blocks_all) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
+    if (n_free != c->n_free) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_free does not match the ParameterVector");
+    if (alpha != 1.0) return fail(c, SMCB200_ERR_UNSUPPORTED, "mixture proposal (alpha < 1) has no device kernel yet");
+    if (n_mh_steps < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_mh_steps must be >= 1");
+    cudaSetDevice(c->device);
+    BlockSpec bs;
+    st = make_blockspec(c, n_blocks, block_sizes, blocks_all, &bs); if (st) return st;
+    // scatter the free-parameter moments back to full parameter order (fixed rows/cols are never read)
+    const int d = c->d;
+    std::vector<double> mean(d, 0.0), cov((size_t)d * d, 0.0), work(2 * DMAX * DMAX);
+    for (int a = 0; a < n_free; ++a) {
+        mean[c->free_idx[a]] = mean_fr[a];
+        for (int b = 0; b < n_free; ++b) cov[(size_t)c->free_idx[a] * d + c->free_idx[b]] = cov_fr[(size_t)a * n_free + b];
+    }
+    st = build_mutconst(mean.data(), cov.data(), d, bs, cc, c->mutc_host, work.data());
+    if (st) return fail(c, SMCB200_ERR_NOT_POSDEF, "proposal covariance is not positive definite");
+    st = mutate_upload_proposal(c, false); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    st = mutate_launch(c, phi_n, n_mh_steps, has_old != 0, seed, stage); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+    st = mean_accept(c); if (st) return st;
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    cudaEventElapsedTime(&c->last_ms[3], c->ev[6], c->ev[7]);
+    if (mean_accept_out) *mean_accept_out = c->h_scal[SC_ACC] / (double)c->N_global;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_stage_state* state, const double* sched, int32_t n_phi,
+                      double* inc_out, double* normw_out, smcb200_stage_result* res)
+{
+    int st = check_ready(c, true); if (st) return st;
+    if (!cfg || !state || !res) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
+    if (cfg->alpha != 1.0) return fail(c, SMCB200_ERR_UNSUPPORTED, "mixture proposal (alpha < 1) has no device kernel yet");
+    if (!(cfg->prior_weight >= 0.0 && cfg->prior_weight <= 1.0))
+        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
+    cudaSetDevice(c->device);
+    std::memset(res, 0, sizeof(*res));
+    double phi_n = cfg->phi_n;
+    if (cfg->adaptive) {
+        st = smcb200_solve_adaptive_phi(c, sched, n_phi, &state->j, &state->phi_prop, cfg->phi_n1, cfg->tempering_target,
+                                        state->ess_prev, state->resampled_last_period, &phi_n);
+        if (st) return st;
+        state->resampled_last_period = 0;
+    }
+    res->phi_n = phi_n;
+    const double n = (double)c->N_global;
+    // ---- correction -------------------------------------------------------------------------------------
+    double* inc_dev = inc_out ? c->tmp : nullptr;
+    double* nw_dev = normw_out ? c->rmax : nullptr;
+    SMC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    st = launch_correct(c, cfg->phi_n1, phi_n, cfg->prior_weight, cfg->log_prob_old_data, inc_dev, nw_dev); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, inc_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, nw_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    res->sum_weights = c->h_scal[SC_S];
+    res->ess = (n * n) / c->h_scal[SC_Q];
+    if (res->ess != res->ess) { res->status = SMCB200_ERR_NAN_ESS; return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight."); }
+    // ---- selection ----------------------------------------------------------------------------------------
+    SMC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if (res->ess < cfg->threshold_ratio * n) {
+        st = launch_resample_cloud(c, cfg->resample_method, cfg->seed, cfg->stage, -1.0); if (st) return st;
+        res->resampled = 1;
+        state->resampled_last_period = 1;
+        if (normw_out) for (int64_t i = 0; i < c->N; ++i) normw_out[i] = 1.0;   // W_matrix[:, i] .= 1
+    }
+    SMC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    // ---- mutation -----------------------------------------------------------------------------------------
+    state->c = update_step_size(state->c, state->accept, cfg->target);
+    res->c = state->c;
+    SMC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    st = launch_moments(c); if (st) return st;
+    int perm[DMAX], sizes[NBMAX], ball[DMAX];
+    if (cfg->n_blocks < 1 || cfg->n_blocks > NBMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_blocks must be in 1..8");
+    generate_blocks(c->n_free, cfg->n_blocks, cfg->seed, cfg->stage, perm, sizes);
+    for (int a = 0; a < c->n_free; ++a) ball[a] = c->free_idx[perm[a]];
+    BlockSpec bs;
+    st = make_blockspec(c, cfg->n_blocks, sizes, ball, &bs); if (st) return st;
+    double* work = reinterpret_cast<double*>(c->mutc_dev + 1);
+    k_prepare_proposal<<<1, 32, 0, c->stream>>>(c->msum, c->csum, bs, state->c, c->mutc_dev, work, c->status_dev);
+    c->launches += 1;
+    c->mutc_host->n_blocks = cfg->n_blocks;
+    st = mutate_upload_proposal(c, true); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    st = mutate_launch(c, phi_n, cfg->n_mh_steps, cfg->has_old_data != 0, cfg->seed, cfg->stage); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+    st = mean_accept(c); if (st) return st;
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_status, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    if (*c->h_status) {
+        cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream);
+        res->status = *c->h_status;
+        return fail(c, *c->h_status, "proposal covariance is not positive definite");
+    }
+    state->accept = c->h_scal[SC_ACC] / n;
+    state->ess_prev = res->ess;
+    res->accept = state->accept;
+    cudaEventElapsedTime(&res->ms_correct, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res->ms_resample, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res->ms_moments, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&res->ms_mutate, c->ev[6], c->ev[7]);
+    c->last_ms[0] = res->ms_correct; c->last_ms[1] = res->ms_resample; c->last_ms[2] = res->ms_moments; c->last_ms[3] = res->ms_mutate;
+    return SMCB200_OK;
+}
+
+int32_t smcb200_stage_host(smcb200_ctx* c, double* particles, int64_t ld, const smcb200_stage_config* cfg, smcb200_stage_state* state,
+                           const double* sched, int32_t n_phi, smcb200_stage_result* res)
+{
+    int st = smcb200_cloud_upload(c, particles, ld, 0); if (st) return st;
+    st = smcb200_stage(c, cfg, state, sched, n_phi, nullptr, nullptr, res); if (st) return st;
+    return smcb200_cloud_download(c, particles, ld, 0);
+}
+
+int64_t smcb200_kernel_launches(const smcb200_ctx* c) { return c ? c->launches : 0; }
+
+int32_t smcb200_last_kernel_ms(const smcb200_ctx* c, int32_t which, float* ms)
+{
+    if (!c || which < 0 || which > 3 || !ms) return SMCB200_ERR_BAD_ARGUMENT;
+    *ms = c->last_ms[which];
+    return SMCB200_OK;
+}
+
+int32_t smcb200_debug_math(smcb200_ctx* c, int32_t op, const double* x, int64_t n, uint64_t seed, double* out)
+{
+    if (!c || !x || !out || n < 1) return SMCB200_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    double *dx = nullptr, *dout = nullptr;
+    SMC_CUDA(c, cudaMalloc(&dx, sizeof(double) * n));
+    SMC_CUDA(c, cudaMalloc(&dout, sizeof(double) * n));
+    SMC_CUDA(c, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    k_debug_math<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(op, dx, n, seed, dout);
+    c->launches += 1;
+    cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    int st = sync(c);
+    cudaFree(dx); cudaFree(dout);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,595 @@
+// kernels.cuh -- K1..K6: correction/ESS, adaptive-phi state machine, resampling (scan + search +
+// gather) and moments.  All of them are single-pass streaming kernels over struct-of-arrays columns
+// (HBM-bound); every reduction follows the canonical orders of DESIGN.md "Numerical contract".
+#pragma once
+#include "common.cuh"
+
+namespace smc {
+
+// =================================================================================================
+// canonical 256-lane block tree + last-block tile tree
+// =================================================================================================
+__device__ __forceinline__ double warp_tree(double v)
+{
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// adjacent-pair tree over the 256 threads of the block; result valid in thread 0. sm: 8 doubles.
+__device__ __forceinline__ double block_tree_256(double v, double* sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_tree(v);
+    __syncthreads();               // protect sm reuse across calls
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double x = (lane < 8) ? sm[lane] : 0.0;
+        x = x + __shfl_xor_sync(0xffffffffu, x, 1);
+        x = x + __shfl_xor_sync(0xffffffffu, x, 2);
+        x = x + __shfl_xor_sync(0xffffffffu, x, 4);
+        v = x;
+    }
+    return v;
+}
+
+// adjacent-pair tree over `ntiles` tile partials (zero padded to the power of two P) by one block
+// of 256 threads; result valid in thread 0.  part[] entries >= ntiles must be zero (they are never
+// written after the initial memset).
+__device__ __forceinline__ double tiles_tree_256(double* part, int ntiles, int P, double* sm)
+{
+    double x;
+    if (P <= 256) {
+        x = ((int)threadIdx.x < ntiles) ? __ldcg(part + threadIdx.x) : 0.0;
+    } else {
+        const int m = P / 256;
+        double* p = part + (size_t)threadIdx.x * m;
+        for (int s = 1; s < m; s <<= 1)
+            for (int i = 0; i < m; i += 2 * s) __stcg(p + i, __ldcg(p + i) + __ldcg(p + i + s));
+        x = __ldcg(p);
+    }
+    return block_tree_256(x, sm);
+}
+
+// The block that finishes last reduces the tile partials of NQ quantities into out[q].
+// v[q] must be valid in thread 0.  Returns true (block-uniform) in the finishing block.
+template <int NQ>
+__device__ __forceinline__ bool finish_tiles(const double (&v)[NQ], double* partials, int ntiles, int P,
+                                             unsigned* counter, double* out, double* sm)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) __stcg(partials + (size_t)q * P + blockIdx.x, v[q]);
+        __threadfence();
+        const unsigned t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const double r = tiles_tree_256(partials + (size_t)q * P, ntiles, P, sm);
+        if (threadIdx.x == 0) out[q] = r;
+    }
+    return true;
+}
+
+// =================================================================================================
+// K1 / K2: correction and ESS  (src/smc_main.jl:400-427, src/helpers.jl:173-181)
+// =================================================================================================
+struct CorrArgs {
+    double phi_n1, phi_n, pw, lpod, log_1m_pw;
+    int mode;   // 0: prior weight 0, 1: prior weight 1, 2: in between
+};
+
+__device__ __forceinline__ double inc_weight(double ll, double old, const CorrArgs& a, double phi_n)
+{
+    if (a.mode == 0) return det_exp((a.phi_n1 - phi_n) * old + (phi_n - a.phi_n1) * ll);
+    if (a.mode == 1) return det_exp((phi_n - a.phi_n1) * ll);
+    const double inner = det_log(det_exp((old - a.lpod) + a.log_1m_pw) + a.pw);
+    return det_exp((a.phi_n1 - phi_n) * inner + (phi_n - a.phi_n1) * ll);
+}
+
+// pass A: w~ = w * inc; S = canonical sum of w~.   wout = w (correction, in place) or a scratch
+// column (compute_ESS).  phi_state != nullptr: trial phi comes from the device state machine.
+__global__ void __launch_bounds__(256)
+k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const double* w,
+            double* wout, double* __restrict__ inc_out, int64_t N, CorrArgs a,
+            const PhiState* __restrict__ phi_state, double* partials, int ntiles, int P, unsigned* counter,
+            double* scal)
+{
+    __shared__ double sm[8];
+    double phi_n = a.phi_n;
+    if (phi_state) {
+        if (phi_state->done) return;
+        phi_n = phi_state->phi_cur;
+    }
+    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
+    double x[W_R];
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) {
+        const int64_t i = base + (int64_t)r * W_LANES;
+        x[r] = 0.0;
+        if (i < N) {
+            const double inc = inc_weight(ll[i], old[i], a, phi_n);
+            x[r] = w[i] * inc;
+            wout[i] = x[r];
+            if (inc_out) inc_out[i] = inc;
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) acc = acc + x[r];
+    double v[1] = {block_tree_256(acc, sm)};
+    finish_tiles<1>(v, partials, ntiles, P, counter, scal + SC_S, sm);
+}
+
+// device transition of solve_adaptive_phi (src/helpers.jl:26-54); executed by one thread
+__device__ inline void phi_transition(PhiState* st, const double* sched, double ess)
+{
+    const double g = ess - st->ess_bar;
+    st->evals += 1;
+    st->g_last = g;
+    bool finish = false;
+    if (st->phase == 0) {
+        if (g >= 0.0 && st->j <= st->n_phi) {
+            st->phi_prop = sched[st->j - 1];
+            st->j += 1;
+            st->phi_cur = st->phi_prop;
+            return;
+        }
+        if (st->phi_prop != 1.0 || g < 0.0) {
+            st->lo = st->phi_n1; st->hi = st->phi_prop; st->phase = 1;
+        } else {
+            st->phi_n = 1.0; st->done = 1;
+            return;
+        }
+    } else {
+        if (g == 0.0) { st->lo = st->phi_cur; finish = true; }
+        else if (g > 0.0) st->lo = st->phi_cur;
+        else st->hi = st->phi_cur;
+    }
+    if (!finish) {
+        const double mid = 0.5 * (st->lo + st->hi);
+        if (mid > st->lo && mid < st->hi) { st->phi_cur = mid; return; }
+    }
+    st->phi_n = (st->lo == st->phi_n1) ? st->hi : st->lo;
+    st->done = 1;
+}
+
+// pass B: W = (w~ * N) / S; Q = sum W^2, S2 = sum W.  store != 0 writes W back (normalize_weights!).
+__global__ void __launch_bounds__(256)
+k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts, int store,
+            PhiState* phi_state, const double* __restrict__ sched, double* partials, int ntiles, int P,
+            unsigned* counter, double* scal)
+{
+    __shared__ double sm[8];
+    if (phi_state && phi_state->done) return;
+    const double S = scal[SC_S];
+    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
+    double x[W_R];
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) {
+        const int64_t i = base + (int64_t)r * W_LANES;
+        x[r] = 0.0;
+        if (i < N) {
+            x[r] = (w[i] * n_parts) / S;
+            if (store) w[i] = x[r];
+            if (normw_out) normw_out[i] = x[r];
+        }
+    }
+    double q = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) { q = q + x[r] * x[r]; s2 = s2 + x[r]; }
+    double v[2];
+    v[0] = block_tree_256(q, sm);
+    v[1] = block_tree_256(s2, sm);
+    const bool last = finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, scal + SC_Q, sm);
+    if (last && phi_state && threadIdx.x == 0) {
+        const double ess = (n_parts * n_parts) / scal[SC_Q];
+        phi_transition(phi_state, sched, ess);
+    }
+}
+
+// canonical sum of one column (optionally divided by a constant first): out = sum_i x_i / div
+__global__ void __launch_bounds__(256)
+k_colsum(const double* __restrict__ x, int64_t N, double div, int use_div, double* partials, int ntiles, int P,
+         unsigned* counter, double* out)
+{
+    __shared__ double sm[8];
+    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) {
+        const int64_t i = base + (int64_t)r * W_LANES;
+        double v = 0.0;
+        if (i < N) v = use_div ? x[i] / div : x[i];
+        acc = acc + v;
+    }
+    double v[1] = {block_tree_256(acc, sm)};
+    finish_tiles<1>(v, partials, ntiles, P, counter, out, sm);
+}
+
+// =================================================================================================
+// K3: Julia-style pairwise cumsum with 64-element sequential leaves (src/resample.jl:29,47)
+// =================================================================================================
+__host__ __device__ inline int lvl_off(int n_level0, int k) { return 2 * n_level0 - ((2 * n_level0) >> k); }
+
+// FINAL = false: leaf totals + in-block tree -> blocktot[b]
+// FINAL = true : + top-down offsets from blockoff[b]; writes the block-local running max of the
+//                cumsum (rmax), optionally the raw cumsum, and the block maximum.
+template <bool FINAL>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* __restrict__ S_ptr, int64_t n, int B,
+       double* __restrict__ blocktot, const double* __restrict__ blockoff, double* __restrict__ rmax,
+       double* __restrict__ craw, double* __restrict__ bmax)
+{
+    extern __shared__ double sm_dyn[];
+    double* tile = sm_dyn;                       // [nleaf][65]
+    double* lv = sm_dyn + SCAN_THREADS * 65;     // [2*nleaf] tree levels
+    double* lmax = lv + 2 * SCAN_THREADS;        // [nleaf]
+    const int tid = threadIdx.x;
+    const int nleaf = B / LEAF;
+    const int64_t base = (int64_t)blockIdx.x * B;
+    const double S = *S_ptr;
+    for (int k = tid; k < B; k += SCAN_THREADS) {
+        const int64_t i = base + k;
+        double x = 0.0;
+        if (i < n) {
+            x = src[i];
+            if (div_n) x = x / n_parts;
+            x = x / S;
+        }
+        tile[(k >> 6) * 65 + (k & 63)] = x;
+    }
+    __syncthreads();
+    double total = 0.0;
+    if (tid < nleaf) {
+        double run = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < LEAF; ++i) {
+            run = run + tile[tid * 65 + i];
+            tile[tid * 65 + i] = run;
+        }
+        total = run;
+        lv[tid] = total;
+    }
+    int nlev = 0;
+    while ((1 << nlev) < nleaf) ++nlev;
+    for (int k = 1; k <= nlev; ++k) {
+        __syncthreads();
+        if (tid < (nleaf >> k))
+            lv[lvl_off(nleaf, k) + tid] = lv[lvl_off(nleaf, k - 1) + 2 * tid] + lv[lvl_off(nleaf, k - 1) + 2 * tid + 1];
+    }
+    __syncthreads();
+    if (!FINAL) {
+        if (tid == 0) blocktot[blockIdx.x] = lv[lvl_off(nleaf, nlev)];
+        return;
+    }
+    if (tid < nleaf) {
+        double off = blockoff[blockIdx.x];
+        for (int k = nlev - 1; k >= 0; --k) {
+            const int node = tid >> k;
+            if (node & 1) off = off + lv[lvl_off(nleaf, k) + node - 1];
+        }
+        const int64_t first = base + (int64_t)tid * LEAF;
+        int64_t valid = n - first;
+        if (valid > LEAF) valid = LEAF;
+        double last = -dinf();
+#pragma unroll 8
+        for (int i = 0; i < LEAF; ++i) {
+            const double c = off + tile[tid * 65 + i];
+            tile[tid * 65 + i] = c;
+            if (i < valid) last = c;    // c is non-decreasing inside a leaf
+        }
+        lmax[tid] = last;
+    }
+    // inclusive prefix max over the leaves (Hillis-Steele; max is exact, any order)
+    for (int s = 1; s < nleaf; s <<= 1) {
+        __syncthreads();
+        double v = 0.0;
+        if (tid < nleaf) v = (tid >= s) ? fmax(lmax[tid], lmax[tid - s]) : lmax[tid];
+        __syncthreads();
+        if (tid < nleaf) lmax[tid] = v;
+    }
+    __syncthreads();
+    for (int k = tid; k < B; k += SCAN_THREADS) {
+        const int64_t i = base + k;
+        if (i < n) {
+            const int leaf = k >> 6;
+            const double c = tile[leaf * 65 + (k & 63)];
+            const double pm = (leaf > 0) ? lmax[leaf - 1] : -dinf();
+            rmax[i] = fmax(c, pm);
+            if (craw) craw[i] = c;
+        }
+    }
+    if (tid == 0) bmax[blockIdx.x] = lmax[nleaf - 1];
+}
+
+// upper tree over the nb (power of two) block totals: block offsets (top-down), single block
+__global__ void __launch_bounds__(256)
+k_scan_upper(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ blockoff)
+{
+    int nlev = 0;
+    while ((1 << nlev) < nb) ++nlev;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) lv[i] = blocktot[i];
+    for (int k = 1; k <= nlev; ++k) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (nb >> k); i += blockDim.x)
+            lv[lvl_off(nb, k) + i] = lv[lvl_off(nb, k - 1) + 2 * i] + lv[lvl_off(nb, k - 1) + 2 * i + 1];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        double off = 0.0;
+        for (int k = nlev - 1; k >= 0; --k) {
+            const int node = b >> k;
+            if (node & 1) off = off + lv[lvl_off(nb, k) + node - 1];
+        }
+        blockoff[b] = off;
+    }
+}
+
+// inclusive prefix max of the block maxima (tiny; one thread)
+__global__ void k_prefix_max(double* bmax, int nb)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double m = -dinf();
+        for (int b = 0; b < nb; ++b) { m = fmax(m, bmax[b]); bmax[b] = m; }
+    }
+}
+
+// =================================================================================================
+// K4: ancestor search.  Sequential semantics of src/resample.jl:51-70 ("first j >= previous ancestor
+// with cum[j] > threshold") == first exceedance of the threshold in the running max of cum
+// (thresholds are non-decreasing), found by a two-level binary search.  "Not found" (resample.jl:60
+// returns 0) is clamped to n.
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_search(const double* __restrict__ rmax, const double* __restrict__ bmax_incl, int nb, int B, int64_t n,
+         int64_t n_out, int64_t out0, int method, uint64_t seed, uint32_t stage, double u, double n_parts,
+         int64_t* __restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_out) return;
+    const int64_t gi = out0 + i;
+    double t;
+    if (method == SMCB200_RESAMPLE_SYSTEMATIC) {
+        t = ((double)gi + u) / n_parts;                       // (i - 1 + offset) / n_parts, resample.jl:53
+    } else {
+        const u32x4 r = rng4(seed, (uint32_t)gi, stage, 1u, PURP_RESAMPLE);
+        t = u01(r.x, r.y);                                    // offset[i], resample.jl:30
+    }
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (bmax_incl[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    int64_t res = n;
+    if (lo < nb) {
+        int64_t jlo = (int64_t)lo * B, jhi = jlo + B;
+        if (jhi > n) jhi = n;
+        while (jlo < jhi) {
+            const int64_t mid = (jlo + jhi) >> 1;
+            if (rmax[mid] > t) jhi = mid; else jlo = mid + 1;
+        }
+        res = jlo + 1;
+        if (res > n) res = n;
+    }
+    idx[i] = res;
+}
+
+// =================================================================================================
+// K5: gather rows by ancestor + reset weights (src/smc_main.jl:440-442, particle.jl:378-383)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t* __restrict__ idx, int64_t N,
+         int ncopy, int wcol)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const int64_t a = idx[i] - 1;
+    int c = 0;
+    for (; c + 4 <= ncopy; c += 4) {
+        const double v0 = src[col_off(N, c) + a], v1 = src[col_off(N, c + 1) + a];
+        const double v2 = src[col_off(N, c + 2) + a], v3 = src[col_off(N, c + 3) + a];
+        dst[col_off(N, c) + i] = v0; dst[col_off(N, c + 1) + i] = v1;
+        dst[col_off(N, c + 2) + i] = v2; dst[col_off(N, c + 3) + i] = v3;
+    }
+    for (; c < ncopy; ++c) dst[col_off(N, c) + i] = src[col_off(N, c) + a];
+    dst[col_off(N, wcol) + i] = 1.0;
+}
+
+// =================================================================================================
+// K6: moments (src/particle.jl:481-486,526-532).  Canonical order: lane l of a 2048-particle tile
+// accumulates particles l, l+32, ... (64 of them) with fma, then a 32-lane adjacent-pair tree,
+// then the tile tree.  One warp per tile.
+// =================================================================================================
+// pass 1: msum[0] = sum w, msum[1+k] = sum w x_k.  partials layout [1+d][P].
+__global__ void __launch_bounds__(32)
+k_moments1(const double* __restrict__ cloud, int64_t N, int d, double* __restrict__ partials, int P)
+{
+    const int lane = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
+    const double* w = cloud + col_off(N, d + 4);
+    for (int q = 0; q <= d; ++q) {
+        const double* x = (q == 0) ? nullptr : cloud + col_off(N, q - 1);
+        double acc = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < M_R; ++r) {
+            const int64_t i = base + (int64_t)r * M_LANES;
+            if (i < N) acc = x ? fma(w[i], x[i], acc) : acc + w[i];
+        }
+        acc = warp_tree(acc);
+        if (lane == 0) partials[(size_t)q * P + blockIdx.x] = acc;
+    }
+}
+
+// pass 2: csum[a(a+1)/2 + b] = sum_i (w_i (x_ia - mean_a)) (x_ib - mean_b), b <= a.
+// Entries are split over the warps of the block in contiguous slabs so that each thread keeps its
+// slab's accumulators in registers; every warp streams the same tile (L1 serves the re-reads).
+template <int D, int SLABS>
+__global__ void __launch_bounds__(32 * SLABS)
+k_moments2(const double* __restrict__ cloud, int64_t N, const double* __restrict__ msum,
+           double* __restrict__ partials, int P)
+{
+    constexpr int E = D * (D + 1) / 2;
+    constexpr int PER = (E + SLABS - 1) / SLABS;
+    __shared__ double mean[D];
+    const int lane = threadIdx.x & 31, slab = threadIdx.x >> 5;
+    if (threadIdx.x < D) mean[threadIdx.x] = msum[1 + threadIdx.x] / msum[0];
+    __syncthreads();
+    const double* w = cloud + col_off(N, D + 4);
+    const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
+    double acc[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) acc[e] = 0.0;
+    const int lo = slab * PER;
+    for (int r = 0; r < M_R; ++r) {
+        const int64_t i = base + (int64_t)r * M_LANES;
+        if (i < N) {
+            const double wi = w[i];
+            double dx[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) dx[k] = cloud[col_off(N, k) + i] - mean[k];
+            // the slab index is warp-uniform; the switch keeps every accumulator index a literal
+#pragma unroll
+            for (int s = 0; s < SLABS; ++s) {
+                if (s == slab) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) {
+                        const double wa = wi * dx[a];
+#pragma unroll
+                        for (int b = 0; b <= a; ++b) {
+                            const int e = a * (a + 1) / 2 + b;
+                            if (e >= s * PER && e < (s + 1) * PER) acc[e - s * PER] = fma(wa, dx[b], acc[e - s * PER]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const double v = warp_tree(acc[e]);
+        if (lane == 0 && lo + e < E) partials[(size_t)(lo + e) * P + blockIdx.x] = v;
+    }
+}
+
+// generic-d fallback of pass 2 (one warp per tile, one entry at a time; slow, any d <= DMAX)
+__global__ void __launch_bounds__(32)
+k_moments2_generic(const double* __restrict__ cloud, int64_t N, int d, const double* __restrict__ msum,
+                   double* __restrict__ partials, int P)
+{
+    const int lane = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
+    const double* w = cloud + col_off(N, d + 4);
+    const double sw = msum[0];
+    for (int a = 0; a < d; ++a) {
+        const double ma = msum[1 + a] / sw;
+        const double* xa = cloud + col_off(N, a);
+        for (int b = 0; b <= a; ++b) {
+            const double mb = msum[1 + b] / sw;
+            const double* xb = cloud + col_off(N, b);
+            double acc = 0.0;
+            for (int r = 0; r < M_R; ++r) {
+                const int64_t i = base + (int64_t)r * M_LANES;
+                if (i < N) acc = fma(w[i] * (xa[i] - ma), xb[i] - mb, acc);
+            }
+            acc = warp_tree(acc);
+            if (lane == 0) partials[(size_t)(a * (a + 1) / 2 + b) * P + blockIdx.x] = acc;
+        }
+    }
+}
+
+// one block per quantity: adjacent-pair tree over its tile partials
+__global__ void __launch_bounds__(256) k_tree_finalize(double* partials, int ntiles, int P, double* out)
+{
+    __shared__ double sm[8];
+    const double r = tiles_tree_256(partials + (size_t)blockIdx.x * P, ntiles, P, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
+// =================================================================================================
+// proposal preparation: mean, covariance, per-block Cholesky -> MutConst (staged in global memory)
+// =================================================================================================
+// Shared by host (explicit mean/cov through the C ABI) and device (fused stage).  cov: d x d full.
+SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const BlockSpec& bs, double c, MutConst* out,
+                          double* work /* 2*DMAX*DMAX */)
+{
+    out->n_blocks = bs.n_blocks;
+    out->status = 0;
+    for (int k = 0; k < DMAX; ++k) out->mu[k] = (k < d) ? mean[k] : 0.0;
+    double* S = work;
+    double* L = work + DMAX * DMAX;
+    for (int b = 0; b < bs.n_blocks; ++b) {
+        const int n = bs.bsize[b];
+        out->bsize[b] = n;
+        uint32_t mask = 0;
+        for (int e = 0; e < PACKMAX; ++e) out->L[b][e] = 0.0;
+        for (int k = 0; k < DMAX; ++k) out->csd[b][k] = 0.0;
+        for (int i = 0; i < n; ++i) {
+            mask |= 1u << bs.member[b][i];
+            for (int j = 0; j < n; ++j) {
+                // R_fr = (R[f,f] + R[f,f]') / 2, src/smc_main.jl:462
+                const int ai = bs.member[b][i], aj = bs.member[b][j];
+                S[i * n + j] = (cov[ai * d + aj] + cov[aj * d + ai]) / 2.0;
+            }
+        }
+        out->mask[b] = mask;
+        const int st = cholesky_lower(S, n, L);
+        if (st) { out->status = SMCB200_ERR_NOT_POSDEF; return SMCB200_ERR_NOT_POSDEF; }
+        for (int i = 0; i < n; ++i) {
+            const int ai = bs.member[b][i];
+            for (int j = 0; j <= i; ++j) {
+                const int aj = bs.member[b][j];
+                out->L[b][ai * (ai + 1) / 2 + aj] = c * L[i * n + j];
+            }
+            out->csd[b][ai] = c * sqrt(S[i * n + i]);
+        }
+    }
+    return 0;
+}
+
+__global__ void k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ csum, BlockSpec bs,
+                                   double c, MutConst* out, double* work /* (3*DMAX*DMAX + DMAX) doubles */,
+                                   int* status)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int d = bs.d;
+    double* mean = work;
+    double* cov = work + DMAX;
+    const double sw = msum[0];
+    for (int k = 0; k < d; ++k) mean[k] = msum[1 + k] / sw;
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b <= a; ++b) {
+            const double v = csum[a * (a + 1) / 2 + b] / sw;
+            cov[a * d + b] = v;
+            cov[b * d + a] = v;
+        }
+    const int st = build_mutconst(mean, cov, d, bs, c, out, work + DMAX + DMAX * DMAX);
+    if (st) *status = st;
+}
+
+// debug: elementwise deterministic math on the device
+__global__ void k_debug_math(int op, const double* __restrict__ x, int64_t n, uint64_t seed, double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    switch (op) {
+    case 0: out[i] = det_exp(x[i]); break;
+    case 1: out[i] = det_log(x[i]); break;
+    case 2: det_sincos2pi(x[i], s, c); out[i] = s; break;
+    case 3: det_sincos2pi(x[i], s, c); out[i] = c; break;
+    default: {
+        double z0, z1;
+        normal_pair(rng4(seed, (uint32_t)i, 0u, (uint32_t)x[i], PURP_NORMAL), z0, z1);
+        out[i] = (op == 4) ? z0 : z1;
+    }
+    }
+}
+
+}  // namespace smc

@@ -1,0 +1,327 @@
+// mutate.cu -- K7: random-walk Metropolis-Hastings mutation of every particle, plus the stage-0
+// likelihood/prior evaluators that share its device functors.
+//
+// Replaces src/mutation.jl:56-138 fanned out at src/smc_main.jl:471-484 (one Distributed.jl task
+// per particle, 1 Cholesky + 4 SVD per MH step) with ONE kernel per stage:
+//   * one thread per particle: the cloud is a struct-of-arrays [n_para+5][N], so a warp's loads and
+//     stores of any column are 256 contiguous bytes; the particle lives in registers for all
+//     n_mh_steps * n_blocks steps, so HBM traffic is 8(2d+7) B/particle/stage regardless of n_mh_steps;
+//   * the scaled Cholesky factor c*L (factored ONCE per stage), the likelihood's sufficient statistics
+//     and the prior table live in __constant__ memory and enter the DFMAs as constant-bank operands
+//     (fully unrolled loops => immediate offsets): no shared-memory or register traffic for them;
+//   * counter-based Philox4x32-10 keyed on the GLOBAL particle index => results are invariant to the
+//     launch shape and to the number of GPUs.
+// The kernel is FP64-pipe bound (see DESIGN.md roofline), not HBM bound, for d >~ 8.
+#include "common.cuh"
+
+namespace smc {
+
+__constant__ MutConst c_mut;
+__constant__ LikSlot c_lik[2];
+__constant__ PriorConst c_pri;
+
+// ---- priors (ModelConstructors.prior: sum over free parameters) ------------------
+__device__ __forceinline__ double logpdf1(int k, double x)
+{
+    switch (c_pri.kind[k]) {
+    case SMCB200_PRIOR_NORMAL: {
+        const double z = (x - c_pri.p1[k]) * c_pri.a1[k];
+        return fma(-0.5 * z, z, c_pri.cst[k]);
+    }
+    case SMCB200_PRIOR_UNIFORM:
+        return (x >= c_pri.p1[k] && x <= c_pri.p2[k]) ? c_pri.cst[k] : -dinf();
+    case SMCB200_PRIOR_GAMMA:
+        if (!(x > 0.0)) return (x == 0.0 && c_pri.a1[k] == 0.0) ? c_pri.cst[k] : -dinf();
+        return fma(c_pri.a1[k], det_log(x), c_pri.cst[k]) - x * c_pri.a2[k];
+    case SMCB200_PRIOR_ROOT_INV_GAMMA: {
+        if (!(x > 0.0)) return -dinf();
+        const double x2 = x * x;
+        return fma(-c_pri.a1[k], det_log(x2), c_pri.cst[k]) - c_pri.a2[k] / x2;
+    }
+    case SMCB200_PRIOR_BETA:
+        if (!(x > 0.0 && x < 1.0)) return -dinf();
+        return fma(c_pri.a2[k], det_log(1.0 - x), fma(c_pri.a1[k], det_log(x), c_pri.cst[k]));
+    case SMCB200_PRIOR_INV_GAMMA:
+        if (!(x > 0.0)) return -dinf();
+        return fma(-c_pri.a1[k], det_log(x), c_pri.cst[k]) - c_pri.a2[k] / x;
+    }
+    return dnan();
+}
+
+template <int D>
+__device__ __forceinline__ double logprior(const double (&th)[D])
+{
+    double lp = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (!c_pri.fixed[k]) lp = lp + logpdf1(k, th[k]);
+    return lp;
+}
+template <int D>
+__device__ __forceinline__ bool in_bounds(const double (&th)[D])
+{
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (!c_pri.fixed[k]) ok = ok && (th[k] >= c_pri.lo[k] && th[k] <= c_pri.hi[k]);
+    return ok;
+}
+
+// ---- Gaussian regression family (centred sufficient statistics) ---------------------------------
+template <int NEQ_, int K_, int STRIDE_, int COEF_, int SIG_>
+struct GaussReg {
+    static constexpr int NEQ = NEQ_, K = K_, STRIDE = STRIDE_, COEF = COEF_, SIG = SIG_;
+    static constexpr int KP = K * (K + 1) / 2;
+    static constexpr int D_COEF = COEF + (NEQ - 1) * STRIDE + K;
+    static constexpr int D_SIG = (SIG >= 0) ? SIG + (NEQ - 1) * STRIDE + 1 : 0;
+    static constexpr int D = (D_COEF > D_SIG) ? D_COEF : D_SIG;
+
+    template <int SLOT>
+    static __device__ __forceinline__ double ll(const double (&th)[D])
+    {
+        const LikSlot& L = c_lik[SLOT];
+        double ll = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) {
+            double dl[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) dl[j] = th[COEF + e * STRIDE + j] - L.bhat[e * K + j];
+            double q = L.rss[e];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                double r = 0.0;
+#pragma unroll
+                for (int j = i; j < K; ++j) r = fma(L.U[e * KP + i * K - (i * (i - 1)) / 2 + (j - i)], dl[j], r);
+                q = fma(r, r, q);
+            }
+            double logs, inv_s2;
+            if (SIG >= 0) {
+                const double s = th[(SIG >= 0 ? SIG : 0) + e * STRIDE];
+                bad = bad || !(s > 0.0);
+                logs = det_log(s);
+                inv_s2 = 1.0 / (s * s);
+            } else {
+                logs = L.logs[e];
+                inv_s2 = L.inv_s2[e];
+            }
+            const double le = fma(-L.T[e], logs, L.cT[e]) - (0.5 * L.qscale[e] * q) * inv_s2;
+            ll = ll + le;
+        }
+        return bad ? -dinf() : ll;
+    }
+};
+
+struct MutArgs {
+    double phi_n;
+    int n_mh_steps, n_blocks, n_free;
+    uint64_t seed;
+    uint32_t stage;
+};
+
+// One MH chain per thread.  SINGLE = (n_blocks == 1): block index is a literal, so every factor entry
+// is an immediate constant-bank operand.
+template <class LIK, bool HAS_OLD, bool SINGLE>
+__global__ void __launch_bounds__(128) k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
+{
+    constexpr int D = LIK::D;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= N) return;
+    double th[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = cloud[col_off(N, k) + i];
+    double like = cloud[col_off(N, D) + i];
+    double lpri = cloud[col_off(N, D + 1) + i];
+    double lprev = cloud[col_off(N, D + 2) + i];
+    double accept = 0.0;
+    const uint32_t gp = (uint32_t)(index0 + i);
+    const double phi = a.phi_n, omphi = 1.0 - a.phi_n;
+    const int nb = SINGLE ? 1 : a.n_blocks;
+
+    for (int step = 0; step < a.n_mh_steps; ++step) {
+        for (int bb = 0; bb < nb; ++bb) {
+            const int b = SINGLE ? 0 : bb;
+            const uint32_t sb = (uint32_t)(step * nb + b);
+            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
+            const double step_prob = u01(r4.x, r4.y);
+            const uint32_t mask = c_mut.mask[b];
+            double s[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) s[k] = 0.0;
+            // proposal increment s = (c L) z, built column by column as the normals are generated
+#pragma unroll
+            for (int p = 0; p < (D + 1) / 2; ++p) {
+                if ((mask >> (2 * p)) & 3u) {
+                    double z0, z1;
+                    normal_pair(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)p, PURP_NORMAL), z0, z1);
+                    if ((mask >> (2 * p)) & 1u) {
+                        const int j = 2 * p;
+#pragma unroll
+                        for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][(r * (r + 1)) / 2 + j], z0, s[r]);
+                    }
+                    if (2 * p + 1 < D && ((mask >> (2 * p + 1)) & 1u)) {
+                        const int j = 2 * p + 1;
+#pragma unroll
+                        for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][(r * (r + 1)) / 2 + j], z1, s[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? th[k] + s[k] : th[k];   // s is now theta'
+            const bool ok = in_bounds<D>(s);
+            double pn = logprior<D>(s);
+            double ln = LIK::template ll<0>(s);
+            if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
+            double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
+            if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
+            // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
+            const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + 0.0);
+            if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
+#pragma unroll
+                for (int k = 0; k < D; ++k) th[k] = s[k];
+                like = ln; lpri = pn; lprev = lo;
+                accept += (double)c_mut.bsize[b];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = th[k];
+    cloud[col_off(N, D) + i] = like;
+    cloud[col_off(N, D + 1) + i] = lpri;
+    cloud[col_off(N, D + 2) + i] = lprev;
+    cloud[col_off(N, D + 3) + i] = accept / (double)a.n_free;      // particle.jl:410-418
+}
+
+// stage-0 evaluators: mode 0 = draw_likelihood (initialization.jl:129-139); mode 1 =
+// initialize_likelihoods! (:153-186): old_loglh <- loglh, then loglh/logprior on the new data
+template <class LIK>
+__global__ void __launch_bounds__(128) k_evaluate(double* __restrict__ cloud, int64_t N, int mode)
+{
+    constexpr int D = LIK::D;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= N) return;
+    double th[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = cloud[col_off(N, k) + i];
+    if (mode == 1) {
+        cloud[col_off(N, D + 2) + i] = cloud[col_off(N, D) + i];
+        cloud[col_off(N, D) + i] = LIK::template ll<0>(th);
+    } else {
+        cloud[col_off(N, D) + i] = in_bounds<D>(th) ? LIK::template ll<0>(th) : -dinf();
+    }
+    cloud[col_off(N, D + 1) + i] = logprior<D>(th);
+}
+
+// ---- dispatch ------------------------------------------------------------------------------------
+struct KernelEntry {
+    int neq, k, stride, coef, sig;
+    void (*mut[2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single]
+    void (*eval)(double*, int64_t, int);
+};
+
+template <class LIK>
+static KernelEntry make_entry()
+{
+    KernelEntry e;
+    e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG;
+    e.mut[0][0] = k_mutate<LIK, false, false>;
+    e.mut[0][1] = k_mutate<LIK, false, true>;
+    e.mut[1][0] = k_mutate<LIK, true, false>;
+    e.mut[1][1] = k_mutate<LIK, true, true>;
+    e.eval = k_evaluate<LIK>;
+    return e;
+}
+
+#define LINREG(K) make_entry<GaussReg<1, K, K, 0, -1>>()
+static const std::vector<KernelEntry>& table()
+{
+    static const std::vector<KernelEntry> t = {
+        LINREG(1), LINREG(2), LINREG(3), LINREG(4), LINREG(5), LINREG(6), LINREG(8), LINREG(10),
+        LINREG(12), LINREG(16), LINREG(20), LINREG(24), LINREG(32),
+        make_entry<GaussReg<3, 2, 3, 0, 2>>(),   // test/modelsetup.jl 3-equation model, CAPM (per-period form)
+        make_entry<GaussReg<3, 1, 3, 0, 2>>(),   // examples/capm_model as written
+        make_entry<GaussReg<1, 2, 3, 0, 2>>(),   // one equation (alpha, beta, sigma)
+        make_entry<GaussReg<2, 2, 3, 0, 2>>(),
+    };
+    return t;
+}
+
+static const KernelEntry* find_entry(const Ctx* ctx)
+{
+    const LikDesc& l = ctx->lik[0];
+    if (l.kind != SMCB200_LIK_GAUSSREG) return nullptr;
+    for (const auto& e : table())
+        if (e.neq == l.neq && e.k == l.k && e.stride == l.stride && e.coef == l.coef_off && e.sig == l.sig_off) {
+            // n_para must equal the functor's D
+            int dcoef = e.coef + (e.neq - 1) * e.stride + e.k;
+            int dsig = e.sig >= 0 ? e.sig + (e.neq - 1) * e.stride + 1 : 0;
+            if ((dcoef > dsig ? dcoef : dsig) == ctx->d) return &e;
+        }
+    return nullptr;
+}
+
+bool mutate_supported(const Ctx* ctx, bool has_old)
+{
+    const KernelEntry* e = find_entry(ctx);
+    if (!e) return false;
+    if (has_old) {
+        const LikDesc &a = ctx->lik[0], &b = ctx->lik[1];
+        if (b.kind != a.kind || b.neq != a.neq || b.k != a.k || b.stride != a.stride || b.coef_off != a.coef_off ||
+            b.sig_off != a.sig_off)
+            return false;
+    }
+    return true;
+}
+
+int mutate_upload_model(Ctx* ctx)
+{
+    SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_pri, &ctx->prior, sizeof(PriorConst), 0, cudaMemcpyHostToDevice, ctx->stream));
+    SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lik, ctx->lik_host, sizeof(LikSlot) * 2, 0, cudaMemcpyHostToDevice, ctx->stream));
+    SMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SMCB200_OK;
+}
+
+int mutate_upload_proposal(Ctx* ctx, bool from_device)
+{
+    // only the blocks in use are copied: header fields sit after the factor table
+    if (from_device) {
+        SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_mut, ctx->mutc_dev, sizeof(MutConst), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_mut, ctx->mutc_host, sizeof(MutConst), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return SMCB200_OK;
+}
+
+int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage)
+{
+    const KernelEntry* e = find_entry(ctx);
+    if (!e || !mutate_supported(ctx, has_old)) {
+        ctx->err = "no device mutation kernel for this likelihood / n_para";
+        return SMCB200_ERR_UNSUPPORTED;
+    }
+    MutArgs a;
+    a.phi_n = phi_n; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
+    a.seed = seed; a.stage = stage;
+    const bool single = (a.n_blocks == 1);
+    const unsigned grid = (unsigned)((ctx->N + 127) / 128);
+    e->mut[has_old ? 1 : 0][single ? 1 : 0]<<<grid, 128, 0, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);
+    ctx->launches++;
+    SMC_CUDA(ctx, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+int evaluate_launch(Ctx* ctx, int mode)
+{
+    const KernelEntry* e = find_entry(ctx);
+    if (!e) {
+        ctx->err = "no device likelihood functor for this likelihood / n_para";
+        return SMCB200_ERR_UNSUPPORTED;
+    }
+    const unsigned grid = (unsigned)((ctx->N + 127) / 128);
+    e->eval<<<grid, 128, 0, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, mode);
+    ctx->launches++;
+    SMC_CUDA(ctx, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+}  // namespace smc

@@ -1,0 +1,209 @@
+"""Engine -- thin object wrapper over the C ABI (include/smcb200.h), one per GPU.
+
+Status codes are converted to the exception classes the Julia shim would raise
+(SURVEY 8(b) / INTEGRATION.md).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import StageConfig, StageResult, StageState, lib, ptr
+from .model import ModelSpec
+
+RESAMPLERS = {"systematic": 0, "multinomial": 1}
+
+
+class NotPosDefError(np.linalg.LinAlgError):
+    pass
+
+
+def _raise(status, handle):
+    msg = lib.smcb200_last_error(handle).decode() if handle else ""
+    base = lib.smcb200_status_string(status).decode()
+    text = "%s%s" % (base, (": " + msg) if msg and msg != base else "")
+    if status == _lib.ERR_NAN_ESS:
+        raise AssertionError(text)
+    if status in (_lib.ERR_BAD_RESAMPLER, _lib.ERR_BAD_ARGUMENT):
+        raise ValueError(text)
+    if status == _lib.ERR_NOT_POSDEF:
+        raise NotPosDefError(text)
+    if status == _lib.ERR_UNSUPPORTED:
+        raise NotImplementedError(text)
+    raise RuntimeError(text)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        st = lib.smcb200_create(C.byref(self.h), int(device))
+        if st:
+            self.h = None
+            raise RuntimeError("smcb200_create(device=%d) failed: %s -- a CUDA GPU is required, there is no CPU "
+                               "fallback" % (device, lib.smcb200_status_string(st).decode()))
+        self.n_parts = 0
+        self.n_para = 0
+        self.spec = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.smcb200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st:
+            _raise(st, self.h)
+
+    # ---- cloud ----------------------------------------------------------------------------------
+    def cloud_create(self, n_parts, n_para):
+        self._ck(lib.smcb200_cloud_create(self.h, int(n_parts), int(n_para)))
+        self.n_parts, self.n_para = int(n_parts), int(n_para)
+        first, count = C.c_int64(), C.c_int64()
+        self._ck(lib.smcb200_cloud_shard(self.h, C.byref(first), C.byref(count)))
+        self.first, self.count = first.value, count.value
+
+    def upload(self, particles):
+        """particles: n_parts x (n_para+5); Fortran-ordered arrays are passed without a copy."""
+        p = np.asfortranarray(particles, dtype=np.float64)
+        assert p.shape == (self.n_parts, self.n_para + 5), p.shape
+        self._ck(lib.smcb200_cloud_upload(self.h, ptr(p), p.shape[0], self.first))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros((self.n_parts, self.n_para + 5), order="F")
+        assert out.flags.f_contiguous and out.shape == (self.n_parts, self.n_para + 5)
+        self._ck(lib.smcb200_cloud_download(self.h, ptr(out), out.shape[0], self.first))
+        return out
+
+    def read_column(self, col):
+        if col < 0:
+            col += self.n_para + 5
+        out = np.zeros(self.count)
+        self._ck(lib.smcb200_cloud_read_column(self.h, col, ptr(out)))
+        return out
+
+    def write_column(self, col, v):
+        if col < 0:
+            col += self.n_para + 5
+        v = _f64(v)
+        assert v.shape == (self.count,)
+        self._ck(lib.smcb200_cloud_write_column(self.h, col, ptr(v)))
+
+    # ---- model ----------------------------------------------------------------------------------
+    def set_model(self, spec: ModelSpec):
+        self.spec = spec
+        self._ck(lib.smcb200_set_parameters(self.h, spec.d, ptr(_i32(spec.fixed)), ptr(_f64(spec.lo)), ptr(_f64(spec.hi)),
+                                            ptr(_i32(spec.kind)), ptr(_f64(spec.p1)), ptr(_f64(spec.p2))))
+        for slot, lk in enumerate(spec.liks):
+            if lk is None:
+                continue
+            ip, dp = lk.iparams(), _f64(lk.eqdata)
+            self._ck(lib.smcb200_set_likelihood(self.h, slot, lk.kind, ptr(ip), len(ip), ptr(dp), dp.size))
+
+    def evaluate(self, mode=0):
+        self._ck(lib.smcb200_evaluate(self.h, mode))
+
+    # ---- stage operations -------------------------------------------------------------------------
+    def correct(self, phi_n1, phi_n, prior_weight=0.0, log_prob_old_data=0.0, want_inc=False, want_normw=False):
+        inc = np.zeros(self.count) if want_inc else None
+        nw = np.zeros(self.count) if want_normw else None
+        out = np.zeros(3)
+        self._ck(lib.smcb200_correct(self.h, phi_n1, phi_n, prior_weight, log_prob_old_data, ptr(inc), ptr(nw), ptr(out)))
+        return out, inc, nw
+
+    def ess_at(self, phis, phi_n1):
+        phis = _f64(np.atleast_1d(phis))
+        out = np.zeros(len(phis))
+        self._ck(lib.smcb200_ess_at(self.h, ptr(phis), len(phis), phi_n1, ptr(out)))
+        return out
+
+    def solve_adaptive_phi(self, schedule, j, phi_prop, phi_n1, tempering_target, ess_prev, resampled_last_period):
+        sched = _f64(schedule)
+        jj, pp, pn = C.c_int64(int(j)), C.c_double(phi_prop), C.c_double()
+        self._ck(lib.smcb200_solve_adaptive_phi(self.h, ptr(sched), len(sched), C.byref(jj), C.byref(pp), phi_n1,
+                                                tempering_target, ess_prev, int(bool(resampled_last_period)), C.byref(pn)))
+        return pn.value, False, jj.value, pp.value
+
+    def resample(self, method="systematic", seed=0, stage=0, u=-1.0, want_indices=False):
+        if method not in RESAMPLERS:
+            raise ValueError("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
+        idx = np.zeros(self.count, np.int64) if want_indices else None
+        self._ck(lib.smcb200_resample(self.h, RESAMPLERS[method], seed, stage, u, ptr(idx)))
+        return idx
+
+    def resample_weights(self, weights, method="systematic", seed=0, stage=0, u=-1.0, want_cum=False):
+        if method not in RESAMPLERS:
+            raise ValueError("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
+        w = _f64(weights)
+        idx = np.zeros(len(w), np.int64)
+        cum = np.zeros(len(w)) if want_cum else None
+        self._ck(lib.smcb200_resample_weights(self.h, ptr(w), len(w), RESAMPLERS[method], seed, stage, u, ptr(idx), ptr(cum)))
+        return (idx, cum) if want_cum else idx
+
+    def moments(self):
+        mean = np.zeros(self.n_para)
+        cov = np.zeros((self.n_para, self.n_para))
+        self._ck(lib.smcb200_moments(self.h, ptr(mean), ptr(cov)))
+        return mean, cov
+
+    def mutate(self, mean_fr, cov_fr, blocks_free, blocks_all, phi_n, phi_n1, c=1.0, alpha=1.0, n_mh_steps=1,
+               has_old_data=False, seed=0, stage=0):
+        """blocks_*: list of 0-based index lists (generate_free_blocks / generate_all_blocks)."""
+        sizes = _i32([len(b) for b in blocks_all])
+        bf = _i32(np.concatenate([np.asarray(b) for b in blocks_free]))
+        ba = _i32(np.concatenate([np.asarray(b) for b in blocks_all]))
+        mean_fr, cov_fr = _f64(mean_fr), _f64(cov_fr)
+        acc = C.c_double()
+        self._ck(lib.smcb200_mutate(self.h, ptr(mean_fr), ptr(cov_fr), len(mean_fr), len(sizes), ptr(sizes), ptr(bf), ptr(ba),
+                                    phi_n, phi_n1, c, alpha, n_mh_steps, int(bool(has_old_data)), seed, stage, C.byref(acc)))
+        return acc.value
+
+    def stage(self, cfg: StageConfig, state: StageState, schedule=None, want_inc=False, want_normw=False):
+        inc = np.zeros(self.count) if want_inc else None
+        nw = np.zeros(self.count) if want_normw else None
+        sched = _f64(schedule) if schedule is not None else None
+        res = StageResult()
+        self._ck(lib.smcb200_stage(self.h, C.byref(cfg), C.byref(state), ptr(sched), 0 if sched is None else len(sched),
+                                   ptr(inc), ptr(nw), C.byref(res)))
+        return res, inc, nw
+
+    def stage_host(self, particles, cfg: StageConfig, state: StageState, schedule=None):
+        """One stage on a host-resident cloud (Fortran-ordered, updated in place)."""
+        assert particles.flags.f_contiguous and particles.dtype == np.float64
+        sched = _f64(schedule) if schedule is not None else None
+        res = StageResult()
+        self._ck(lib.smcb200_stage_host(self.h, ptr(particles), particles.shape[0], C.byref(cfg), C.byref(state), ptr(sched),
+                                        0 if sched is None else len(sched), C.byref(res)))
+        return res
+
+    # ---- introspection ------------------------------------------------------------------------------
+    @property
+    def kernel_launches(self):
+        return lib.smcb200_kernel_launches(self.h)
+
+    def last_kernel_ms(self, which):
+        ms = C.c_float()
+        self._ck(lib.smcb200_last_kernel_ms(self.h, which, C.byref(ms)))
+        return ms.value
+
+    def debug_math(self, op, x, seed=0):
+        x = _f64(x)
+        out = np.zeros_like(x)
+        self._ck(lib.smcb200_debug_math(self.h, op, ptr(x), x.size, seed, ptr(out)))
+        return out

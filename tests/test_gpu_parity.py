@@ -1,0 +1,449 @@
+"""GPU parity tests: every C-ABI entry point of the CUDA engine against the CPU oracle on the same
+seeded inputs.  Bar: BIT-EXACT (np.array_equal on float64) for weights, ESS, cumsum, ancestor
+indices, moments and whole mutated clouds -- the engine and the oracle share a numerical contract
+(DESIGN.md), so no tolerance is needed or used unless stated.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from smc_jl_b200 import model as M
+from smc_jl_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smc_jl_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def rand_cloud(rng, N, d, ll_scale=50.0, with_old=False):
+    P = np.zeros((N, d + 5), order="F")
+    P[:, :d] = rng.normal(size=(N, d))
+    P[:, d] = -np.abs(rng.normal(size=N)) * ll_scale
+    P[:, d + 1] = rng.normal(size=N)
+    P[:, d + 2] = -np.abs(rng.normal(size=N)) * ll_scale if with_old else 0.0
+    P[:, d + 3] = rng.uniform(size=N)
+    P[:, d + 4] = rng.uniform(0.2, 2.0, size=N)
+    return P
+
+
+# --------------------------------------------------------------------------------------------------
+def test_device_math_bitexact(eng):
+    L = O.lib()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-745, 709, 50000), rng.normal(0, 2, 50000), [0.0, -0.0, 800.0, -800.0, np.inf, -np.inf]])
+    got = eng.debug_math(0, x)
+    want = np.array([L.orc_exp(v) for v in x])
+    assert np.array_equal(got, want)
+    x = np.concatenate([rng.uniform(0, 2, 50000), 10.0 ** rng.uniform(-300, 300, 50000), [0.0, 1.0, np.inf, 5e-324]])
+    got = eng.debug_math(1, x)
+    want = np.array([L.orc_log(v) for v in x])
+    assert np.array_equal(got, want)
+    u = rng.uniform(0, 1, 50000)
+    out = np.zeros(2)
+    s, c = eng.debug_math(2, u), eng.debug_math(3, u)
+    for i in range(0, len(u), 7):
+        L.orc_sincos2pi_v(u[i], out)
+        assert s[i] == out[0] and c[i] == out[1]
+    slots = np.arange(4096, dtype=np.float64) % 11
+    z0, z1 = eng.debug_math(4, slots, seed=99), eng.debug_math(5, slots, seed=99)
+    for i in range(4096):
+        L.orc_normal_pair(99, i, 0, int(slots[i]), out)
+        assert z0[i] == out[0] and z1[i] == out[1]
+
+
+@pytest.mark.parametrize("N", [400, 5000, 65536 + 17])
+@pytest.mark.parametrize("pw", [0.0, 1.0, 0.3])
+def test_correct_bitexact(eng, N, pw):
+    rng = np.random.default_rng(N + int(pw * 10))
+    d = 3
+    P = rand_cloud(rng, N, d, with_old=True)
+    eng.cloud_create(N, d)
+    eng.upload(P)
+    out, inc, nw = eng.correct(0.2, 0.35, pw, -1.5, want_inc=True, want_normw=True)
+    buf = O.cloud_f(P)
+    oout, oinc, onw = np.zeros(3), np.zeros(N), np.zeros(N)
+    st = O.lib().orc_correct(buf, N, d, 0.2, 0.35, pw, -1.5, oinc.ctypes.data_as(C.c_void_p), onw.ctypes.data_as(C.c_void_p), oout)
+    assert st == 0
+    assert np.array_equal(out, oout)
+    assert np.array_equal(inc, oinc) and np.array_equal(nw, onw)
+    assert np.array_equal(eng.download(), O.cloud_m(buf, N, d))
+
+
+def test_correct_nan_ess_is_an_error(eng):
+    P = rand_cloud(np.random.default_rng(0), 1000, 2)
+    P[:, 2] = -np.inf       # every incremental weight is 0 => ESS NaN => check_nan_ess assertion
+    eng.cloud_create(1000, 2)
+    eng.upload(P)
+    with pytest.raises(AssertionError):
+        eng.correct(0.0, 0.5)
+
+
+def test_compute_ess_golden(eng, golden):
+    g = golden("compute_ess.npz")
+    n = len(g["loglh"])
+    P = np.zeros((n, 6), order="F")
+    P[:, 1], P[:, 3], P[:, 5] = g["loglh"], g["old_loglh"], g["current_weights"]
+    eng.cloud_create(n, 1)
+    eng.upload(P)
+    ess = eng.ess_at([float(g["phi_n"])], float(g["phi_n1"]))[0]
+    assert ess == pytest.approx(float(g["ess"]), rel=1e-13)          # reference golden (test/helpers.jl:133-175)
+    want = O.lib().orc_compute_ess(np.ascontiguousarray(g["loglh"]), np.ascontiguousarray(g["current_weights"]),
+                                   np.ascontiguousarray(g["old_loglh"]), n, float(g["phi_n"]), float(g["phi_n1"]), np.zeros(n))
+    assert ess == want                                                  # oracle, bit-exact
+
+
+def test_solve_adaptive_phi_golden(eng, golden):
+    g = golden("solve_adaptive_phi.npz")
+    P = np.asfortranarray(g["particles"])
+    N, d = P.shape[0], P.shape[1] - 5
+    eng.cloud_create(N, d)
+    eng.upload(P)
+    i = int(g["i"])
+    phi_n, rl, j, phi_prop = eng.solve_adaptive_phi(g["proposed_fixed_schedule"], int(g["j"]), float(g["phi_prop"]),
+                                                    float(g["phi_n1"]), float(g["tempering_target"]),
+                                                    float(g["cloud_ESS"][i - 2]), int(g["resampled_last_period"]))
+    assert phi_n == pytest.approx(float(g["out_phi_n"]), rel=1e-12)   # reference golden (test/helpers.jl:15-53)
+    assert j == int(g["out_j"]) and phi_prop == float(g["out_phi_prop"])
+    jj, pp, pn = C.c_int64(int(g["j"])), C.c_double(float(g["phi_prop"])), C.c_double()
+    O.lib().orc_solve_adaptive_phi(O.cloud_f(P), N, d, np.ascontiguousarray(g["proposed_fixed_schedule"]), 100, C.byref(jj),
+                                   C.byref(pp), float(g["phi_n1"]), float(g["tempering_target"]), float(g["cloud_ESS"][i - 2]),
+                                   int(g["resampled_last_period"]), C.byref(pn), None)
+    assert (phi_n, j, phi_prop) == (pn.value, jj.value, pp.value)       # oracle, bit-exact
+
+
+@pytest.mark.parametrize("N", [3000, 40000])
+def test_solve_adaptive_phi_random(eng, N):
+    rng = np.random.default_rng(N)
+    d = 2
+    P = rand_cloud(rng, N, d, ll_scale=300.0, with_old=True)
+    P[:, d + 4] = 1.0
+    eng.cloud_create(N, d)
+    eng.upload(P)
+    sched = (np.arange(200) / 199.0) ** 2.1
+    for phi_n1, j0, prop0, resampled in [(0.0, 2, 0.0, True), (float(sched[40]), 42, float(sched[40]), False)]:
+        got = eng.solve_adaptive_phi(sched, j0, prop0, phi_n1, 0.95, 0.9 * N, resampled)
+        jj, pp, pn = C.c_int64(j0), C.c_double(prop0), C.c_double()
+        O.lib().orc_solve_adaptive_phi(O.cloud_f(P), N, d, sched, 200, C.byref(jj), C.byref(pp), phi_n1, 0.95, 0.9 * N,
+                                       int(resampled), C.byref(pn), None)
+        assert (got[0], got[2], got[3]) == (pn.value, jj.value, pp.value)
+        assert phi_n1 < got[0] <= 1.0
+
+
+@pytest.mark.parametrize("N", [64, 400, 5000, 8192, 131072 + 3])
+@pytest.mark.parametrize("method", ["systematic", "multinomial"])
+def test_resample_weights_bitexact(eng, N, method):
+    rng = np.random.default_rng(N)
+    for case in range(3):
+        if case == 0:
+            w = rng.uniform(size=N)
+        elif case == 1:                                  # degenerate: few heavy particles, many zeros
+            w = np.where(rng.uniform(size=N) < 0.01, rng.uniform(size=N), 0.0)
+            w[rng.integers(N)] = 5.0
+        else:                                            # widely varying magnitudes
+            w = np.exp(rng.normal(0, 8, size=N))
+        w = w / w.sum()
+        idx, cum = eng.resample_weights(w, method, seed=11, stage=7 + case, u=-1.0, want_cum=True)
+        oidx, ocum = np.zeros(N, np.int64), np.zeros(N)
+        O.lib().orc_resample(w, N, 0 if method == "systematic" else 1, 11, 7 + case, -1.0, oidx, ocum.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(cum, ocum)
+        assert np.array_equal(idx, oidx)
+        assert idx.min() >= 1 and idx.max() <= N
+        if method == "systematic":
+            assert np.all(np.diff(idx) >= 0)
+            assert np.all(np.abs(np.bincount(idx - 1, minlength=N) - N * w) < 1 + 1e-6)
+
+
+def test_resample_explicit_offset_edges(eng):
+    """u = 0 and u -> 1: first/last thresholds; 'not found' clamps to N (reference would return 0)."""
+    N = 1000
+    w = np.random.default_rng(5).uniform(size=N)
+    w /= w.sum()
+    for u in (0.0, 0.5, 1.0 - 2 ** -53):
+        idx = eng.resample_weights(w, "systematic", u=u)
+        oidx = np.zeros(N, np.int64)
+        O.lib().orc_resample(w, N, 0, 0, 0, u, oidx, None)
+        assert np.array_equal(idx, oidx)
+    with pytest.raises(ValueError):
+        eng.resample_weights(w, "polyalgo")
+
+
+@pytest.mark.parametrize("N,d", [(5000, 9), (4096, 20), (70000, 2), (3000, 5)])
+def test_selection_and_moments_bitexact(eng, N, d):
+    rng = np.random.default_rng(N + d)
+    P = rand_cloud(rng, N, d)
+    P[:, d + 4] *= N / P[:, d + 4].sum()
+    eng.cloud_create(N, d)
+    eng.upload(P)
+    mean, cov = eng.moments()
+    omean, ocov = np.zeros(d), np.zeros((d, d))
+    O.lib().orc_moments(O.cloud_f(P), N, d, omean, ocov)
+    assert np.array_equal(mean, omean) and np.array_equal(cov, ocov)
+    np.testing.assert_allclose(mean, np.average(P[:, :d], axis=0, weights=P[:, -1]), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(cov, np.cov(P[:, :d].T, aweights=P[:, -1], bias=True), rtol=1e-10, atol=1e-14)
+    # selection: indices, gather of all columns, weights reset to 1
+    idx = eng.resample("systematic", seed=3, stage=9, want_indices=True)
+    oidx = np.zeros(N, np.int64)
+    wn = np.ascontiguousarray(P[:, -1] / N)
+    O.lib().orc_resample(wn, N, 0, 3, 9, -1.0, oidx, None)
+    assert np.array_equal(idx, oidx)
+    dst = np.zeros(N * (d + 5))
+    O.lib().orc_gather(O.cloud_f(P), dst, N, d, oidx)
+    got = eng.download()
+    assert np.array_equal(got, O.cloud_m(dst, N, d))
+    assert np.all(got[:, -1] == 1.0)
+
+
+def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, stage):
+    N, d = P.shape[0], spec.d
+    free = spec.free_inds
+    mean = np.average(P[:, :d], axis=0, weights=P[:, -1])
+    cov = np.cov(P[:, :d].T, aweights=P[:, -1], bias=True).reshape(d, d)
+    mean_fr, cov_fr = mean[free], np.ascontiguousarray(cov[np.ix_(free, free)])
+    blocks_free = [np.asarray(b, np.int32) for b in blocks]
+    blocks_all = [free[b].astype(np.int32) for b in blocks_free]
+    eng.cloud_create(N, d)
+    eng.set_model(spec)
+    eng.upload(P)
+    acc = eng.mutate(mean_fr, cov_fr, blocks_free, blocks_all, phi_n, phi_n1, c=c, alpha=1.0, n_mh_steps=n_mh,
+                     has_old_data=has_old, seed=seed, stage=stage)
+    got = eng.download()
+    L = O.lib()
+    mod = O.Model(spec)
+    st = C.c_int()
+    pr = L.orc_proposal_create(d, len(free), np.ascontiguousarray(mean_fr), cov_fr, len(blocks),
+                               np.array([len(b) for b in blocks], np.int32), np.concatenate(blocks_free).astype(np.int32),
+                               np.concatenate(blocks_all).astype(np.int32), c, C.byref(st))
+    assert pr and st.value == 0
+    buf = O.cloud_f(P)
+    L.orc_mutate(mod.h, pr, buf, N, 0, phi_n, phi_n1, 1.0, n_mh, len(free), int(has_old), seed, stage, 0)
+    L.orc_proposal_free(pr)
+    want = O.cloud_m(buf, N, d)
+    oacc = L.orc_mean_accept(buf, N, d)
+    return got, want, acc, oacc
+
+
+def _evaluated_cloud(eng, spec, params, N, rng):
+    P = W.initial_cloud(params, N, rng)
+    eng.cloud_create(N, spec.d)
+    eng.set_model(spec)
+    eng.upload(P)
+    eng.evaluate(0)
+    return eng.download()
+
+
+def test_evaluate_matches_oracle_and_direct(eng):
+    params, lk, (y, X, _) = W.linear_gaussian(d=20, T=256)
+    spec = M.make_spec(params, lk)
+    rng = np.random.default_rng(1)
+    N = 5000
+    P = _evaluated_cloud(eng, spec, params, N, rng)
+    mod = O.Model(spec)
+    buf = O.cloud_f(W_reset(P))
+    O.lib().orc_evaluate(mod.h, buf, N)
+    want = O.cloud_m(buf, N, 20)
+    assert np.array_equal(P, want)
+    # against the per-observation form of the reference's example likelihood (relative 1e-12)
+    Xf = np.ascontiguousarray(X)
+    for r in range(0, N, 97):
+        direct = O.lib().orc_loglik_linreg_direct(np.ascontiguousarray(P[r, :20]), np.ascontiguousarray(y), Xf, 256, 20, 1.0)
+        assert P[r, 20] == pytest.approx(direct, rel=1e-12)
+
+
+def W_reset(P):
+    Q = P.copy(order="F")
+    d = P.shape[1] - 5
+    Q[:, d] = 0.0
+    Q[:, d + 1] = 0.0
+    return Q
+
+
+@pytest.mark.parametrize("d,n_mh", [(20, 3), (2, 1), (8, 2)])
+def test_mutation_linear_gaussian_bitexact(eng, d, n_mh):
+    params, lk, _ = W.linear_gaussian(d=d, T=64)
+    spec = M.make_spec(params, lk)
+    rng = np.random.default_rng(d)
+    N = 4096 + 37
+    P = _evaluated_cloud(eng, spec, params, N, rng)
+    P[:, -1] = rng.uniform(0.5, 1.5, N)
+    got, want, acc, oacc = _mutation_case(eng, spec, P, [np.arange(d)], 0.05, 0.02, 0.4, n_mh, False, 1793, 5)
+    assert np.array_equal(got, want)
+    assert acc == oacc
+    assert 0.0 < acc < n_mh + 1e-9
+    assert not np.array_equal(got[:, :d], P[:, :d])            # something moved
+
+
+def test_mutation_three_equation_blocks_and_old_data_bitexact(eng):
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters()
+    spec = M.make_spec(params, M.LinearEquationsLogLik(data, X), M.LinearEquationsLogLik(data[:, :50], X))
+    rng = np.random.default_rng(4)
+    N = 3000
+    P = W.initial_cloud(params, N, rng)
+    P[:, :9] = np.abs(rng.normal(1.5, 0.5, (N, 9)))             # near the posterior so that moves are accepted
+    eng.cloud_create(N, 9)
+    eng.set_model(spec)
+    eng.upload(P)
+    eng.evaluate(0)
+    P = eng.download()
+    # old_loglh column as initialize_likelihoods! would leave it: likelihood of the old data
+    mod = O.Model(spec)
+    P[:, 11] = [mod.loglik(np.ascontiguousarray(P[r, :9]), 1) for r in range(N)]
+    blocks = [np.array([6, 1, 4]), np.array([0, 8, 3]), np.array([2, 7, 5])]
+    got, want, acc, oacc = _mutation_case(eng, spec, P, blocks, 0.3, 0.2, 0.3, 2, True, 7, 11)
+    assert np.array_equal(got, want)
+    assert acc == oacc and acc > 0.0
+
+
+def test_mutation_golden(eng, golden):
+    """Reference golden test/mutation.jl:1-59 through the CUDA path (reject-all pass-through, accept = 0)."""
+    g = golden("mutation.npz")
+    lm = golden("linear_model_rows.npz")
+    params = W.three_equation_parameters()
+    spec = M.make_spec(params, M.LinearEquationsLogLik(lm["data"], lm["X"]), M.LinearEquationsLogLik(g["old_data"], lm["X"]))
+    P = np.asfortranarray(g["particles_in"])
+    eng.cloud_create(P.shape[0], 9)
+    eng.set_model(spec)
+    eng.upload(P)
+    bf = [(g["blocks_free"] - 1).astype(np.int32)]
+    ba = [(g["blocks_all"] - 1).astype(np.int32)]
+    acc = eng.mutate(g["mu"], g["Sigma"], bf, ba, float(g["phi_n"]), float(g["phi_n1"]), c=float(g["c"]), alpha=1.0,
+                     n_mh_steps=1, has_old_data=True, seed=42, stage=2)
+    got = eng.download()
+    assert np.array_equal(got, g["particles_out"])
+    assert acc == 0.0
+
+
+def test_not_posdef_is_an_error(eng):
+    params, lk, _ = W.linear_gaussian(d=4, T=32)
+    spec = M.make_spec(params, lk)
+    eng.cloud_create(256, 4)
+    eng.set_model(spec)
+    eng.upload(W.initial_cloud(params, 256, np.random.default_rng(0)))
+    bad = -np.eye(4)
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.mutate(np.zeros(4), bad, [np.arange(4)], [np.arange(4)], 0.1, 0.0)
+
+
+def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False):
+    """Run stages on the GPU (fused smcb200_stage) and in the oracle (orc_stage); compare everything."""
+    from smc_jl_b200._lib import StageConfig, StageState
+    N, d = P0.shape[0], spec.d
+    eng.cloud_create(N, d)
+    eng.set_model(spec)
+    eng.upload(P0)
+    state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2, resampled_last_period=0)
+    io = O.StageIO(threshold_ratio=0.5, target=0.25, alpha=1.0, tempering_target=0.95, pw=0.0, log_prob_old_data=0.0,
+                   n_mh_steps=cfg_kw["n_mh_steps"], n_blocks=cfg_kw["n_blocks"], resample_method=0, adaptive=int(adaptive),
+                   has_old=cfg_kw.get("has_old", 0), nthreads=0, seed=1793, c=0.5, accept=0.25, ess_prev=float(N),
+                   resampled_last=0, j=2, phi_prop=0.0)
+    mod = O.Model(spec)
+    buf = O.cloud_f(P0)
+    scratch = np.zeros_like(buf)
+    phi_prev = 0.0
+    n_resampled = 0
+    for s in range(n_stage):
+        stage = s + 2
+        phi_n = float(sched[s + 1])
+        cfg = StageConfig(phi_n1=phi_prev, phi_n=phi_n, threshold_ratio=0.5, target=0.25, alpha=1.0, tempering_target=0.95,
+                          prior_weight=0.0, log_prob_old_data=0.0, n_mh_steps=cfg_kw["n_mh_steps"], n_blocks=cfg_kw["n_blocks"],
+                          resample_method=0, adaptive=int(adaptive), has_old_data=cfg_kw.get("has_old", 0), seed=1793, stage=stage)
+        res, inc, nw = eng.stage(cfg, state, schedule=sched, want_inc=True, want_normw=True)
+        io.phi_n1, io.phi_n, io.stage = phi_prev, phi_n, stage
+        oinc, onw = np.zeros(N), np.zeros(N)
+        st = O.lib().orc_stage(mod.h, buf, scratch, N, np.ascontiguousarray(sched), len(sched), C.byref(io),
+                               oinc.ctypes.data_as(C.c_void_p), onw.ctypes.data_as(C.c_void_p), None, None)
+        assert st == 0
+        assert res.phi_n == io.phi_out
+        assert res.ess == io.ess and res.sum_weights == io.sum_w
+        assert res.resampled == io.resampled
+        assert res.c == io.c and res.accept == io.accept
+        assert np.array_equal(inc, oinc) and np.array_equal(nw, onw)
+        assert np.array_equal(eng.download(), O.cloud_m(buf, N, d)), "cloud differs at stage %d" % stage
+        assert (state.j, state.phi_prop, state.resampled_last_period) == (io.j, io.phi_prop, io.resampled_last)
+        n_resampled += res.resampled
+        phi_prev = res.phi_n
+        if phi_prev >= 1.0:
+            break
+    return n_resampled, phi_prev
+
+
+def test_stage_trajectory_linear_gaussian_bitexact(eng):
+    """C2-shaped run (d = 20, n_mh = 3, fixed schedule) at a size the oracle finishes in seconds: identical
+    phi/ESS/c/accept trajectory, identical resample decisions, identical clouds after every stage."""
+    params, lk, _ = W.linear_gaussian(d=20, T=256)
+    spec = M.make_spec(params, lk)
+    N = 8192
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(7))
+    sched = (np.arange(40) / 39.0) ** 2.1
+    n_res, phi = _run_stages(eng, spec, P0, sched, 39, dict(n_mh_steps=3, n_blocks=1))
+    assert phi == 1.0 and n_res >= 3
+    # posterior mean of the final cloud is near the OLS estimate
+    mean, cov = eng.moments()
+    bhat = lk.eqdata[4:24]
+    assert np.max(np.abs(mean - bhat) / np.sqrt(np.diag(cov))) < 0.5
+
+
+def test_stage_trajectory_blocks_old_data_bitexact(eng):
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters(prior_para=10.0)
+    spec = M.make_spec(params, M.LinearEquationsLogLik(data, X), M.LinearEquationsLogLik(data[:, :50], X))
+    N = 5000
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(8))
+    mod = O.Model(spec)
+    P0[:, 11] = [mod.loglik(np.ascontiguousarray(P0[r, :9]), 1) for r in range(N)]
+    sched = (np.arange(25) / 24.0) ** 2.0
+    n_res, phi = _run_stages(eng, spec, P0, sched, 24, dict(n_mh_steps=2, n_blocks=3, has_old=1))
+    assert phi == 1.0 and n_res >= 2
+
+
+def test_stage_trajectory_adaptive_bitexact(eng):
+    params, lk, _ = W.regression_example()
+    spec = M.make_spec(params, lk)
+    N = 1000                                                   # config C1 size
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(9))
+    sched = (np.arange(60) / 59.0) ** 2.1
+    n_res, phi = _run_stages(eng, spec, P0, sched, 59, dict(n_mh_steps=1, n_blocks=1), adaptive=True)
+    assert 0.0 < phi <= 1.0
+
+
+# ---- full-size (BASELINE config C2) property tests: the oracle is too slow there ------------------
+def test_full_size_properties(eng):
+    from smc_jl_b200._lib import StageConfig, StageState
+    params, lk, _ = W.linear_gaussian(d=20, T=256)
+    spec = M.make_spec(params, lk)
+    N = 1 << 20
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(10))
+    assert np.all(np.isfinite(P0[:, 20])) and np.all(P0[:, -1] == 1.0)
+    sched = ((np.arange(300)) / 299.0) ** 2.1
+    state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2, resampled_last_period=0)
+    eng.upload(P0)
+    ess_seq, resamples = [], 0
+    for s in range(6):
+        cfg = StageConfig(phi_n1=float(sched[s]), phi_n=float(sched[s + 1]), threshold_ratio=0.5, target=0.25, alpha=1.0,
+                          tempering_target=0.95, n_mh_steps=3, n_blocks=1, resample_method=0, seed=1793, stage=s + 2)
+        res, _, nw = eng.stage(cfg, state, want_normw=True)
+        assert abs(nw.sum() - N) < 1e-6 * N                         # weights normalised to N (particle.jl:362-369)
+        assert res.ess == pytest.approx(N * N / np.sum(nw.astype(np.longdouble) ** 2) if not res.resampled else res.ess,
+                                        rel=1e-12)
+        assert 0 < res.ess <= N * (1 + 1e-12)
+        ess_seq.append(res.ess)
+        resamples += res.resampled
+    # selection at full size: sortedness, range, offspring counts within 1 of N*w, gather idempotence
+    w = eng.read_column(-1)
+    idx = eng.resample("systematic", seed=5, stage=99, want_indices=True)
+    assert np.all(np.diff(idx) >= 0) and idx[0] >= 1 and idx[-1] <= N
+    counts = np.bincount(idx - 1, minlength=N)
+    assert np.all(np.abs(counts - w / w.sum() * N) < 1 + 1e-6)
+    before = eng.download()
+    assert np.all(before[:, -1] == 1.0)
+    idx2 = eng.resample("systematic", seed=5, stage=100, u=0.5, want_indices=True)   # uniform weights: identity
+    assert np.array_equal(idx2, np.arange(1, N + 1))
+    assert np.array_equal(eng.download(), before)

@@ -1,0 +1,132 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-side model
+description is consistent with the reference's example likelihoods, and the oracle's stage loop is
+self-consistent (so that the GPU parity tests compare against something meaningful)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from smc_jl_b200 import cloud as CL
+from smc_jl_b200 import model as M
+from smc_jl_b200 import workloads as W
+
+
+def test_library_exports_every_declared_symbol():
+    from smc_jl_b200 import _lib
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 25
+    assert set(declared) == set(_lib.BOUND_SYMBOLS)          # binding and header agree
+    for name in declared:
+        assert hasattr(_lib.lib, name)                        # dlsym succeeds
+    assert _lib.lib.smcb200_abi_version() == 1
+    assert _lib.lib.smcb200_status_string(4).decode().startswith("proposal covariance")
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    from smc_jl_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert _lib.lib.smcb200_create(C.byref(h), 0) == _lib.ERR_CUDA and not h
+    from smc_jl_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(0)
+
+
+def test_arbitrary_callable_is_rejected():
+    params, lk, _ = W.regression_example()
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        M.make_spec(params, lambda p, d: 0.0)
+
+
+def test_sufficient_statistics_match_direct_likelihoods():
+    L = O.lib()
+    rng = np.random.default_rng(0)
+    # linear-Gaussian, d = 20 (C2)
+    params, lk, (y, X, _) = W.linear_gaussian(d=20, T=256)
+    mod = O.Model(M.make_spec(params, lk))
+    for _ in range(200):
+        th = rng.normal(0, 3, 20)
+        direct = L.orc_loglik_linreg_direct(th, np.ascontiguousarray(y), np.ascontiguousarray(X), 256, 20, 1.0)
+        assert mod.loglik(th) == pytest.approx(direct, rel=1e-12)
+    # CAPM as written (examples/capm_model/estimate_capm.jl:48-69), restated literally in numpy
+    g = np.load(O.ROOT + "/tests/golden/capm_data.npz")
+    lik_data, market = g["lik_data"], g["market_data"]
+    lkw = M.CAPMLogLik(lik_data, market, as_written=True)
+    mod = O.Model(M.make_spec(W.three_equation_parameters(), lkw))
+    for _ in range(100):
+        p = np.abs(rng.normal(1, 0.5, 9))
+        alpha = p[[0, 3, 6]]; beta = p[[0, 3, 6]]; sig2 = p[[2, 5, 8]] ** 2
+        term1 = -3 / 2 * np.log(2 * np.pi) - 0.5 * np.log(np.prod(sig2))
+        errors = lik_data - alpha[:, None] - beta[:, None] * market
+        want = sum(term1 - 0.5 * np.sum(errors * (errors / sig2[:, None])) for _ in range(lik_data.shape[1]))
+        assert mod.loglik(p) == pytest.approx(want, rel=1e-11)
+    # per-period form == test/modelsetup.jl form
+    lkc = M.CAPMLogLik(lik_data, market, as_written=False)
+    mod = O.Model(M.make_spec(W.three_equation_parameters(), lkc))
+    Xm = np.tile(market.reshape(1, -1), (3, 1))
+    for _ in range(100):
+        p = np.abs(rng.normal(1, 0.5, 9))
+        want = L.orc_loglik_lineq_direct(p, np.ascontiguousarray(lik_data.T).ravel(), np.ascontiguousarray(Xm.T).ravel(), 3,
+                                         lik_data.shape[1])
+        assert mod.loglik(p) == pytest.approx(want, rel=1e-11)
+
+
+def test_cloud_container_layout():
+    c = CL.Cloud.empty(3, 10)
+    assert c.particles.shape == (10, 8) and c.particles.flags.f_contiguous
+    assert (c.stage_index, c.n_Φ, c.resamples, c.c, c.accept) == (1, 0, 0, 0.0, 0.25)      # particle.jl:50-53
+    c.particles[:] = np.arange(80).reshape(10, 8)
+    assert np.array_equal(CL.get_loglh(c), c.particles[:, 3]) and np.array_equal(CL.get_weights(c), c.particles[:, 7])
+    assert CL.get_vals(c).shape == (3, 10) and CL.get_vals(c, transpose=False).shape == (10, 3)
+    CL.update_draws(c, np.ones((3, 10)))
+    assert np.all(c.particles[:, :3] == 1.0)
+    with pytest.raises(ValueError):
+        CL.update_draws(c, np.ones((4, 4)))
+    CL.reset_weights(c)
+    assert np.all(CL.get_weights(c) == 1.0) and len(c) == 10
+
+
+def test_canonical_orders_are_shard_invariant():
+    """The canonical sums are binary trees over power-of-two aligned shards: combining per-shard results
+    in rank order reproduces the single-shard result bit-for-bit (basis of multi-GPU invariance)."""
+    L = O.lib()
+    rng = np.random.default_rng(2)
+    N = 1 << 15
+    x = np.exp(rng.normal(0, 3, N))
+    full = L.orc_canon_sum(x, N)
+    for G in (2, 4, 8):
+        parts = [L.orc_canon_sum(np.ascontiguousarray(x[g * N // G:(g + 1) * N // G]), N // G) for g in range(G)]
+        while len(parts) > 1:
+            parts = [parts[i] + parts[i + 1] for i in range(0, len(parts), 2)]
+        assert parts[0] == full
+    assert abs(full - np.sum(x)) <= 1e-12 * np.sum(x)
+    c = np.zeros(N)
+    L.orc_cumsum(x / full, N, c)
+    np.testing.assert_allclose(c, np.cumsum(x / full), rtol=1e-13)
+    assert abs(c[-1] - 1.0) < 1e-13
+
+
+def test_oracle_stage_loop_recovers_posterior():
+    """Oracle-only end-to-end check of config C1 (regression example, N = 1000): the weighted posterior
+    mean reaches the OLS solution (alpha, beta) = (1, 1) of examples/regression_model."""
+    params, lk, _ = W.regression_example()
+    spec = M.make_spec(params, lk)
+    mod = O.Model(spec)
+    N = 1000
+    P = W.initial_cloud(params, N, np.random.default_rng(0))
+    buf = O.cloud_f(P)
+    O.lib().orc_evaluate(mod.h, buf, N)
+    scratch = np.zeros_like(buf)
+    sched = (np.arange(100) / 99.0) ** 2.1
+    io = O.StageIO(threshold_ratio=0.5, target=0.25, alpha=1.0, tempering_target=0.95, n_mh_steps=1, n_blocks=1,
+                   resample_method=0, adaptive=0, has_old=0, nthreads=0, seed=1, c=0.5, accept=0.25, ess_prev=float(N), j=2)
+    for s in range(99):
+        io.phi_n1, io.phi_n, io.stage = float(sched[s]), float(sched[s + 1]), s + 2
+        assert O.lib().orc_stage(mod.h, buf, scratch, N, sched, 100, C.byref(io), None, None, None, None) == 0
+    got = O.cloud_m(buf, N, 2)
+    mean = np.average(got[:, :2], axis=0, weights=got[:, -1])
+    assert np.allclose(mean, [1.0, 1.0], atol=0.1)
+    assert 0.05 < io.accept < 0.8
