@@ -196,6 +196,10 @@ int64_t smcb200_kernel_launches(const smcb200_ctx *ctx);
 /* last device timings (ms) of the named kernel family measured with CUDA events on the launch stream:
  * which = 0 correct, 1 resample, 2 moments, 3 mutate */
 int32_t smcb200_last_kernel_ms(const smcb200_ctx *ctx, int32_t which, float *ms_out);
+/* CUDA-event stopwatch on the context's launch stream: start records an event, stop records a second
+ * one, synchronises and returns the elapsed device time in milliseconds */
+int32_t smcb200_timer_start(smcb200_ctx *ctx);
+int32_t smcb200_timer_stop(smcb200_ctx *ctx, float *ms_out);
 /* device-side deterministic elementary functions, for parity tests: op 0 exp, 1 log, 2 sin(2 pi x),
  * 3 cos(2 pi x), 4/5 = z0/z1 of normal_pair(seed, particle = i, stage = 0, slot = x[i]) */
 int32_t smcb200_debug_math(smcb200_ctx *ctx, int32_t op, const double *x, int64_t n, uint64_t seed, double *out);

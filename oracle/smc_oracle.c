@@ -836,7 +836,9 @@ ORC_API orc_proposal *orc_proposal_create(int d, int n_free, const double *mean_
         double *S = (double *)malloc(sizeof(double) * (size_t)n * n);
         double *L = (double *)malloc(sizeof(double) * (size_t)n * n);
         for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) S[(size_t)i * n + j] = cov_fr[(size_t)p->mfree[b][i] * n_free + p->mfree[b][j]];
+            for (int j = 0; j < n; ++j)   /* (R + R') / 2, smc_main.jl:462 (exact no-op for symmetric input) */
+                S[(size_t)i * n + j] = (cov_fr[(size_t)p->mfree[b][i] * n_free + p->mfree[b][j]] +
+                                        cov_fr[(size_t)p->mfree[b][j] * n_free + p->mfree[b][i]]) / 2.0;
         int st = orc_cholesky(S, n, L);
         if (st) { *status = 4; free(S); free(L); orc_proposal_free(p); return NULL; }
         p->Lc[b] = (double *)malloc(sizeof(double) * (size_t)n * n);

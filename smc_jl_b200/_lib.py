@@ -88,6 +88,8 @@ def _load():
                                      C.POINTER(StageResult)]),
         "smcb200_kernel_launches": (i64, [vp]),
         "smcb200_last_kernel_ms": (i32, [vp, i32, C.POINTER(C.c_float)]),
+        "smcb200_timer_start": (i32, [vp]),
+        "smcb200_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
         "smcb200_debug_math": (i32, [vp, i32, vp, i64, u64, vp]),
     }
     for name, (res, args) in sig.items():

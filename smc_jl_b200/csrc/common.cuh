@@ -102,6 +102,7 @@ struct Ctx {
     long long launches = 0;
     float last_ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev[8]{};
+    cudaEvent_t tev[2]{};
     std::string err;
 };
 

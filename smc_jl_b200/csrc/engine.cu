@@ -29,6 +29,7 @@ void free_cloud(Ctx* c)
     cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
     c->cloud[0] = c->cloud[1] = c->tmp = c->rmax = nullptr; c->idx = nullptr; c->partials = c->mpartials = nullptr;
     c->scan_blocktot = c->scan_blockoff = c->scan_levels = c->scan_bmax = nullptr; c->msum = c->csum = nullptr;
+    c->scan_nb_cap = 0;
     c->N = c->N_global = 0;
 }
 
@@ -281,6 +282,7 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     ok = ok && cudaMallocHost(&c->h_status, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_moments, sizeof(double) * (1 + DMAX + PACKMAX)) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&c->tev[i]) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     if (!ok) { smcb200_destroy(c); return SMCB200_ERR_CUDA; }
@@ -299,6 +301,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SMCB200_OK;
@@ -760,6 +763,24 @@ int32_t smcb200_last_kernel_ms(const smcb200_ctx* c, int32_t which, float* ms)
 {
     if (!c || which < 0 || which > 3 || !ms) return SMCB200_ERR_BAD_ARGUMENT;
     *ms = c->last_ms[which];
+    return SMCB200_OK;
+}
+
+int32_t smcb200_timer_start(smcb200_ctx* c)
+{
+    if (!c) return SMCB200_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    SMC_CUDA(c, cudaEventRecord(c->tev[0], c->stream));
+    return SMCB200_OK;
+}
+
+int32_t smcb200_timer_stop(smcb200_ctx* c, float* ms)
+{
+    if (!c || !ms) return SMCB200_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    SMC_CUDA(c, cudaEventRecord(c->tev[1], c->stream));
+    SMC_CUDA(c, cudaEventSynchronize(c->tev[1]));
+    SMC_CUDA(c, cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
     return SMCB200_OK;
 }
 

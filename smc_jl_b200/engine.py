@@ -202,6 +202,14 @@ class Engine:
         self._ck(lib.smcb200_last_kernel_ms(self.h, which, C.byref(ms)))
         return ms.value
 
+    def timer_start(self):
+        self._ck(lib.smcb200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(lib.smcb200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def debug_math(self, op, x, seed=0):
         x = _f64(x)
         out = np.zeros_like(x)

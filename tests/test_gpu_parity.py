@@ -378,7 +378,7 @@ def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False):
 def test_stage_trajectory_linear_gaussian_bitexact(eng):
     """C2-shaped run (d = 20, n_mh = 3, fixed schedule) at a size the oracle finishes in seconds: identical
     phi/ESS/c/accept trajectory, identical resample decisions, identical clouds after every stage."""
-    params, lk, _ = W.linear_gaussian(d=20, T=256)
+    params, lk, _ = W.linear_gaussian(d=20, T=256, prior_sd=1.0)   # 40-point schedule: a N(0,10) prior would collapse the ESS
     spec = M.make_spec(params, lk)
     N = 8192
     P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(7))
