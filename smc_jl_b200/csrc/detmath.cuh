@@ -18,6 +18,37 @@
 
 namespace smc {
 
+// Polynomial / reduction constants.  On the device they live in __constant__ memory (one LDCU.128
+// brings two of them into uniform registers; as immediates each would cost two UMOVs per use);
+// on the host they are the same literals.
+#define SMC_DM_COEFS(X)                                                                               \
+    X(1.4426950408889634074) X(6755399441055744.0) X(6.93147180369123816490e-01)                      \
+    X(1.90821492927058770002e-10) /* 0-3: log2(e), 1.5*2^52, ln2_hi, ln2_lo */                        \
+    X(1.6059043836821613e-10) X(2.08767569878681e-09) X(2.505210838544172e-08)                        \
+    X(2.755731922398589e-07) X(2.7557319223985893e-06) X(2.48015873015873e-05)                        \
+    X(1.984126984126984e-04) X(1.388888888888889e-03) X(8.333333333333333e-03)                        \
+    X(4.1666666666666664e-02) X(1.6666666666666666e-01) /* 4-14: 1/13! .. 1/3! */                     \
+    X(6.666666666666735130e-01) X(3.999999999940941908e-01) X(2.857142874366239149e-01)               \
+    X(2.222219843214978396e-01) X(1.818357216161805012e-01) X(1.531383769920937332e-01)               \
+    X(1.479819860511658591e-01) /* 15-21: Lg1..Lg7 */                                                 \
+    X(-1.66666666666666324348e-01) X(8.33333333332248946124e-03) X(-1.98412698298579493134e-04)       \
+    X(2.75573137070700676789e-06) X(-2.50507602534068634195e-08) X(1.58969099521155010221e-10)        \
+    /* 22-27: S1..S6 */                                                                               \
+    X(4.16666666666666019037e-02) X(-1.38888888888741095749e-03) X(2.48015872894767294178e-05)        \
+    X(-2.75573143513906633035e-07) X(2.08757232129817482790e-09) X(-1.13596475577881948265e-11)       \
+    /* 28-33: C1..C6 */                                                                               \
+    X(7.85398163397448278999e-01) /* 34: pi/4 */
+#define SMC_DM_VAL(v) v,
+#if defined(__CUDACC__)
+static __constant__ double dm_coef_dev[] = {SMC_DM_COEFS(SMC_DM_VAL)};
+#endif
+static constexpr double dm_coef_host[] = {SMC_DM_COEFS(SMC_DM_VAL)};
+#if defined(__CUDA_ARCH__)
+#define DMC(i) dm_coef_dev[i]
+#else
+#define DMC(i) dm_coef_host[i]
+#endif
+
 SMC_HD double bits_to_double(uint64_t u)
 {
 #if defined(__CUDA_ARCH__)
@@ -50,22 +81,22 @@ SMC_HD double det_exp(double x)
     if (x != x) return x;
     if (x > 709.782712893384) return dinf();
     if (x < -745.1332191019412) return 0.0;
-    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
-    const double kd = t - 6755399441055744.0;
+    const double t = fma(x, DMC(0), DMC(1));
+    const double kd = t - DMC(1);
     int k = (int)kd;
-    double r = fma(-kd, 6.93147180369123816490e-01, x);
-    r = fma(-kd, 1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 1.984126984126984e-04);
-    p = fma(p, r, 1.388888888888889e-03);
-    p = fma(p, r, 8.333333333333333e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
+    double r = fma(-kd, DMC(2), x);
+    r = fma(-kd, DMC(3), r);
+    double p = DMC(4);
+    p = fma(p, r, DMC(5));
+    p = fma(p, r, DMC(6));
+    p = fma(p, r, DMC(7));
+    p = fma(p, r, DMC(8));
+    p = fma(p, r, DMC(9));
+    p = fma(p, r, DMC(10));
+    p = fma(p, r, DMC(11));
+    p = fma(p, r, DMC(12));
+    p = fma(p, r, DMC(13));
+    p = fma(p, r, DMC(14));
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
@@ -75,37 +106,44 @@ SMC_HD double det_exp(double x)
 }
 
 // log(x): fdlibm-style reduction x = 2^k (1+f), s = f/(2+f), degree-14 odd series in s.
-SMC_HD double det_log(double x)
+// Core for positive, finite, NORMAL x given as bits (k0 = exponent adjustment already applied).
+SMC_HD double det_log_core(uint64_t ix, int k)
 {
-    uint64_t ix = double_to_bits(x);
     int32_t hx = (int32_t)(ix >> 32);
-    const uint32_t lx = (uint32_t)ix;
-    int k = 0;
-    if (hx < 0x00100000) {
-        if (((hx & 0x7fffffff) | lx) == 0) return -dinf();
-        if (hx < 0) return dnan();
-        k -= 54; x *= 0x1p54; ix = double_to_bits(x); hx = (int32_t)(ix >> 32);
-    }
-    if (hx >= 0x7ff00000) return x + x;
     k += (hx >> 20) - 1023;
     hx &= 0x000fffff;
     const int32_t i = (hx + 0x95f64) & 0x100000;
     ix = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (ix & 0xffffffffull);
-    x = bits_to_double(ix);
+    const double x = bits_to_double(ix);
     k += (i >> 20);
     const double dk = (double)k;
     const double f = x - 1.0;
     const double s = f / (2.0 + f);
     const double z = s * s;
     const double w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
-                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double t1 = w * fma(w, fma(w, DMC(20), DMC(18)), DMC(16));
+    const double t2 = z * fma(w, fma(w, fma(w, DMC(21), DMC(19)), DMC(17)), DMC(15));
     const double R = t2 + t1;
     const double hfsq = 0.5 * f * f;
-    const double u = fma(s, hfsq + R, dk * 1.90821492927058770002e-10);
-    return fma(dk, 6.93147180369123816490e-01, -((hfsq - u) - f));
+    const double u = fma(s, hfsq + R, dk * DMC(3));
+    return fma(dk, DMC(2), -((hfsq - u) - f));
 }
+SMC_HD double det_log(double x)
+{
+    uint64_t ix = double_to_bits(x);
+    const int32_t hx = (int32_t)(ix >> 32);
+    const uint32_t lx = (uint32_t)ix;
+    int k = 0;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -dinf();
+        if (hx < 0) return dnan();
+        k -= 54; x *= 0x1p54; ix = double_to_bits(x);
+    }
+    if ((int32_t)(ix >> 32) >= 0x7ff00000) return x + x;
+    return det_log_core(ix, k);
+}
+// same value as det_log(x) for positive finite normal x (no special-case branches)
+SMC_HD double det_log_normal(double x) { return det_log_core(double_to_bits(x), 0); }
 
 // sin(2*pi*u), cos(2*pi*u) for u in [0,1): exact octant split, fdlibm kernels on [0, pi/4].
 SMC_HD void det_sincos2pi(double u, double& sn, double& cs)
@@ -114,15 +152,11 @@ SMC_HD void det_sincos2pi(double u, double& sn, double& cs)
     const int o = (int)t;
     const double f = t - (double)o;
     const double g = (o & 1) ? (1.0 - f) : f;
-    const double x = g * 7.85398163397448278999e-01;
+    const double x = g * DMC(34);
     const double z = x * x;
-    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
-                                               2.75573137070700676789e-06), -1.98412698298579493134e-04),
-                                 8.33333333332248946124e-03), -1.66666666666666324348e-01);
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, DMC(27), DMC(26)), DMC(25)), DMC(24)), DMC(23)), DMC(22));
     const double s = fma(x * z, ps, x);
-    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
-                                               -2.75573143513906633035e-07), 2.48015872894767294178e-05),
-                                 -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, DMC(33), DMC(32)), DMC(31)), DMC(30)), DMC(29)), DMC(28));
     const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
     const double sp = (o & 1) ? c : s;
     const double cp = (o & 1) ? s : c;
@@ -178,7 +212,7 @@ SMC_HD void normal_pair(u32x4 r, double& z0, double& z1)
 {
     const double u1 = u01_open0(r.x, r.y);
     const double u2 = u01(r.z, r.w);
-    const double rad = sqrt(-2.0 * det_log(u1));
+    const double rad = sqrt(-2.0 * det_log_normal(u1));   // u1 in [2^-53, 1]: always normal
     double sn, cs;
     det_sincos2pi(u2, sn, cs);
     z0 = rad * cs;

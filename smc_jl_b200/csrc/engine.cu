@@ -153,7 +153,7 @@ int launch_moments(Ctx* c)
     const Tiles t = moment_tiles(c->N);
     const int E = d * (d + 1) / 2;
     double* part = c->mpartials;  // [max(1+d, E)][P] -- sized at cloud creation
-    k_moments1<<<t.ntiles, 32, 0, c->stream>>>(cl, c->N, d, part, t.P);
+    k_moments1<<<dim3(t.ntiles, (d + 4) / 4), 128, 0, c->stream>>>(cl, c->N, d, part, t.P);
     k_tree_finalize<<<1 + d, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->msum);
     switch (d) {
     case 2: launch_m2<2>(c, cl, part, t); break;
@@ -720,8 +720,7 @@ int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_s
     for (int a = 0; a < c->n_free; ++a) ball[a] = c->free_idx[perm[a]];
     BlockSpec bs;
     st = make_blockspec(c, cfg->n_blocks, sizes, ball, &bs); if (st) return st;
-    double* work = reinterpret_cast<double*>(c->mutc_dev + 1);
-    k_prepare_proposal<<<1, 32, 0, c->stream>>>(c->msum, c->csum, bs, state->c, c->mutc_dev, work, c->status_dev);
+    k_prepare_proposal<<<1, 32, 0, c->stream>>>(c->msum, c->csum, bs, state->c, c->mutc_dev, c->status_dev);
     c->launches += 1;
     c->mutc_host->n_blocks = cfg->n_blocks;
     st = mutate_upload_proposal(c, true); if (st) return st;

@@ -408,23 +408,39 @@ k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t
 // then the tile tree.  One warp per tile.
 // =================================================================================================
 // pass 1: msum[0] = sum w, msum[1+k] = sum w x_k.  partials layout [1+d][P].
-__global__ void __launch_bounds__(32)
+// One warp per (tile, quantity): grid = (ntiles, ceil((1+d)/4)), 4 warps per block; the weight column is
+// re-read by every warp of a tile from L1/L2.
+__global__ void __launch_bounds__(128)
 k_moments1(const double* __restrict__ cloud, int64_t N, int d, double* __restrict__ partials, int P)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (q > d) return;
     const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
-    const double* w = cloud + col_off(N, d + 4);
-    for (int q = 0; q <= d; ++q) {
-        const double* x = (q == 0) ? nullptr : cloud + col_off(N, q - 1);
-        double acc = 0.0;
-#pragma unroll 8
+    const double* __restrict__ w = cloud + col_off(N, d + 4);
+    const double* __restrict__ x = (q == 0) ? nullptr : cloud + col_off(N, q - 1);
+    double acc = 0.0;
+    if (base + (int64_t)(M_R - 1) * M_LANES < N) {          // full tile: all loads issued up front
+        double wv[16], xv[16];
+#pragma unroll
+        for (int r0 = 0; r0 < M_R; r0 += 16) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int64_t i = base + (int64_t)(r0 + r) * M_LANES;
+                wv[r] = w[i];
+                xv[r] = x ? x[i] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc = x ? fma(wv[r], xv[r], acc) : acc + wv[r];
+        }
+    } else {
         for (int r = 0; r < M_R; ++r) {
             const int64_t i = base + (int64_t)r * M_LANES;
             if (i < N) acc = x ? fma(w[i], x[i], acc) : acc + w[i];
         }
-        acc = warp_tree(acc);
-        if (lane == 0) partials[(size_t)q * P + blockIdx.x] = acc;
     }
+    acc = warp_tree(acc);
+    if (lane == 0) partials[(size_t)q * P + blockIdx.x] = acc;
 }
 
 // pass 2: csum[a(a+1)/2 + b] = sum_i (w_i (x_ia - mean_a)) (x_ib - mean_b), b <= a.
@@ -553,24 +569,71 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
     return 0;
 }
 
-__global__ void k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ csum, BlockSpec bs,
-                                   double c, MutConst* out, double* work /* (3*DMAX*DMAX + DMAX) doubles */,
-                                   int* status)
+// One warp.  Same per-element arithmetic as build_mutconst()/cholesky_lower() (each L_ij is the same
+// fma chain over k ascending), evaluated column by column with one lane per row.
+__global__ void __launch_bounds__(32)
+k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ csum, BlockSpec bs, double c,
+                   MutConst* out, int* status)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double cov[DMAX][DMAX + 1];
+    __shared__ double S[DMAX][DMAX + 1];
+    __shared__ double L[DMAX][DMAX + 1];
+    const int lane = threadIdx.x;
     const int d = bs.d;
-    double* mean = work;
-    double* cov = work + DMAX;
     const double sw = msum[0];
-    for (int k = 0; k < d; ++k) mean[k] = msum[1 + k] / sw;
-    for (int a = 0; a < d; ++a)
-        for (int b = 0; b <= a; ++b) {
-            const double v = csum[a * (a + 1) / 2 + b] / sw;
-            cov[a * d + b] = v;
-            cov[b * d + a] = v;
+    if (lane == 0) { out->n_blocks = bs.n_blocks; out->status = 0; }
+    out->mu[lane] = (lane < d) ? msum[1 + lane] / sw : 0.0;
+    for (int e = lane; e < d * (d + 1) / 2; e += 32) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int b = e - a * (a + 1) / 2;
+        const double v = csum[e] / sw;
+        cov[a][b] = v;
+        cov[b][a] = v;
+    }
+    __syncwarp();
+    for (int b = 0; b < bs.n_blocks; ++b) {
+        const int n = bs.bsize[b];
+        for (int e = lane; e < PACKMAX; e += 32) out->L[b][e] = 0.0;
+        out->csd[b][lane] = 0.0;
+        uint32_t mask = 0;
+        for (int i = 0; i < n; ++i) mask |= 1u << bs.member[b][i];
+        if (lane == 0) { out->mask[b] = mask; out->bsize[b] = n; }
+        const int ai = (lane < n) ? bs.member[b][lane] : 0;
+        if (lane < n)
+            for (int j = 0; j < n; ++j) {
+                const int aj = bs.member[b][j];
+                S[lane][j] = (cov[ai][aj] + cov[aj][ai]) / 2.0;      // R_fr = (R + R') / 2, smc_main.jl:462
+            }
+        __syncwarp();
+        bool bad = false;
+        for (int j = 0; j < n; ++j) {
+            double sv = 0.0;
+            if (lane >= j && lane < n) {
+                sv = S[lane][j];
+                for (int k = 0; k < j; ++k) sv = fma(-L[lane][k], L[j][k], sv);
+            }
+            const double sj = __shfl_sync(0xffffffffu, sv, j);
+            if (!(sj > 0.0)) { bad = true; break; }
+            const double dj = sqrt(sj);
+            if (lane == j) L[j][j] = dj;
+            else if (lane > j && lane < n) L[lane][j] = sv / dj;
+            __syncwarp();
         }
-    const int st = build_mutconst(mean, cov, d, bs, c, out, work + DMAX + DMAX * DMAX);
-    if (st) *status = st;
+        if (bad) {
+            if (lane == 0) { out->status = SMCB200_ERR_NOT_POSDEF; *status = SMCB200_ERR_NOT_POSDEF; }
+            return;
+        }
+        __syncwarp();
+        if (lane < n) {
+            for (int j = 0; j <= lane; ++j) {
+                const int aj = bs.member[b][j];
+                out->L[b][ai * (ai + 1) / 2 + aj] = c * L[lane][j];
+            }
+            out->csd[b][ai] = c * sqrt(S[lane][lane]);
+        }
+        __syncwarp();
+    }
 }
 
 // debug: elementwise deterministic math on the device

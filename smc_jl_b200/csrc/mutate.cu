@@ -119,21 +119,31 @@ struct MutArgs {
     uint32_t stage;
 };
 
-// One MH chain per thread.  SINGLE = (n_blocks == 1): block index is a literal, so every factor entry
-// is an immediate constant-bank operand.
+// One MH chain per thread.  The chain's current state lives in shared memory ([2][D][128] doubles:
+// current and candidate buffer, thread-private columns => conflict-free); registers hold only the working
+// vector, which is in turn the proposal increment, the candidate and (inside the likelihood) the centred
+// candidate.  Accepting a move flips which buffer is current.  This keeps the kernel under ~100 registers
+// (5 blocks = 20 warps per SM) -- it is FP64-latency bound, so resident warps are what buys throughput.
+// SINGLE = (n_blocks == 1): block index is a literal, so factor entries load as LDCU.128 pairs.
+constexpr int MUT_THREADS = 128;
+
 template <class LIK, bool HAS_OLD, bool SINGLE>
-__global__ void __launch_bounds__(128) k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
+__global__ void __launch_bounds__(MUT_THREADS, (LIK::D <= 20) ? 5 : ((LIK::D <= 24) ? 4 : 3))
+k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 {
     constexpr int D = LIK::D;
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    extern __shared__ double sm_state[];
+    const int64_t i = (int64_t)blockIdx.x * MUT_THREADS + threadIdx.x;
     if (i >= N) return;
-    double th[D];
+    double* buf0 = sm_state + threadIdx.x;
+    double* buf1 = sm_state + D * MUT_THREADS + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < D; ++k) th[k] = cloud[col_off(N, k) + i];
+    for (int k = 0; k < D; ++k) buf0[k * MUT_THREADS] = cloud[col_off(N, k) + i];
     double like = cloud[col_off(N, D) + i];
     double lpri = cloud[col_off(N, D + 1) + i];
     double lprev = cloud[col_off(N, D + 2) + i];
     double accept = 0.0;
+    bool flipped = false;
     const uint32_t gp = (uint32_t)(index0 + i);
     const double phi = a.phi_n, omphi = 1.0 - a.phi_n;
     const int nb = SINGLE ? 1 : a.n_blocks;
@@ -142,8 +152,6 @@ __global__ void __launch_bounds__(128) k_mutate(double* __restrict__ cloud, int6
         for (int bb = 0; bb < nb; ++bb) {
             const int b = SINGLE ? 0 : bb;
             const uint32_t sb = (uint32_t)(step * nb + b);
-            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
-            const double step_prob = u01(r4.x, r4.y);
             const uint32_t mask = c_mut.mask[b];
             double s[D];
 #pragma unroll
@@ -166,8 +174,14 @@ __global__ void __launch_bounds__(128) k_mutate(double* __restrict__ cloud, int6
                     }
                 }
             }
+            const double* cur = flipped ? buf1 : buf0;
+            double* cand = flipped ? buf0 : buf1;
 #pragma unroll
-            for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? th[k] + s[k] : th[k];   // s is now theta'
+            for (int k = 0; k < D; ++k) {
+                const double t = cur[k * MUT_THREADS];
+                s[k] = ((mask >> k) & 1u) ? t + s[k] : t;              // s is now theta'
+                cand[k * MUT_THREADS] = s[k];
+            }
             const bool ok = in_bounds<D>(s);
             double pn = logprior<D>(s);
             double ln = LIK::template ll<0>(s);
@@ -176,16 +190,18 @@ __global__ void __launch_bounds__(128) k_mutate(double* __restrict__ cloud, int6
             if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
             // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
             const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + 0.0);
+            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
+            const double step_prob = u01(r4.x, r4.y);
             if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
-#pragma unroll
-                for (int k = 0; k < D; ++k) th[k] = s[k];
+                flipped = !flipped;
                 like = ln; lpri = pn; lprev = lo;
                 accept += (double)c_mut.bsize[b];
             }
         }
     }
+    const double* cur = flipped ? buf1 : buf0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = th[k];
+    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = cur[k * MUT_THREADS];
     cloud[col_off(N, D) + i] = like;
     cloud[col_off(N, D + 1) + i] = lpri;
     cloud[col_off(N, D + 2) + i] = lprev;
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(128) k_evaluate(double* __restrict__ cloud, in
 
 // ---- dispatch ------------------------------------------------------------------------------------
 struct KernelEntry {
-    int neq, k, stride, coef, sig;
+    int neq, k, stride, coef, sig, d;
     void (*mut[2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single]
     void (*eval)(double*, int64_t, int);
 };
@@ -223,7 +239,7 @@ template <class LIK>
 static KernelEntry make_entry()
 {
     KernelEntry e;
-    e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG;
+    e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
     e.mut[0][0] = k_mutate<LIK, false, false>;
     e.mut[0][1] = k_mutate<LIK, false, true>;
     e.mut[1][0] = k_mutate<LIK, true, false>;
@@ -303,8 +319,12 @@ int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t
     a.phi_n = phi_n; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
     a.seed = seed; a.stage = stage;
     const bool single = (a.n_blocks == 1);
-    const unsigned grid = (unsigned)((ctx->N + 127) / 128);
-    e->mut[has_old ? 1 : 0][single ? 1 : 0]<<<grid, 128, 0, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);
+    const unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
+    const size_t smem = sizeof(double) * 2 * (size_t)e->d * MUT_THREADS;
+    auto kern = e->mut[has_old ? 1 : 0][single ? 1 : 0];
+    if (smem > 48 * 1024)
+        SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, MUT_THREADS, smem, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);
     ctx->launches++;
     SMC_CUDA(ctx, cudaGetLastError());
     return SMCB200_OK;
