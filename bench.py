@@ -41,23 +41,42 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, ~2 ms period; falls back to
+    polling nvidia-smi when pynvml is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+        self.index, self.sm, self.reason_bits, self.max_mhz = index, [], 0, None
+        self.smi_rows, self.stop, self.th, self.nv = [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nv is not None:
+                    self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)))
+                    try:
+                        self.reason_bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        self.reason_bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.stop.wait(0.002)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.smi_rows.append([x.strip() for x in out.split(",")])
+                    self.stop.wait(0.05)
             except Exception:
-                pass
-            self.stop.wait(0.1)
+                self.stop.wait(0.01)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -69,12 +88,17 @@ class ClockSampler:
         self.th.join(timeout=10)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        if self.nv is not None and self.sm:
+            sm = sorted(self.sm)
+            reasons = [n for n, b in self.BITS.items() if self.reason_bits & b]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "via": "nvml"}
+        if self.smi_rows:
+            sm = sorted(float(r[0]) for r in self.smi_rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.smi_rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.smi_rows[0][1]), "reasons": reasons, "samples": len(sm),
+                    "via": "nvidia-smi"}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "samples": 0}
 
 
 def schedule():
@@ -268,7 +292,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

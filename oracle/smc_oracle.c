@@ -26,7 +26,7 @@
  *   - exp/log/sincos are the fixed polynomial algorithms below (<= ~1 ulp of libm), so that the
  *     device and this file agree bit-for-bit; the reference's libm differs from them by <= 2 ulp.
  *   - Reductions use fixed, shard-invariant orders: canon_sum (strided-sequential then adjacent-
- *     pair binary tree) and cumsum_pairwise64 (Julia-style pairwise accumulate: 64-element
+ *     pair binary tree) and the pairwise cumsum (Julia-style pairwise accumulate: 16-element
  *     sequential leaves, tree totals, top-down offsets).  Julia's own `sum`/`cumsum` orders are
  *     SIMD-/length-dependent and not bit-portable; ours are a fixed member of the same family.
  *   - Randomness: Philox4x32-10 keyed by the engine seed, counter = (global particle, stage,
@@ -273,13 +273,13 @@ ORC_API double orc_canon_sumsq(const double *x, i64 n) { return canon_sum_fn(ter
 ORC_API double orc_canon_sum_generic(const double *x, i64 n, int lanes, int R) { return canon_sum_fn(term_plain, (void *)x, n, lanes, R); }
 
 /* Julia-style pairwise inclusive cumsum (cf. Base.accumulate_pairwise!, leaf < 128) on a
- * zero-padded power-of-two length with fixed 64-element sequential leaves:
+ * zero-padded power-of-two length with fixed 16-element sequential leaves:
  *   total(leaf)   = sequential sum of the leaf
  *   total(node)   = total(left) + total(right)
  *   offset(root)  = 0; offset(left) = offset(node); offset(right) = offset(node) + total(left)
  *   c[i]          = offset(leaf(i)) + running_sum_within_leaf(i)
  */
-#define LEAF 64
+#define LEAF 16
 static double cs_total(const double *x, i64 n, i64 lo, i64 len)
 {
     if (len == LEAF) {
@@ -512,6 +512,7 @@ ORC_API double orc_update_c(double c, double accept, double target)
 /* ------------------------------------------------------------------------------------------ */
 #define M_LANES 32
 #define M_R 64
+#define M2_CH 512
 struct wx_ctx { const double *w, *x, *y; double mx, my, sw; };
 ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double *cov)
 {
@@ -540,28 +541,27 @@ ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double
     double sw = tree_inplace(tiles, P);
     for (int k = 0; k < d; ++k) mean[k] = tree_inplace(tiles + (size_t)(k + 1) * P, P) / sw;
     free(tiles);
-    /* pass 2: centred weighted scatter, lower triangle, then / Sw; symmetric by construction */
-    double *tl = (double *)calloc((size_t)P, sizeof(double));
+    /* pass 2: centred weighted scatter, lower triangle, then / Sw; symmetric by construction.
+     * Canonical order: sequential fma over each chunk of M2_CH consecutive particles, then the
+     * adjacent-pair tree over chunks (zero padded to a power of two). */
+    i64 nch = (N + M2_CH - 1) / M2_CH;
+    i64 Pc = next_pow2(nch < 1 ? 1 : nch);
+    double *tl = (double *)calloc((size_t)Pc, sizeof(double));
     for (int a = 0; a < d; ++a) {
         const double *xa = COL(cloud, N, a);
         for (int b = 0; b <= a; ++b) {
             const double *xb = COL(cloud, N, b);
-            memset(tl, 0, sizeof(double) * (size_t)P);
-            for (i64 t = 0; t < nt; ++t) {
-                for (int l = 0; l < M_LANES; ++l) {
-                    double acc = 0.0;
-                    for (int r = 0; r < M_R; ++r) {
-                        i64 i = t * tile + (i64)r * M_LANES + l;
-                        if (i < N) {
-                            double da = xa[i] - mean[a], db = xb[i] - mean[b];
-                            acc = FMA(w[i] * da, db, acc);
-                        }
-                    }
-                    lane[l] = acc;
+            memset(tl, 0, sizeof(double) * (size_t)Pc);
+            for (i64 c = 0; c < nch; ++c) {
+                double acc = 0.0;
+                i64 hi = (c + 1) * M2_CH < N ? (c + 1) * M2_CH : N;
+                for (i64 i = c * M2_CH; i < hi; ++i) {
+                    double da = xa[i] - mean[a], db = xb[i] - mean[b];
+                    acc = FMA(w[i] * da, db, acc);
                 }
-                tl[t] = tree_inplace(lane, M_LANES);
+                tl[c] = acc;
             }
-            double v = tree_inplace(tl, P) / sw;
+            double v = tree_inplace(tl, Pc) / sw;
             cov[(size_t)a * d + b] = v;
             cov[(size_t)b * d + a] = v;
         }

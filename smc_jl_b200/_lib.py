@@ -11,7 +11,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmcb200.so")
+LIB_PATH = os.environ.get("SMCB200_LIB", os.path.join(_HERE, "libsmcb200.so"))   # env override: developer experiments only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "smcb200.h")
 
 OK, ERR_NAN_ESS, ERR_BAD_RESAMPLER, ERR_BAD_ARGUMENT, ERR_NOT_POSDEF, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED, ERR_NOT_READY = range(9)

@@ -13,9 +13,10 @@ namespace smc {
 
 // ---- canonical reduction orders (DESIGN.md "Numerical contract"; mirrored by the oracle) --------
 constexpr int W_LANES = 256, W_R = 4, W_TILE = W_LANES * W_R;      // weight-type sums
-constexpr int M_LANES = 32, M_R = 64, M_TILE = M_LANES * M_R;      // moment-type sums
-constexpr int LEAF = 64;                                           // cumsum leaf (sequential)
-constexpr int SCAN_THREADS = 128, SCAN_TILE = SCAN_THREADS * LEAF; // cumsum block tile
+constexpr int M_LANES = 32, M_R = 64, M_TILE = M_LANES * M_R;      // moment-type sums (pass 1)
+constexpr int M2_CH = 512;                                         // scatter-matrix chunk (sequential fma)
+constexpr int LEAF = 16;                                           // cumsum leaf (sequential)
+constexpr int SCAN_THREADS = 256, SCAN_TILE = SCAN_THREADS * LEAF; // cumsum block tile
 
 constexpr int DMAX = 32;               // max n_para with a device mutation kernel
 constexpr int NBMAX = 8;               // max n_blocks
@@ -76,7 +77,7 @@ struct Ctx {
     int64_t* idx = nullptr;        // N
     double* partials = nullptr;    // tile partial sums, weight-type orders  [6][P_w]
     double* mpartials = nullptr;   // tile partial sums, moment-type orders  [max(1+d, E)][P_m]
-    size_t partials_len = 0;
+    size_t partials_len = 0, partials_len_m = 0;
     unsigned* counters = nullptr;  // last-block counters
     double* scal = nullptr;        // SC_COUNT device scalars
     double* h_scal = nullptr;      // pinned mirror

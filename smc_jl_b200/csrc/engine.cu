@@ -74,7 +74,7 @@ ScanGeom scan_geom(int64_t n)
     g.nb = (int)(g.P / g.B);
     return g;
 }
-constexpr size_t SCAN_SMEM = (size_t)(SCAN_THREADS * 65 + 2 * SCAN_THREADS + SCAN_THREADS) * sizeof(double);
+constexpr size_t SCAN_SMEM = (size_t)(SCAN_THREADS * (LEAF + 1) + 2 * SCAN_THREADS + SCAN_THREADS) * sizeof(double);
 
 int ensure_scan_buffers(Ctx* c, int nb)
 {
@@ -108,7 +108,7 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
     k_scan_upper<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scan_blockoff);
     k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
                                                              craw, c->scan_bmax);
-    k_prefix_max<<<1, 32, 0, c->stream>>>(c->scan_bmax, g.nb);
+    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, g.nb);
     double u = u_override;
     if (!(u >= 0.0)) {
         const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
@@ -138,12 +138,16 @@ int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, dou
 }
 
 // ---- moments ------------------------------------------------------------------------------------------
+Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+
 template <int D>
-void launch_m2(Ctx* c, const double* cl, double* partials, const Tiles& t)
+int launch_m2(Ctx* c, const double* cl, double* partials, const Tiles& t)
 {
-    constexpr int E = D * (D + 1) / 2;
-    constexpr int SLABS = (E + 55) / 56 > 8 ? 8 : (E + 55) / 56;
-    k_moments2<D, SLABS><<<t.ntiles, 32 * SLABS, 0, c->stream>>>(cl, c->N, c->msum, partials, t.P);
+    const size_t smem = sizeof(double) * M2_WARPS * 32 * M2Cfg<D>::STRIDE;
+    if (smem > 48 * 1024)
+        SMC_CUDA(c, cudaFuncSetAttribute(k_moments2<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_moments2<D><<<(t.ntiles + M2_WARPS - 1) / M2_WARPS, 32 * M2_WARPS, smem, c->stream>>>(cl, c->N, c->msum, partials, t.P);
+    return SMCB200_OK;
 }
 
 int launch_moments(Ctx* c)
@@ -151,18 +155,35 @@ int launch_moments(Ctx* c)
     const int d = c->d;
     const double* cl = c->cloud[c->cur];
     const Tiles t = moment_tiles(c->N);
+    const Tiles tc = chunk_tiles(c->N);
     const int E = d * (d + 1) / 2;
-    double* part = c->mpartials;  // [max(1+d, E)][P] -- sized at cloud creation
+    double* part = c->mpartials;  // max([1+d][P_m], [E][P_c]) -- sized at cloud creation
     k_moments1<<<dim3(t.ntiles, (d + 4) / 4), 128, 0, c->stream>>>(cl, c->N, d, part, t.P);
     k_tree_finalize<<<1 + d, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->msum);
+    // pass 2 reuses the partial buffer with the chunk geometry: clear the zero padding it relies on
+    if (tc.ntiles < tc.P || t.ntiles < t.P)
+        SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * c->partials_len_m, c->stream));
+    int st = SMCB200_OK;
     switch (d) {
-    case 2: launch_m2<2>(c, cl, part, t); break;
-    case 9: launch_m2<9>(c, cl, part, t); break;
-    case 16: launch_m2<16>(c, cl, part, t); break;
-    case 20: launch_m2<20>(c, cl, part, t); break;
-    default: k_moments2_generic<<<t.ntiles, 32, 0, c->stream>>>(cl, c->N, d, c->msum, part, t.P); break;
+    case 2: st = launch_m2<2>(c, cl, part, tc); break;
+    case 3: st = launch_m2<3>(c, cl, part, tc); break;
+    case 4: st = launch_m2<4>(c, cl, part, tc); break;
+    case 5: st = launch_m2<5>(c, cl, part, tc); break;
+    case 6: st = launch_m2<6>(c, cl, part, tc); break;
+    case 8: st = launch_m2<8>(c, cl, part, tc); break;
+    case 9: st = launch_m2<9>(c, cl, part, tc); break;
+    case 10: st = launch_m2<10>(c, cl, part, tc); break;
+    case 12: st = launch_m2<12>(c, cl, part, tc); break;
+    case 16: st = launch_m2<16>(c, cl, part, tc); break;
+    case 20: st = launch_m2<20>(c, cl, part, tc); break;
+    case 24: st = launch_m2<24>(c, cl, part, tc); break;
+    case 32: st = launch_m2<32>(c, cl, part, tc); break;
+    default: k_moments2_generic<<<tc.ntiles, 32, 0, c->stream>>>(cl, c->N, d, c->msum, part, tc.P); break;
     }
-    k_tree_finalize<<<E, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->csum);
+    if (st) return st;
+    k_tree_finalize<<<E, 256, 0, c->stream>>>(part, tc.ntiles, tc.P, c->csum);
+    if (tc.ntiles < tc.P || t.ntiles < t.P)
+        SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * c->partials_len_m, c->stream));
     c->launches += 4;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
@@ -344,7 +365,10 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     const Tiles tw = weight_tiles(c->N), tm = moment_tiles(c->N);
     const int E = n_para * (n_para + 1) / 2;
     const size_t len = (size_t)6 * tw.P;
-    const size_t lm = (size_t)((E > n_para + 1) ? E : n_para + 1) * tm.P;
+    const Tiles tch = chunk_tiles(c->N);
+    size_t lm = (size_t)(n_para + 1) * tm.P;
+    if ((size_t)E * tch.P > lm) lm = (size_t)E * tch.P;
+    c->partials_len_m = lm;
     c->partials_len = len;
     SMC_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * len));
     SMC_CUDA(c, cudaMemset(c->partials, 0, sizeof(double) * len));

@@ -214,7 +214,7 @@ k_colsum(const double* __restrict__ x, int64_t N, double div, int use_div, doubl
 }
 
 // =================================================================================================
-// K3: Julia-style pairwise cumsum with 64-element sequential leaves (src/resample.jl:29,47)
+// K3: Julia-style pairwise cumsum with 16-element sequential leaves (src/resample.jl:29,47)
 // =================================================================================================
 __host__ __device__ inline int lvl_off(int n_level0, int k) { return 2 * n_level0 - ((2 * n_level0) >> k); }
 
@@ -228,8 +228,8 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
        double* __restrict__ craw, double* __restrict__ bmax)
 {
     extern __shared__ double sm_dyn[];
-    double* tile = sm_dyn;                       // [nleaf][65]
-    double* lv = sm_dyn + SCAN_THREADS * 65;     // [2*nleaf] tree levels
+    double* tile = sm_dyn;                               // [nleaf][LEAF + 1]
+    double* lv = sm_dyn + SCAN_THREADS * (LEAF + 1);     // [2*nleaf] tree levels
     double* lmax = lv + 2 * SCAN_THREADS;        // [nleaf]
     const int tid = threadIdx.x;
     const int nleaf = B / LEAF;
@@ -243,16 +243,16 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
             if (div_n) x = x / n_parts;
             x = x / S;
         }
-        tile[(k >> 6) * 65 + (k & 63)] = x;
+        tile[(k / LEAF) * (LEAF + 1) + (k % LEAF)] = x;
     }
     __syncthreads();
     double total = 0.0;
     if (tid < nleaf) {
         double run = 0.0;
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < LEAF; ++i) {
-            run = run + tile[tid * 65 + i];
-            tile[tid * 65 + i] = run;
+            run = run + tile[tid * (LEAF + 1) + i];
+            tile[tid * (LEAF + 1) + i] = run;
         }
         total = run;
         lv[tid] = total;
@@ -279,10 +279,10 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
         int64_t valid = n - first;
         if (valid > LEAF) valid = LEAF;
         double last = -dinf();
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < LEAF; ++i) {
-            const double c = off + tile[tid * 65 + i];
-            tile[tid * 65 + i] = c;
+            const double c = off + tile[tid * (LEAF + 1) + i];
+            tile[tid * (LEAF + 1) + i] = c;
             if (i < valid) last = c;    // c is non-decreasing inside a leaf
         }
         lmax[tid] = last;
@@ -299,8 +299,8 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
     for (int k = tid; k < B; k += SCAN_THREADS) {
         const int64_t i = base + k;
         if (i < n) {
-            const int leaf = k >> 6;
-            const double c = tile[leaf * 65 + (k & 63)];
+            const int leaf = k / LEAF;
+            const double c = tile[leaf * (LEAF + 1) + (k % LEAF)];
             const double pm = (leaf > 0) ? lmax[leaf - 1] : -dinf();
             rmax[i] = fmax(c, pm);
             if (craw) craw[i] = c;
@@ -332,12 +332,31 @@ k_scan_upper(const double* __restrict__ blocktot, int nb, double* __restrict__ l
     }
 }
 
-// inclusive prefix max of the block maxima (tiny; one thread)
-__global__ void k_prefix_max(double* bmax, int nb)
+// inclusive prefix max of the block maxima (one block of 256 threads; max is exact in any order)
+__global__ void __launch_bounds__(256) k_prefix_max(double* bmax, int nb)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double m = -dinf();
-        for (int b = 0; b < nb; ++b) { m = fmax(m, bmax[b]); bmax[b] = m; }
+    __shared__ double sm[256];
+    __shared__ double carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = -dinf();
+    __syncthreads();
+    for (int base = 0; base < nb; base += 256) {
+        const int i = base + tid;
+        double v = (i < nb) ? bmax[i] : -dinf();
+        sm[tid] = v;
+        for (int s = 1; s < 256; s <<= 1) {
+            __syncthreads();
+            const double o = (tid >= s) ? sm[tid - s] : -dinf();
+            __syncthreads();
+            v = fmax(v, o);
+            sm[tid] = v;
+        }
+        __syncthreads();
+        v = fmax(v, carry);
+        if (i < nb) bmax[i] = v;
+        __syncthreads();
+        if (tid == 255) carry = v;
+        __syncthreads();
     }
 }
 
@@ -444,79 +463,121 @@ k_moments1(const double* __restrict__ cloud, int64_t N, int d, double* __restric
 }
 
 // pass 2: csum[a(a+1)/2 + b] = sum_i (w_i (x_ia - mean_a)) (x_ib - mean_b), b <= a.
-// Entries are split over the warps of the block in contiguous slabs so that each thread keeps its
-// slab's accumulators in registers; every warp streams the same tile (L1 serves the re-reads).
-template <int D, int SLABS>
-__global__ void __launch_bounds__(32 * SLABS)
+// Register-tiled SYRK: one warp owns a chunk of M2_CH consecutive particles and accumulates over them
+// sequentially (canonical order); lane (I, J), I >= J, owns the BS x BS block of entries
+// (a, b) = (BS*I + i, BS*J + j).  Particles are staged 32 at a time through shared memory as rows
+// [dx_0..dx_{DP-1} | w*dx_0..w*dx_{DP-1}], so each particle costs a lane 2*BS broadcast LDS and BS*BS DFMA.
+template <int D>
+struct M2Cfg {
+    static constexpr int BS = (D + 6) / 7;            // <= 7 block rows  =>  <= 28 lower block pairs
+    static constexpr int DB = (D + BS - 1) / BS;
+    static constexpr int DP = DB * BS;                // padded dimension
+    static constexpr int STRIDE = 2 * DP + 1;         // odd row stride: conflict-free transposed stores
+    static constexpr int NPAIR = DB * (DB + 1) / 2;
+};
+constexpr int M2_WARPS = 4;
+
+template <int D>
+__global__ void __launch_bounds__(32 * M2_WARPS)
 k_moments2(const double* __restrict__ cloud, int64_t N, const double* __restrict__ msum,
            double* __restrict__ partials, int P)
 {
-    constexpr int E = D * (D + 1) / 2;
-    constexpr int PER = (E + SLABS - 1) / SLABS;
+    using C = M2Cfg<D>;
+    constexpr int BS = C::BS, DP = C::DP, STRIDE = C::STRIDE;
+    extern __shared__ double sm_m2[];
     __shared__ double mean[D];
-    const int lane = threadIdx.x & 31, slab = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < D) mean[threadIdx.x] = msum[1 + threadIdx.x] / msum[0];
     __syncthreads();
-    const double* w = cloud + col_off(N, D + 4);
-    const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
-    double acc[PER];
+    double* rows = sm_m2 + (size_t)warp * 32 * STRIDE;
+    const int64_t chunk = (int64_t)blockIdx.x * M2_WARPS + warp;
+    const int64_t c0 = chunk * M2_CH;
+    if (c0 >= N) return;
+    // lane -> block pair (I, J), I >= J
+    int I = 0;
+    while ((I + 1) * (I + 2) / 2 <= lane) ++I;
+    const int J = lane - I * (I + 1) / 2;
+    const bool active = lane < C::NPAIR;
+    const int ao = active ? DP + BS * I : DP, bo = active ? BS * J : 0;
+    double acc[BS][BS];
 #pragma unroll
-    for (int e = 0; e < PER; ++e) acc[e] = 0.0;
-    const int lo = slab * PER;
-    for (int r = 0; r < M_R; ++r) {
-        const int64_t i = base + (int64_t)r * M_LANES;
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) acc[i][j] = 0.0;
+    const double* __restrict__ w = cloud + col_off(N, D + 4);
+
+    double xv[D], wv = 0.0;
+    auto load = [&](int64_t i) {
         if (i < N) {
-            const double wi = w[i];
-            double dx[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) dx[k] = cloud[col_off(N, k) + i] - mean[k];
-            // the slab index is warp-uniform; the switch keeps every accumulator index a literal
+            for (int k = 0; k < D; ++k) xv[k] = cloud[col_off(N, k) + i];
+            wv = w[i];
+        } else {
 #pragma unroll
-            for (int s = 0; s < SLABS; ++s) {
-                if (s == slab) {
-#pragma unroll
-                    for (int a = 0; a < D; ++a) {
-                        const double wa = wi * dx[a];
-#pragma unroll
-                        for (int b = 0; b <= a; ++b) {
-                            const int e = a * (a + 1) / 2 + b;
-                            if (e >= s * PER && e < (s + 1) * PER) acc[e - s * PER] = fma(wa, dx[b], acc[e - s * PER]);
-                        }
-                    }
-                }
-            }
+            for (int k = 0; k < D; ++k) xv[k] = 0.0;
+            wv = 0.0;
         }
-    }
+    };
+    load(c0 + lane);
+    for (int sub = 0; sub < M2_CH / 32; ++sub) {
+        // stage the prefetched particle of this lane
+        double* my = rows + lane * STRIDE;
 #pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const double v = warp_tree(acc[e]);
-        if (lane == 0 && lo + e < E) partials[(size_t)(lo + e) * P + blockIdx.x] = v;
+        for (int k = 0; k < DP; ++k) {
+            const double dx = (k < D) ? xv[k < D ? k : 0] - mean[k < D ? k : 0] : 0.0;
+            my[k] = dx;
+            my[DP + k] = wv * dx;
+        }
+        __syncwarp();
+        const int64_t nxt = c0 + (int64_t)(sub + 1) * 32 + lane;
+        if (sub + 1 < M2_CH / 32) load(nxt);                 // prefetch the next 32 particles (in flight during the FMAs)
+        int64_t rem = N - (c0 + (int64_t)sub * 32);
+        const int np = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+        for (int p = 0; p < np; ++p) {
+            const double* row = rows + p * STRIDE;
+            double av[BS], bv[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) { av[i] = row[ao + i]; bv[i] = row[bo + i]; }
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+                for (int j = 0; j < BS; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncwarp();
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+                const int a = BS * I + i, b = BS * J + j;
+                if (a < D && b <= a) partials[(size_t)(a * (a + 1) / 2 + b) * P + chunk] = acc[i][j];
+            }
     }
 }
 
-// generic-d fallback of pass 2 (one warp per tile, one entry at a time; slow, any d <= DMAX)
+// generic-d fallback of pass 2 (one warp per chunk, lanes over entries; any d <= DMAX)
 __global__ void __launch_bounds__(32)
 k_moments2_generic(const double* __restrict__ cloud, int64_t N, int d, const double* __restrict__ msum,
                    double* __restrict__ partials, int P)
 {
     const int lane = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * M_TILE + lane;
+    const int64_t chunk = blockIdx.x;
+    const int64_t c0 = chunk * M2_CH;
+    const int64_t c1 = (c0 + M2_CH < N) ? c0 + M2_CH : N;
     const double* w = cloud + col_off(N, d + 4);
     const double sw = msum[0];
-    for (int a = 0; a < d; ++a) {
-        const double ma = msum[1 + a] / sw;
+    const int E = d * (d + 1) / 2;
+    for (int e = lane; e < E; e += 32) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int b = e - a * (a + 1) / 2;
+        const double ma = msum[1 + a] / sw, mb = msum[1 + b] / sw;
         const double* xa = cloud + col_off(N, a);
-        for (int b = 0; b <= a; ++b) {
-            const double mb = msum[1 + b] / sw;
-            const double* xb = cloud + col_off(N, b);
-            double acc = 0.0;
-            for (int r = 0; r < M_R; ++r) {
-                const int64_t i = base + (int64_t)r * M_LANES;
-                if (i < N) acc = fma(w[i] * (xa[i] - ma), xb[i] - mb, acc);
-            }
-            acc = warp_tree(acc);
-            if (lane == 0) partials[(size_t)(a * (a + 1) / 2 + b) * P + blockIdx.x] = acc;
-        }
+        const double* xb = cloud + col_off(N, b);
+        double acc = 0.0;
+        for (int64_t i = c0; i < c1; ++i) acc = fma(w[i] * (xa[i] - ma), xb[i] - mb, acc);
+        partials[(size_t)e * P + chunk] = acc;
     }
 }
 

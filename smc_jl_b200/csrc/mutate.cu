@@ -131,10 +131,17 @@ struct MutArgs {
 // candidate.  Accepting a move flips which buffer is current.  This keeps the kernel under ~100 registers
 // (5 blocks = 20 warps per SM) -- it is FP64-latency bound, so resident warps are what buys throughput.
 // SINGLE = (n_blocks == 1): block index is a literal, so factor entries load as LDCU.128 pairs.
-constexpr int MUT_THREADS = 128;
+#ifndef SMC_MUT_THREADS
+#define SMC_MUT_THREADS 128
+#endif
+#ifndef SMC_MUT_WARPS_PER_SM
+#define SMC_MUT_WARPS_PER_SM 20
+#endif
+constexpr int MUT_THREADS = SMC_MUT_THREADS;
+constexpr int MUT_MINB20 = SMC_MUT_WARPS_PER_SM * 32 / MUT_THREADS;   // resident blocks asked of ptxas for D <= 20
 
 template <class LIK, bool HAS_OLD, bool SINGLE>
-__global__ void __launch_bounds__(MUT_THREADS, (LIK::D <= 20) ? 5 : ((LIK::D <= 24) ? 4 : 3))
+__global__ void __launch_bounds__(MUT_THREADS, (LIK::D <= 20) ? MUT_MINB20 : ((LIK::D <= 24) ? MUT_MINB20 * 4 / 5 : MUT_MINB20 * 3 / 5))
 k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 {
     constexpr int D = LIK::D;
