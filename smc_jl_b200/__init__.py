@@ -6,3 +6,10 @@ is the host-side mirror of the reference's Julia interface.  There is no CPU fal
 from .model import (Beta, CAPMLogLik, Gamma, GaussRegLogLik, InverseGamma, LinearEquationsLogLik,  # noqa: F401
                     LinearGaussianLogLik, ModelSpec, Normal, Parameter, RootInverseGamma, Uniform, make_spec,
                     parameter)
+from .cloud import Cloud  # noqa: F401,E402
+
+
+def smc(*args, **kwargs):
+    """smc(loglikelihood, parameters, data; ...) -- see smc_jl_b200.driver.smc (imports the CUDA library lazily)."""
+    from .driver import smc as _smc
+    return _smc(*args, **kwargs)

@@ -1,0 +1,102 @@
+"""Full-run tests of the `smc(...)` driver on the GPU, mirroring the reference's integration tests
+(test/smc.jl:13-143): the 3-equation linear model on the reference's own data (test_data.h5), a bridged
+(tempered-update) second run, and the regression example with an adaptive schedule."""
+import numpy as np
+import pytest
+
+from smc_jl_b200 import model as M
+from smc_jl_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def ols_truth(data, X):
+    out = []
+    for i in range(data.shape[0]):
+        Z = np.column_stack([np.ones(data.shape[1]), X[i, :data.shape[1]]])
+        b, res, *_ = np.linalg.lstsq(Z, data[i], rcond=None)
+        sig = np.sqrt(np.sum((data[i] - Z @ b) ** 2) / data.shape[1])
+        out += [b[0], b[1], sig]
+    return np.array(out)
+
+
+def wmean(cloud):
+    d = cloud.n_para
+    return np.average(cloud.particles[:, :d], axis=0, weights=cloud.particles[:, -1])
+
+
+def test_full_run_linear_model(golden):
+    """test/smc.jl:13-57: N = 5000, n_Phi = 120, lambda = 2.1; 'mean within 0.5 of truth' (:53-57)."""
+    from smc_jl_b200 import smc
+    g = golden("linear_model_rows.npz")
+    data, X = g["data"], g["X"]
+    params = W.three_equation_parameters()
+    cloud, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=5000,
+                       n_Φ=120, λ=2.1, resampling_method="systematic", threshold_ratio=0.5, c=0.5, α=1.0, target=0.25,
+                       use_fixed_schedule=True, seed=42)
+    truth = np.array([1, 1, 1, 2, 2, 1, 3, 3, 1], dtype=float)     # alpha_i = beta_i = i, sigma = 1
+    mean = wmean(cloud)
+    assert np.all(np.abs(mean - truth) < 0.5)
+    assert np.all(np.abs(mean - ols_truth(data, X)) < 0.15)        # tighter: the posterior mean is near OLS
+    assert cloud.stage_index == 120 and len(cloud.ESS) == 120 and cloud.tempering_schedule[-1] == 1.0
+    assert w.shape == (5000, 120) and Wm.shape == (5000, 120)
+    # the stored history obeys the reference's correction identities (checked against its golden in the oracle tests)
+    for n in (1, 5, 60, 119):
+        if cloud.ESS[n] >= 2500:                                      # not resampled: W[:, n] = N W[:, n-1] w[:, n] / sum
+            v = Wm[:, n - 1] * w[:, n]
+            np.testing.assert_allclose(Wm[:, n], 5000 * v / v.sum(), rtol=1e-12)
+            assert cloud.ESS[n] == pytest.approx(5000 ** 2 / np.sum(Wm[:, n] ** 2), rel=1e-12)
+        else:
+            assert np.all(Wm[:, n] == 1.0)
+    assert cloud.resamples == int(np.sum(cloud.ESS[1:] < 2500))
+    assert 0.1 < cloud.accept < 0.6
+    # same statistical anchor as the reference's stored run (under-converged there)
+    ref = golden("correction_history.npz")
+    assert np.all(np.abs(mean - ref["final_mean"]) < 0.35)
+
+
+def test_bridged_run_with_old_data(golden):
+    """test/smc.jl:92-143 (tempered update): first half of the sample, then the full sample starting from the
+    first cloud with old_data = first half (branch (a) of SURVEY 3.5: same n_parts, prior weight 0)."""
+    from smc_jl_b200 import smc
+    g = golden("linear_model_rows.npz")
+    data, X = g["data"], g["X"]
+    params = W.three_equation_parameters()
+    old = M.LinearEquationsLogLik(data[:, :50], X)
+    c1, _, _ = smc(old, params, data[:, :50], verbose="none", testing=True, n_parts=4000, n_Φ=150, n_mh_steps=3, seed=1)
+    c2, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=4000, n_Φ=60, n_mh_steps=3,
+                    old_data=data[:, :50], old_cloud=c1, old_loglikelihood=old, seed=2)
+    truth = np.array([1, 1, 1, 2, 2, 1, 3, 3, 1], dtype=float)
+    assert np.all(np.abs(wmean(c1) - truth) < 0.5)
+    assert np.all(np.abs(wmean(c2) - truth) < 0.5)
+    assert np.all(np.abs(wmean(c2) - ols_truth(data, X)) < 0.15)
+    # generalised tempering: old_loglh holds the likelihood of the old data at the final draws
+    import oracle_lib as O
+    mod = O.Model(M.make_spec(params, M.LinearEquationsLogLik(data, X), old))
+    for r in range(0, 4000, 400):
+        th = np.ascontiguousarray(c2.particles[r, :9])
+        assert c2.particles[r, 11] == mod.loglik(th, 1)
+        assert c2.particles[r, 9] == mod.loglik(th, 0)
+
+
+def test_adaptive_schedule_regression_example():
+    """Config C1: examples/regression_model (N = 1000), adaptive phi (use_fixed_schedule = false)."""
+    from smc_jl_b200 import smc
+    params, lk, _ = W.regression_example()
+    cloud, _, _ = smc(lk, params, None, verbose="none", testing=True, n_parts=1000, use_fixed_schedule=False,
+                      tempering_target=0.95, n_Φ=300, seed=3)
+    assert cloud.tempering_schedule[-1] == 1.0 and np.all(np.diff(cloud.tempering_schedule) > 0)
+    assert len(cloud.tempering_schedule) < 300                  # the adaptive schedule needs far fewer stages
+    assert np.allclose(wmean(cloud), [1.0, 1.0], atol=0.1)
+
+
+def test_errors_mirror_the_reference():
+    from smc_jl_b200 import smc
+    params, lk, _ = W.regression_example()
+    with pytest.raises(ValueError, match="Invalid resampler"):
+        smc(lk, params, None, resampling_method="bogus", testing=True, verbose="none")
+    with pytest.raises(ValueError, match="tempered_update_prior_weight"):
+        smc(lk, params, None, tempered_update_prior_weight=1.5, testing=True, verbose="none")
+    fixed = [M.parameter(p.key, 1.0, fixed=True) for p in params]
+    with pytest.raises((AssertionError, ValueError), match="fixed"):
+        smc(lk, fixed, None, testing=True, verbose="none")
