@@ -64,10 +64,17 @@ struct LikDesc {                // host copy of a likelihood slot's shape
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    // sharding
+    // sharding: contiguous ranges of the zero-padded power-of-two index space, `per` positions per rank
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
-    int64_t N_global = 0, N = 0, index0 = 0;
+    int64_t N_global = 0, N = 0, index0 = 0, per = 0;
+    double* scal_loc = nullptr;    // [256] local roots before the cross-rank tree
+    double* gath = nullptr;        // [world][256] gathered roots
+    double* rmax_g = nullptr;      // [world * per] running max of the global cumsum (world > 1)
+    double* bmax_g = nullptr;      // [world * nb_local]
+    double** peer_tab = nullptr;   // device table [2][world] of peers' cloud buffers (CUDA IPC)
+    int64_t* peer_cnt = nullptr;   // device [world] particles held by each rank
+    void* ipc_open[2][16] = {};    // opened peer mappings (host)
     int d = 0;
     // device buffers
     double* cloud[2] = {nullptr, nullptr};

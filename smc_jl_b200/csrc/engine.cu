@@ -1,6 +1,9 @@
 // engine.cu -- the C ABI of libsmcb200 (include/smcb200.h) and the host-side orchestration of one
 // SMC stage on one GPU shard.  Host code here only sequences kernels and moves scalars; all
 // per-particle arithmetic runs in the kernels of kernels.cuh / mutate.cu.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -22,11 +25,68 @@ int fail(Ctx* c, int code, const char* msg)
     return code;
 }
 
+// ---- NCCL, resolved at run time (the process may already hold torch's bundled libnccl) ----------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    for (const char* n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) { api.lib = nullptr; return nullptr; }
+    return &api;
+}
+#define SMC_NCCL(ctx, call)                                                                        \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess) {                                                                  \
+            NcclApi* a__ = nccl_api();                                                             \
+            (ctx)->err = std::string(#call) + ": " + ((a__ && a__->GetErrorString) ? a__->GetErrorString(r__) : "nccl error"); \
+            return SMCB200_ERR_NCCL;                                                               \
+        }                                                                                          \
+    } while (0)
+
+constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601, SL_COUNT = 640;   // slots of scal_loc
+// where a kernel should write shard-local roots, and the cross-rank tree that follows
+inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
+int reduce_ranks(Ctx* c, double* final_dst, const double* local_src, int nq)
+{
+    if (c->world == 1) return SMCB200_OK;
+    SMC_NCCL(c, nccl_api()->AllGather(local_src, c->gath, (size_t)nq, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    k_combine_ranks<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->gath, c->world, nq, final_dst);
+    c->launches += 1;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
 void free_cloud(Ctx* c)
 {
     cudaFree(c->cloud[0]); cudaFree(c->cloud[1]); cudaFree(c->tmp); cudaFree(c->rmax); cudaFree(c->idx);
     cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
     cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
+    for (int b = 0; b < 2; ++b)
+        for (int r = 0; r < 16; ++r)
+            if (c->ipc_open[b][r]) { cudaIpcCloseMemHandle(c->ipc_open[b][r]); c->ipc_open[b][r] = nullptr; }
+    cudaFree(c->rmax_g); cudaFree(c->bmax_g); cudaFree(c->peer_tab); cudaFree(c->peer_cnt);
+    c->rmax_g = c->bmax_g = nullptr; c->peer_tab = nullptr; c->peer_cnt = nullptr;
     c->cloud[0] = c->cloud[1] = c->tmp = c->rmax = nullptr; c->idx = nullptr; c->partials = c->mpartials = nullptr;
     c->scan_blocktot = c->scan_blockoff = c->scan_levels = c->scan_bmax = nullptr; c->msum = c->csum = nullptr;
     c->scan_nb_cap = 0;
@@ -55,12 +115,37 @@ int launch_correct(Ctx* c, double phi_n1, double phi_n, double pw, double lpod, 
     a.log_1m_pw = (a.mode == 2) ? det_log(1.0 - pw) : 0.0;
     const Tiles t = weight_tiles(c->N);
     double* w = cl + col_off(c->N, d + 4);
+    double* lo = local_out(c);
     k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), w, w, inc_dev, c->N, a,
-                                                 nullptr, c->partials, t.ntiles, t.P, c->counters, c->scal);
+                                                 nullptr, c->partials, t.ntiles, t.P, c->counters, lo);
+    int st = reduce_ranks(c, c->scal + SC_S, lo + SC_S, 1); if (st) return st;
     k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(w, normw_dev, c->N, (double)c->N_global, 1, nullptr, nullptr,
-                                                 c->partials, t.ntiles, t.P, c->counters, c->scal);
+                                                 c->partials, t.ntiles, t.P, c->counters, c->scal, lo, 0);
+    st = reduce_ranks(c, c->scal + SC_Q, lo + SC_Q, 2); if (st) return st;
     c->launches += 2;
     SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+// one evaluation of compute_ESS at a trial phi (host value or the device state machine's current trial)
+int launch_ess_eval(Ctx* c, const CorrArgs& a, PhiState* st_dev, const double* sched_dev)
+{
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    const Tiles t = weight_tiles(c->N);
+    const double n = (double)c->N_global;
+    double* lo = local_out(c);
+    k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
+                                                 c->tmp, nullptr, c->N, a, st_dev, c->partials, t.ntiles, t.P, c->counters, lo);
+    int st = reduce_ranks(c, c->scal + SC_S, lo + SC_S, 1); if (st) return st;
+    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, st_dev, sched_dev, c->partials, t.ntiles, t.P,
+                                                 c->counters, c->scal, lo, c->world > 1 ? 1 : 0);
+    st = reduce_ranks(c, c->scal + SC_Q, lo + SC_Q, 2); if (st) return st;
+    c->launches += 2;
+    if (st_dev && c->world > 1) {
+        k_phi_step<<<1, 32, 0, c->stream>>>(st_dev, sched_dev, c->scal, n);
+        c->launches += 1;
+    }
     return SMCB200_OK;
 }
 
@@ -90,6 +175,7 @@ int ensure_scan_buffers(Ctx* c, int nb)
 
 // src: n weights on the device (div_n: use src/n_parts, the `normalized_weights/n_parts` of smc_main.jl:438);
 // rmax/craw/idx: device outputs.  `sres` = device slot receiving sum(weights) ("weights ./ sum(weights)").
+// Single-shard version (also serves the exported resample(weights) on host vectors).
 int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int method, uint64_t seed, uint32_t stage,
                             double u_override, double* rmax, double* craw, int64_t* idx, double* partials,
                             unsigned* counter, double* sres)
@@ -97,7 +183,7 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
     if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
         return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
     const ScanGeom g = scan_geom(n);
-    if (g.nb > (1 << 15)) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_parts too large for the device scan (max 2^28)");
+    if (g.nb > (1 << 16)) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_parts too large for the device scan (max 2^28)");
     int st = ensure_scan_buffers(c, g.nb);
     if (st) return st;
     const Tiles t = weight_tiles(n);
@@ -105,7 +191,8 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
     k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, n, nd, div_n, partials, t.ntiles, t.P, counter, sres);
     k_scan<false><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, c->scan_blocktot, nullptr,
                                                               nullptr, nullptr, nullptr);
-    k_scan_upper<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scan_blockoff);
+    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT);
+    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, g.nb, nullptr, 1, 0, c->scan_blockoff);
     k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
                                                              craw, c->scan_bmax);
     k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, g.nb);
@@ -116,14 +203,64 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
     }
     k_search<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(rmax, c->scan_bmax, g.nb, g.B, n, n, 0, method, seed, stage,
                                                                  u, nd, idx);
-    c->launches += 6;
+    c->launches += 7;
     SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+// Selection on the sharded cloud: canonical global cumsum (shard totals exchanged), ancestors of this
+// shard's outputs searched in the all-gathered running max, rows pulled from the owners over NVLink.
+int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override)
+{
+    if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
+        return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
+    NcclApi* nc = nccl_api();
+    const int d = c->d;
+    double* cl = c->cloud[c->cur];
+    const double* src = cl + col_off(c->N, d + 4);
+    const int B = SCAN_TILE;
+    const int nb = (int)(c->per / B);                 // blocks of this shard's full subtree
+    int st = ensure_scan_buffers(c, nb); if (st) return st;
+    const Tiles t = weight_tiles(c->N);
+    const double nd = (double)c->N_global;
+    // sum(weights) over all shards
+    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, c->N, nd, 1, c->partials + (size_t)3 * t.P, t.ntiles, t.P, c->counters + 2,
+                                              c->scal_loc + SC_SRES);
+    st = reduce_ranks(c, c->scal + SC_SRES, c->scal_loc + SC_SRES, 1); if (st) return st;
+    k_scan<false><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, c->scan_blocktot, nullptr,
+                                                            nullptr, nullptr, nullptr);
+    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT);
+    SMC_NCCL(c, nc->AllGather(c->scal_loc + SL_SCAN_ROOT, c->gath, 1, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, nb, c->gath, c->world, c->rank, c->scan_blockoff);
+    double* rloc = c->rmax_g + (size_t)c->rank * c->per;
+    double* bloc = c->bmax_g + (size_t)c->rank * nb;
+    k_scan<true><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, nullptr, c->scan_blockoff,
+                                                           rloc, nullptr, bloc);
+    k_prefix_max<<<1, 256, 0, c->stream>>>(bloc, nb);
+    // shard maxima -> carry of the lower ranks, then every rank gets the global running max + block maxima
+    SMC_CUDA(c, cudaMemcpyAsync(c->scal_loc + SL_SCAN_MAX, bloc + nb - 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    SMC_NCCL(c, nc->AllGather(c->scal_loc + SL_SCAN_MAX, c->gath, 1, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    k_apply_rank_carry<<<1, 256, 0, c->stream>>>(bloc, nb, c->gath, c->rank);
+    SMC_NCCL(c, nc->AllGather(bloc, c->bmax_g, (size_t)nb, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    SMC_NCCL(c, nc->AllGather(rloc, c->rmax_g, (size_t)c->per, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    double u = u_override;
+    if (!(u >= 0.0)) {
+        const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
+        u = u01(r.x, r.y);
+    }
+    k_search<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->rmax_g, c->bmax_g, nb * c->world, B, c->N_global, c->N,
+                                                                    c->index0, method, seed, stage, u, nd, c->idx);
+    k_gather_peer<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->peer_tab + (size_t)c->cur * c->world, c->peer_cnt, c->per,
+                                                                         c->cloud[c->cur ^ 1], c->idx, c->N, d + 4, d + 4);
+    c->launches += 9;
+    SMC_CUDA(c, cudaGetLastError());
+    c->cur ^= 1;
     return SMCB200_OK;
 }
 
 int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override)
 {
-    if (c->world > 1) return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU resampling is not available in this build");
+    if (c->world > 1) return launch_resample_cloud_sharded(c, method, seed, stage, u_override);
     const int d = c->d;
     double* cl = c->cloud[c->cur];
     const Tiles t = weight_tiles(c->N);
@@ -159,7 +296,8 @@ int launch_moments(Ctx* c)
     const int E = d * (d + 1) / 2;
     double* part = c->mpartials;  // max([1+d][P_m], [E][P_c]) -- sized at cloud creation
     k_moments1<<<dim3(t.ntiles, (d + 4) / 4), 128, 0, c->stream>>>(cl, c->N, d, part, t.P);
-    k_tree_finalize<<<1 + d, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->msum);
+    k_tree_finalize<<<1 + d, 256, 0, c->stream>>>(part, t.ntiles, t.P, c->world > 1 ? c->scal_loc + SL_MSUM : c->msum);
+    { int st0 = reduce_ranks(c, c->msum, c->scal_loc + SL_MSUM, 1 + d); if (st0) return st0; }
     // pass 2 reuses the partial buffer with the chunk geometry: clear the zero padding it relies on
     if (tc.ntiles < tc.P || t.ntiles < t.P)
         SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * c->partials_len_m, c->stream));
@@ -181,7 +319,8 @@ int launch_moments(Ctx* c)
     default: k_moments2_generic<<<tc.ntiles, 32, 0, c->stream>>>(cl, c->N, d, c->msum, part, tc.P); break;
     }
     if (st) return st;
-    k_tree_finalize<<<E, 256, 0, c->stream>>>(part, tc.ntiles, tc.P, c->csum);
+    k_tree_finalize<<<E, 256, 0, c->stream>>>(part, tc.ntiles, tc.P, c->world > 1 ? c->scal_loc + SL_CSUM : c->csum);
+    { int st0 = reduce_ranks(c, c->csum, c->scal_loc + SL_CSUM, E); if (st0) return st0; }
     if (tc.ntiles < tc.P || t.ntiles < t.P)
         SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * c->partials_len_m, c->stream));
     c->launches += 4;
@@ -247,10 +386,10 @@ int mean_accept(Ctx* c)
 {
     const Tiles t = weight_tiles(c->N);
     k_colsum<<<t.ntiles, 256, 0, c->stream>>>(c->cloud[c->cur] + col_off(c->N, c->d + 3), c->N, 1.0, 0,
-                                              c->partials + (size_t)4 * t.P, t.ntiles, t.P, c->counters + 3, c->scal + SC_ACC);
+                                              c->partials + (size_t)4 * t.P, t.ntiles, t.P, c->counters + 3, local_out(c) + SC_ACC);
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
-    return SMCB200_OK;
+    return reduce_ranks(c, c->scal + SC_ACC, c->scal_loc + SC_ACC, 1);
 }
 
 }  // namespace
@@ -294,6 +433,9 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     ok = ok && cudaMalloc(&c->scal, sizeof(double) * SC_COUNT) == cudaSuccess;
     ok = ok && cudaMemset(c->scal, 0, sizeof(double) * SC_COUNT) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * SC_COUNT) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->scal_loc, sizeof(double) * SL_COUNT) == cudaSuccess;
+    ok = ok && cudaMemset(c->scal_loc, 0, sizeof(double) * SL_COUNT) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->gath, sizeof(double) * SL_COUNT * 16) == cudaSuccess;
     ok = ok && cudaMalloc(&c->phi_state, sizeof(PhiState)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_phi_state, sizeof(PhiState)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mutc_dev, sizeof(MutConst) + sizeof(double) * (DMAX + 3 * DMAX * DMAX)) == cudaSuccess;
@@ -318,6 +460,8 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_cloud(c);
+    if (c->nccl_comm && nccl_api()) { nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+    cudaFree(c->scal_loc); cudaFree(c->gath);
     cudaFree(c->counters); cudaFree(c->scal); cudaFreeHost(c->h_scal); cudaFree(c->phi_state); cudaFreeHost(c->h_phi_state);
     cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
@@ -330,13 +474,32 @@ int32_t smcb200_destroy(smcb200_ctx* c)
 
 const char* smcb200_last_error(const smcb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-int32_t smcb200_comm_unique_id(void* id) { (void)id; return SMCB200_ERR_UNSUPPORTED; }
+int32_t smcb200_comm_unique_id(void* id)
+{
+    NcclApi* nc = nccl_api();
+    if (!nc || !id) return SMCB200_ERR_NCCL;
+    ncclUniqueId u;
+    if (nc->GetUniqueId(&u) != ncclSuccess) return SMCB200_ERR_NCCL;
+    std::memcpy(id, &u, sizeof(u));
+    return SMCB200_OK;
+}
+
 int32_t smcb200_comm_init(smcb200_ctx* c, int32_t rank, int32_t world, const void* id)
 {
-    (void)id;
     if (!c) return SMCB200_ERR_BAD_ARGUMENT;
-    if (world == 1 && rank == 0) return SMCB200_OK;
-    return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU communicator is not available in this build");
+    if (c->cloud[0]) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "smcb200_comm_init must precede smcb200_cloud_create");
+    if (world == 1 && rank == 0) { c->rank = 0; c->world = 1; return SMCB200_OK; }
+    if (world < 1 || world > 16 || (world & (world - 1)) || rank < 0 || rank >= world || !id)
+        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "world must be a power of two <= 16 and 0 <= rank < world");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(c, SMCB200_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    cudaSetDevice(c->device);
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    ncclComm_t comm;
+    SMC_NCCL(c, nc->CommInitRank(&comm, world, u, rank));
+    c->nccl_comm = comm; c->rank = rank; c->world = world;
+    return SMCB200_OK;
 }
 
 // ---- cloud --------------------------------------------------------------------------------------------
@@ -351,10 +514,12 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     // contiguous shard of the zero-padded power-of-two index space (keeps every canonical tree shard-aligned)
     const int64_t P2 = next_pow2(n_parts);
     const int64_t per = P2 / c->world;
+    if (c->world > 1 && (per % SCAN_TILE) != 0)
+        return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU needs at least 4096 (padded) particles per rank");
     int64_t first = per * c->rank, last = first + per;
     if (first > n_parts) first = n_parts;
     if (last > n_parts) last = n_parts;
-    c->index0 = first; c->N = last - first;
+    c->index0 = first; c->N = last - first; c->per = per;
     if (c->N < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "empty shard: fewer particles than ranks");
     const size_t cols = (size_t)n_para + 5;
     SMC_CUDA(c, cudaMalloc(&c->cloud[0], sizeof(double) * cols * c->N));
@@ -378,6 +543,42 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMalloc(&c->csum, sizeof(double) * PACKMAX));
     SMC_CUDA(c, cudaMemset(c->cloud[0], 0, sizeof(double) * cols * c->N));
     c->cur = 0;
+    if (c->world > 1) {
+        // peers' cloud buffers: exchange CUDA-IPC handles + shard sizes through the communicator
+        NcclApi* nc = nccl_api();
+        const int W = c->world;
+        struct Info { cudaIpcMemHandle_t h[2]; int64_t count; int64_t pad; };
+        Info mine, *all_dev = nullptr, *mine_dev = nullptr;
+        std::vector<Info> all(W);
+        SMC_CUDA(c, cudaIpcGetMemHandle(&mine.h[0], c->cloud[0]));
+        SMC_CUDA(c, cudaIpcGetMemHandle(&mine.h[1], c->cloud[1]));
+        mine.count = c->N; mine.pad = 0;
+        SMC_CUDA(c, cudaMalloc(&all_dev, sizeof(Info) * W));
+        SMC_CUDA(c, cudaMalloc(&mine_dev, sizeof(Info)));
+        SMC_CUDA(c, cudaMemcpyAsync(mine_dev, &mine, sizeof(Info), cudaMemcpyHostToDevice, c->stream));
+        SMC_NCCL(c, nc->AllGather(mine_dev, all_dev, sizeof(Info), ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
+        SMC_CUDA(c, cudaMemcpyAsync(all.data(), all_dev, sizeof(Info) * W, cudaMemcpyDeviceToHost, c->stream));
+        SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(all_dev); cudaFree(mine_dev);
+        std::vector<double*> tab(2 * W);
+        std::vector<int64_t> cnt(W);
+        for (int r = 0; r < W; ++r) {
+            cnt[r] = all[r].count;
+            for (int b = 0; b < 2; ++b) {
+                if (r == c->rank) { tab[b * W + r] = c->cloud[b]; continue; }
+                void* p = nullptr;
+                SMC_CUDA(c, cudaIpcOpenMemHandle(&p, all[r].h[b], cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_open[b][r] = p;
+                tab[b * W + r] = (double*)p;
+            }
+        }
+        SMC_CUDA(c, cudaMalloc(&c->peer_tab, sizeof(double*) * 2 * W));
+        SMC_CUDA(c, cudaMalloc(&c->peer_cnt, sizeof(int64_t) * W));
+        SMC_CUDA(c, cudaMemcpy(c->peer_tab, tab.data(), sizeof(double*) * 2 * W, cudaMemcpyHostToDevice));
+        SMC_CUDA(c, cudaMemcpy(c->peer_cnt, cnt.data(), sizeof(int64_t) * W, cudaMemcpyHostToDevice));
+        SMC_CUDA(c, cudaMalloc(&c->rmax_g, sizeof(double) * (size_t)per * W));
+        SMC_CUDA(c, cudaMalloc(&c->bmax_g, sizeof(double) * (size_t)(per / SCAN_TILE) * W));
+    }
     return SMCB200_OK;
 }
 
@@ -535,17 +736,10 @@ int32_t smcb200_ess_at(smcb200_ctx* c, const double* phi, int32_t K, double phi_
     int st = check_ready(c, false); if (st) return st;
     if (K < 0 || (K > 0 && (!phi || !ess_out))) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad phi vector");
     cudaSetDevice(c->device);
-    const int d = c->d;
-    double* cl = c->cloud[c->cur];
-    const Tiles t = weight_tiles(c->N);
     const double n = (double)c->N_global;
     for (int k = 0; k < K; ++k) {
         CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = phi[k]; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
-        k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
-                                                     c->tmp, nullptr, c->N, a, nullptr, c->partials, t.ntiles, t.P, c->counters, c->scal);
-        k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, nullptr, nullptr, c->partials, t.ntiles, t.P,
-                                                     c->counters, c->scal);
-        c->launches += 2;
+        st = launch_ess_eval(c, a, nullptr, nullptr); if (st) return st;
         SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
         st = sync(c); if (st) return st;
         ess_out[k] = (n * n) / c->h_scal[SC_Q];
@@ -571,21 +765,13 @@ int32_t smcb200_solve_adaptive_phi(smcb200_ctx* c, const double* sched, int32_t 
     h->ess_bar = resampled_last ? tempering_target * n : tempering_target * ess_prev;   // helpers.jl:14-20
     h->phi_prop = *phi_prop_io; h->phi_cur = *phi_prop_io; h->phi_n1 = phi_n1; h->j = *j_io; h->n_phi = n_phi;
     SMC_CUDA(c, cudaMemcpyAsync(c->phi_state, h, sizeof(PhiState), cudaMemcpyHostToDevice, c->stream));
-    const int d = c->d;
-    double* cl = c->cloud[c->cur];
-    const Tiles t = weight_tiles(c->N);
     CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = 0.0; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
     // every evaluation of g() = two kernels; the bracket walk and the bisection advance on the device, the host
     // only polls the `done` flag between batches
     for (int round = 0; round < 64; ++round) {
         for (int e = 0; e < 72; ++e) {
-            k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
-                                                         c->tmp, nullptr, c->N, a, c->phi_state, c->partials, t.ntiles, t.P,
-                                                         c->counters, c->scal);
-            k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, c->phi_state, c->sched_dev, c->partials,
-                                                         t.ntiles, t.P, c->counters, c->scal);
+            st = launch_ess_eval(c, a, c->phi_state, c->sched_dev); if (st) return st;
         }
-        c->launches += 144;
         SMC_CUDA(c, cudaGetLastError());
         SMC_CUDA(c, cudaMemcpyAsync(h, c->phi_state, sizeof(PhiState), cudaMemcpyDeviceToHost, c->stream));
         st = sync(c); if (st) return st;

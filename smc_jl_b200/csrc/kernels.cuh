@@ -78,6 +78,24 @@ __device__ __forceinline__ bool finish_tiles(const double (&v)[NQ], double* part
 }
 
 // =================================================================================================
+// cross-rank combination: out[q] = adjacent-pair tree over ranks of gath[r][q] (rank order; world is a
+// power of two).  Every rank evaluates the same tree on the same gathered values => identical bits.
+// =================================================================================================
+__global__ void k_combine_ranks(const double* __restrict__ gath, int world, int nq, double* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double v[16];
+    for (int r = 0; r < world; ++r) v[r] = gath[(size_t)r * nq + q];
+    for (int s = 1; s < world; s <<= 1)
+        for (int i = 0; i + s < world; i += 2 * s) v[i] = v[i] + v[i + s];
+    out[q] = v[0];
+}
+
+// adaptive-phi transition as its own launch (multi-GPU: it must run after the cross-rank combination)
+__global__ void k_phi_step(PhiState* st, const double* __restrict__ sched, const double* __restrict__ scal, double n_parts);
+
+// =================================================================================================
 // K1 / K2: correction and ESS  (src/smc_main.jl:400-427, src/helpers.jl:173-181)
 // =================================================================================================
 struct CorrArgs {
@@ -99,7 +117,7 @@ __global__ void __launch_bounds__(256)
 k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const double* w,
             double* wout, double* __restrict__ inc_out, int64_t N, CorrArgs a,
             const PhiState* __restrict__ phi_state, double* partials, int ntiles, int P, unsigned* counter,
-            double* scal)
+            double* out)
 {
     __shared__ double sm[8];
     double phi_n = a.phi_n;
@@ -124,7 +142,7 @@ k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const
 #pragma unroll
     for (int r = 0; r < W_R; ++r) acc = acc + x[r];
     double v[1] = {block_tree_256(acc, sm)};
-    finish_tiles<1>(v, partials, ntiles, P, counter, scal + SC_S, sm);
+    finish_tiles<1>(v, partials, ntiles, P, counter, out + SC_S, sm);
 }
 
 // device transition of solve_adaptive_phi (src/helpers.jl:26-54); executed by one thread
@@ -164,7 +182,7 @@ __device__ inline void phi_transition(PhiState* st, const double* sched, double 
 __global__ void __launch_bounds__(256)
 k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts, int store,
             PhiState* phi_state, const double* __restrict__ sched, double* partials, int ntiles, int P,
-            unsigned* counter, double* scal)
+            unsigned* counter, double* scal, double* out, int defer_transition)
 {
     __shared__ double sm[8];
     if (phi_state && phi_state->done) return;
@@ -187,11 +205,16 @@ k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts
     double v[2];
     v[0] = block_tree_256(q, sm);
     v[1] = block_tree_256(s2, sm);
-    const bool last = finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, scal + SC_Q, sm);
-    if (last && phi_state && threadIdx.x == 0) {
-        const double ess = (n_parts * n_parts) / scal[SC_Q];
+    const bool last = finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, out + SC_Q, sm);
+    if (last && phi_state && !defer_transition && threadIdx.x == 0) {
+        const double ess = (n_parts * n_parts) / out[SC_Q];
         phi_transition(phi_state, sched, ess);
     }
+}
+
+__global__ void k_phi_step(PhiState* st, const double* __restrict__ sched, const double* __restrict__ scal, double n_parts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) phi_transition(st, sched, (n_parts * n_parts) / scal[SC_Q]);
 }
 
 // canonical sum of one column (optionally divided by a constant first): out = sum_i x_i / div
@@ -309,9 +332,12 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
     if (tid == 0) bmax[blockIdx.x] = lmax[nleaf - 1];
 }
 
-// upper tree over the nb (power of two) block totals: block offsets (top-down), single block
+// upper tree over the nb (power of two) block totals of this shard, single block.
+// up:   levels + shard root (root_out).
+// down: block offsets, top-down, starting from the shard's own offset in the cross-rank tree
+//       (rank_roots = gathered shard roots; nullptr on one GPU).
 __global__ void __launch_bounds__(256)
-k_scan_upper(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ blockoff)
+k_scan_upper_up(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ root_out)
 {
     int nlev = 0;
     while ((1 << nlev) < nb) ++nlev;
@@ -322,14 +348,50 @@ k_scan_upper(const double* __restrict__ blocktot, int nb, double* __restrict__ l
             lv[lvl_off(nb, k) + i] = lv[lvl_off(nb, k - 1) + 2 * i] + lv[lvl_off(nb, k - 1) + 2 * i + 1];
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    if (threadIdx.x == 0) *root_out = lv[lvl_off(nb, nlev)];
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_upper_down(const double* __restrict__ lv, int nb, const double* __restrict__ rank_roots, int world, int rank,
+                  double* __restrict__ blockoff)
+{
+    __shared__ double off0;
+    if (threadIdx.x == 0) {
         double off = 0.0;
+        if (rank_roots && world > 1) {
+            // levels of the cross-rank tree over the gathered shard roots (world <= 16)
+            double t[5][16];
+            int wl = 0;
+            while ((1 << wl) < world) ++wl;
+            for (int r = 0; r < world; ++r) t[0][r] = rank_roots[r];
+            for (int k = 1; k <= wl; ++k)
+                for (int i = 0; i < (world >> k); ++i) t[k][i] = t[k - 1][2 * i] + t[k - 1][2 * i + 1];
+            for (int k = wl - 1; k >= 0; --k) {
+                const int node = rank >> k;
+                if (node & 1) off = off + t[k][node - 1];
+            }
+        }
+        off0 = off;
+    }
+    __syncthreads();
+    int nlev = 0;
+    while ((1 << nlev) < nb) ++nlev;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        double off = off0;
         for (int k = nlev - 1; k >= 0; --k) {
             const int node = b >> k;
             if (node & 1) off = off + lv[lvl_off(nb, k) + node - 1];
         }
         blockoff[b] = off;
     }
+}
+
+// multi-GPU: fold the maxima of the lower ranks into this shard's inclusive prefix max
+__global__ void k_apply_rank_carry(double* __restrict__ bmax, int nb, const double* __restrict__ rank_max, int rank)
+{
+    double carry = -dinf();
+    for (int r = 0; r < rank; ++r) carry = fmax(carry, rank_max[r]);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) bmax[b] = fmax(bmax[b], carry);
 }
 
 // inclusive prefix max of the block maxima (one block of 256 threads; max is exact in any order)
@@ -418,6 +480,31 @@ k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t
         dst[col_off(N, c + 2) + i] = v2; dst[col_off(N, c + 3) + i] = v3;
     }
     for (; c < ncopy; ++c) dst[col_off(N, c) + i] = src[col_off(N, c) + a];
+    dst[col_off(N, wcol) + i] = 1.0;
+}
+
+// multi-GPU gather: ancestors are GLOBAL indices; rows are read straight from the owning rank's cloud
+// through CUDA-IPC peer mappings over NVLink (systematic ancestors are sorted, so a warp's reads of one
+// column are near-contiguous on one or two peers) -- the "all-to-all(v)" of the stage, done by the kernel.
+__global__ void __launch_bounds__(256)
+k_gather_peer(double* const* __restrict__ peers, const int64_t* __restrict__ peer_cnt, int64_t per, double* __restrict__ dst,
+              const int64_t* __restrict__ idx, int64_t N, int ncopy, int wcol)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const int64_t a = idx[i] - 1;
+    const int r = (int)(a / per);
+    const int64_t row = a - (int64_t)r * per;
+    const double* __restrict__ src = peers[r];
+    const int64_t nr = peer_cnt[r];
+    int c = 0;
+    for (; c + 4 <= ncopy; c += 4) {
+        const double v0 = src[col_off(nr, c) + row], v1 = src[col_off(nr, c + 1) + row];
+        const double v2 = src[col_off(nr, c + 2) + row], v3 = src[col_off(nr, c + 3) + row];
+        dst[col_off(N, c) + i] = v0; dst[col_off(N, c + 1) + i] = v1;
+        dst[col_off(N, c + 2) + i] = v2; dst[col_off(N, c + 3) + i] = v3;
+    }
+    for (; c < ncopy; ++c) dst[col_off(N, c) + i] = src[col_off(nr, c) + row];
     dst[col_off(N, wcol) + i] = 1.0;
 }
 

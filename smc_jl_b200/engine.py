@@ -52,6 +52,22 @@ class Engine:
         self.n_parts = 0
         self.n_para = 0
         self.spec = None
+        self.rank, self.world = 0, 1
+
+    @staticmethod
+    def unique_id():
+        """128-byte communicator id (rank 0 creates it, the host distributes it to every rank)."""
+        buf = C.create_string_buffer(128)
+        st = lib.smcb200_comm_unique_id(buf)
+        if st:
+            raise RuntimeError("smcb200_comm_unique_id failed: " + lib.smcb200_status_string(st).decode())
+        return buf.raw
+
+    def comm_init(self, rank, world, comm_id):
+        """Join the job's communicator (one process per GPU).  Must precede cloud_create."""
+        buf = C.create_string_buffer(bytes(comm_id), 128)
+        self._ck(lib.smcb200_comm_init(self.h, int(rank), int(world), buf))
+        self.rank, self.world = int(rank), int(world)
 
     def close(self):
         if getattr(self, "h", None):
@@ -79,16 +95,24 @@ class Engine:
         self.first, self.count = first.value, count.value
 
     def upload(self, particles):
-        """particles: n_parts x (n_para+5); Fortran-ordered arrays are passed without a copy."""
+        """particles: the GLOBAL n_parts x (n_para+5) matrix (this rank copies its shard's rows) or just this
+        rank's shard; Fortran-ordered arrays are passed without a copy."""
         p = np.asfortranarray(particles, dtype=np.float64)
-        assert p.shape == (self.n_parts, self.n_para + 5), p.shape
-        self._ck(lib.smcb200_cloud_upload(self.h, ptr(p), p.shape[0], self.first))
+        if p.shape == (self.n_parts, self.n_para + 5):
+            self._ck(lib.smcb200_cloud_upload(self.h, ptr(p), p.shape[0], self.first))
+        else:
+            assert p.shape == (self.count, self.n_para + 5), p.shape
+            self._ck(lib.smcb200_cloud_upload(self.h, ptr(p), p.shape[0], 0))
 
     def download(self, out=None):
+        """Global-shaped output (only this rank's rows are written) or, with out=None on a sharded engine,
+        this rank's shard."""
         if out is None:
-            out = np.zeros((self.n_parts, self.n_para + 5), order="F")
-        assert out.flags.f_contiguous and out.shape == (self.n_parts, self.n_para + 5)
-        self._ck(lib.smcb200_cloud_download(self.h, ptr(out), out.shape[0], self.first))
+            rows = self.n_parts if self.world == 1 else self.count
+            out = np.zeros((rows, self.n_para + 5), order="F")
+        assert out.flags.f_contiguous and out.shape[1] == self.n_para + 5
+        row0 = self.first if out.shape[0] == self.n_parts and self.world > 1 else (self.first if self.world == 1 else 0)
+        self._ck(lib.smcb200_cloud_download(self.h, ptr(out), out.shape[0], row0))
         return out
 
     def read_column(self, col):

@@ -100,3 +100,23 @@ def test_errors_mirror_the_reference():
     fixed = [M.parameter(p.key, 1.0, fixed=True) for p in params]
     with pytest.raises((AssertionError, ValueError), match="fixed"):
         smc(lk, fixed, None, testing=True, verbose="none")
+
+
+def test_multi_gpu_sharding_is_bit_invariant():
+    """Needs >= 2 GPUs (skipped otherwise): tests/multigpu_check.py under torchrun -- sharded stages over NCCL +
+    NVLink peer reads equal the single-GPU run bit-for-bit."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "multigpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("bit-exact") == 2
