@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
 
 D, T, N_FULL, N_MH, N_BLOCKS, N_PHI, LAM = 20, 256, 1 << 20, 3, 1, 300, 2.1
 SEED = 1793
@@ -154,7 +155,7 @@ def run_reference(args):
     params, spec = make_model()
     n = 1 << 16
     warm = max(args.warmup, 1)
-    sec, cores = oracle_run(spec, params, n, FIRST_STAGE, args.steps, 0)
+    sec, cores = oracle_run(spec, params, n, FIRST_STAGE, args.steps, os.cpu_count() or 1)   # explicit: torchrun exports OMP_NUM_THREADS=1
     value = n * N_MH * N_BLOCKS / sec
     sample = "N=2^16 particles of the same d=20/T=256 model, %d stages from schedule index %d, n_mh_steps=3" % (args.steps, FIRST_STAGE)
     print(json.dumps({
@@ -184,15 +185,24 @@ def run_ours(args):
 
     params, spec = make_model()
     sched = schedule()
-    # weak scaling: every rank runs the full C2 cloud shape (per-GPU work fixed), independent replicas
-    N = N_FULL
+    # weak scaling: ONE global cloud of world x 2^20 particles, sharded over the ranks (2^20 per GPU); the
+    # weight normaliser / ESS / moments / accept reductions and the post-resample row exchange cross GPUs
+    N = N_FULL                     # particles per GPU
+    N_global = N * world
     eng = Engine(local_rank)
-    eng.cloud_create(N, D)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(Engine.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    eng.cloud_create(N_global, D)
+    assert eng.count == N
     eng.set_model(spec)
-    P0 = W.initial_cloud(params, N, np.random.default_rng(rank))
+    P0 = W.initial_cloud(params, N, np.random.default_rng(rank))     # this rank's shard of the prior cloud
     eng.upload(P0)
     eng.evaluate(0)
-    state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2)
+    state = StageState(c=0.5, accept=0.25, ess_prev=float(N_global), phi_prop=0.0, j=2)
 
     def barrier():
         if world > 1:
@@ -254,7 +264,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         try:
-            sec, cores = oracle_run(spec, params, 1 << 15, FIRST_STAGE, 3, 0)
+            sec, cores = oracle_run(spec, params, 1 << 15, FIRST_STAGE, 3, os.cpu_count() or 1)
             cpu = {"value": (1 << 15) * N_MH * N_BLOCKS / sec, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "N=2^15 particles of the same model, 3 stages from schedule index %d (oracle/, OpenMP)" % FIRST_STAGE}
         except Exception as e:  # the oracle is a reported baseline, never the product path
@@ -267,7 +277,9 @@ def run_ours(args):
                                    "schedule (n_phi=300, lambda=2.1), systematic resampling, timed stages %d..%d"
                                    % (FIRST_STAGE + 2, FIRST_STAGE + 1 + args.steps),
                        "l2": "cloud double buffer 2 x 210 MB > 126 MB L2 (inputs larger than L2, no explicit flush)",
-                       "parallelism": "independent replicas per GPU" if world > 1 else "1 GPU",
+                       "parallelism": ("one global cloud of %d x 2^20 particles sharded over %d GPUs: NCCL all-gather + fixed-order "
+                                       "cross-rank trees for the reductions, NVLink peer reads (CUDA IPC) for the post-resample "
+                                       "row exchange" % (world, world)) if world > 1 else "1 GPU",
                        "resamples_in_timed_region": int(resamples)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cols * N * 8), "d2h_bytes_per_step": int(cols * N * 8),
                     "what": "smcb200_stage_host: Cloud in pinned host memory, upload + stage + download each step"},

@@ -34,7 +34,7 @@ def main():
         return bytes(idt.cpu().numpy().tobytes())
 
     cases = [("linreg20", 1 << 17, 12, dict(n_mh_steps=2, n_blocks=1, adaptive=0)),
-             ("threeeq_blocks_adaptive", 40000, 16, dict(n_mh_steps=1, n_blocks=3, adaptive=1))]
+             ("threeeq_blocks_adaptive", 65000, 16, dict(n_mh_steps=1, n_blocks=3, adaptive=1))]
     for name, N, n_stage, kw in cases:
         if name == "linreg20":
             params, lk, _ = W.linear_gaussian(d=20, T=256, prior_sd=1.0)
