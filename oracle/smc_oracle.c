@@ -849,7 +849,7 @@ ORC_API orc_proposal *orc_proposal_create(int d, int n_free, const double *mean_
             for (int j = 0; j < n; ++j) p->Lc[b][(size_t)i * n + j] = c * L[(size_t)i * n + j];
             p->sd[b][i] = sqrt(S[(size_t)i * n + i]);
             p->mu[b][i] = mean_fr[p->mfree[b][i]];
-            ld = ld + log(p->Lc[b][(size_t)i * n + i]);
+            ld = ld + orc_log(p->Lc[b][(size_t)i * n + i]);
         }
         p->logdet_c[b] = 2.0 * ld;
         free(S); free(L);

@@ -47,7 +47,9 @@ struct LikSlot {
 struct MutConst {
     double L[NBMAX][PACKMAX];   // c * L_b embedded in parameter order, packed lower: [i(i+1)/2 + j]
     double csd[NBMAX][DMAX];    // c * sqrt(Sigma_ii)
+    double sd[NBMAX][DMAX];     // sqrt(Sigma_ii) WITHOUT c (diagonal mixture density, helpers.jl:146)
     double mu[DMAX];            // theta_bar
+    double lognorm[NBMAX];      // n_b log(2 pi) + log det(c^2 Sigma_b)
     uint32_t mask[NBMAX];
     int32_t bsize[NBMAX];
     int32_t n_blocks, status;
@@ -133,7 +135,7 @@ __host__ __device__ inline size_t col_off(int64_t N, int j) { return (size_t)j *
 int mutate_upload_model(Ctx* ctx);                      // priors + likelihood slots -> __constant__
 int mutate_upload_proposal(Ctx* ctx, bool from_device); // MutConst -> __constant__
 bool mutate_supported(const Ctx* ctx, bool has_old);
-int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage);
+int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage);
 int evaluate_launch(Ctx* ctx, int mode);
 
 }  // namespace smc

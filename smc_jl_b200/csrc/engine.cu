@@ -852,7 +852,7 @@ int32_t smcb200_mutate(smcb200_ctx* c, const double* mean_fr, const double* cov_
     int st = check_ready(c, true); if (st) return st;
     if (!mean_fr || !cov_fr || !block_sizes || !blocks_all) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
     if (n_free != c->n_free) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_free does not match the ParameterVector");
-    if (alpha != 1.0) return fail(c, SMCB200_ERR_UNSUPPORTED, "mixture proposal (alpha < 1) has no device kernel yet");
+    if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "alpha must be within [0, 1]");
     if (n_mh_steps < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_mh_steps must be >= 1");
     cudaSetDevice(c->device);
     BlockSpec bs;
@@ -868,7 +868,7 @@ int32_t smcb200_mutate(smcb200_ctx* c, const double* mean_fr, const double* cov_
     if (st) return fail(c, SMCB200_ERR_NOT_POSDEF, "proposal covariance is not positive definite");
     st = mutate_upload_proposal(c, false); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    st = mutate_launch(c, phi_n, n_mh_steps, has_old != 0, seed, stage); if (st) return st;
+    st = mutate_launch(c, phi_n, alpha, n_mh_steps, has_old != 0, seed, stage); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
     st = mean_accept(c); if (st) return st;
     SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
@@ -883,7 +883,7 @@ int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_s
 {
     int st = check_ready(c, true); if (st) return st;
     if (!cfg || !state || !res) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
-    if (cfg->alpha != 1.0) return fail(c, SMCB200_ERR_UNSUPPORTED, "mixture proposal (alpha < 1) has no device kernel yet");
+    if (!(cfg->alpha >= 0.0 && cfg->alpha <= 1.0)) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "alpha must be within [0, 1]");
     if (!(cfg->prior_weight >= 0.0 && cfg->prior_weight <= 1.0))
         return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
     cudaSetDevice(c->device);
@@ -936,7 +936,7 @@ int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_s
     st = mutate_upload_proposal(c, true); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    st = mutate_launch(c, phi_n, cfg->n_mh_steps, cfg->has_old_data != 0, cfg->seed, cfg->stage); if (st) return st;
+    st = mutate_launch(c, phi_n, cfg->alpha, cfg->n_mh_steps, cfg->has_old_data != 0, cfg->seed, cfg->stage); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
     st = mean_accept(c); if (st) return st;
     SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));

@@ -693,7 +693,7 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
         out->bsize[b] = n;
         uint32_t mask = 0;
         for (int e = 0; e < PACKMAX; ++e) out->L[b][e] = 0.0;
-        for (int k = 0; k < DMAX; ++k) out->csd[b][k] = 0.0;
+        for (int k = 0; k < DMAX; ++k) { out->csd[b][k] = 0.0; out->sd[b][k] = 0.0; }
         for (int i = 0; i < n; ++i) {
             mask |= 1u << bs.member[b][i];
             for (int j = 0; j < n; ++j) {
@@ -712,7 +712,12 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
                 out->L[b][ai * (ai + 1) / 2 + aj] = c * L[i * n + j];
             }
             out->csd[b][ai] = c * sqrt(S[i * n + i]);
+            out->sd[b][ai] = sqrt(S[i * n + i]);
         }
+        // log-normaliser of N(.; ., c^2 Sigma_b): n log(2 pi) + 2 sum_i log(c L_ii)  (members ascending)
+        double ld = 0.0;
+        for (int i = 0; i < n; ++i) ld = ld + det_log(c * L[i * n + i]);
+        out->lognorm[b] = (double)n * (2.0 * 0.91893853320467274178) + 2.0 * ld;
     }
     return 0;
 }
@@ -744,6 +749,7 @@ k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ c
         const int n = bs.bsize[b];
         for (int e = lane; e < PACKMAX; e += 32) out->L[b][e] = 0.0;
         out->csd[b][lane] = 0.0;
+        out->sd[b][lane] = 0.0;
         uint32_t mask = 0;
         for (int i = 0; i < n; ++i) mask |= 1u << bs.member[b][i];
         if (lane == 0) { out->mask[b] = mask; out->bsize[b] = n; }
@@ -779,6 +785,12 @@ k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ c
                 out->L[b][ai * (ai + 1) / 2 + aj] = c * L[lane][j];
             }
             out->csd[b][ai] = c * sqrt(S[lane][lane]);
+            out->sd[b][ai] = sqrt(S[lane][lane]);
+        }
+        if (lane == 0) {
+            double ld = 0.0;
+            for (int i = 0; i < n; ++i) ld = ld + det_log(c * L[i][i]);
+            out->lognorm[b] = (double)n * (2.0 * 0.91893853320467274178) + 2.0 * ld;
         }
         __syncwarp();
     }

@@ -118,8 +118,28 @@ struct GaussReg {
     }
 };
 
+// Quadratic form v' (c^2 Sigma_b)^{-1} v through the scaled factor embedded in parameter order: forward
+// substitution row by row (each y_i one fma chain over ascending j, then ONE division), v is overwritten by
+// y.  Entries of v outside the block must be 0 (their factor entries are 0, so the chain passes through).
+template <int D>
+__device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
+{
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if ((mask >> i) & 1u) {
+            double s = v[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) s = fma(-c_mut.L[b][(i * (i + 1)) / 2 + j], v[j], s);
+            v[i] = s / c_mut.L[b][(i * (i + 1)) / 2 + i];
+            q = fma(v[i], v[i], q);
+        }
+    }
+    return q;
+}
+
 struct MutArgs {
-    double phi_n;
+    double phi_n, alpha;
     int n_mh_steps, n_blocks, n_free;
     uint64_t seed;
     uint32_t stage;
@@ -140,7 +160,9 @@ struct MutArgs {
 constexpr int MUT_THREADS = SMC_MUT_THREADS;
 constexpr int MUT_MINB20 = SMC_MUT_WARPS_PER_SM * 32 / MUT_THREADS;   // resident blocks asked of ptxas for D <= 20
 
-template <class LIK, bool HAS_OLD, bool SINGLE>
+// MIX = (alpha < 1): the three-component mixture proposal of mvnormal_mixture_draw (helpers.jl:87-100) and
+// the proposal densities of compute_proposal_densities (helpers.jl:128-164).
+template <class LIK, bool HAS_OLD, bool SINGLE, bool MIX>
 __global__ void __launch_bounds__(MUT_THREADS, (LIK::D <= 20) ? MUT_MINB20 : ((LIK::D <= 24) ? MUT_MINB20 * 4 / 5 : MUT_MINB20 * 3 / 5))
 k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 {
@@ -168,6 +190,14 @@ k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
             const uint32_t mask = c_mut.mask[b];
             const double* cur = flipped ? buf1 : buf0;
             double* cand = flipped ? buf0 : buf1;
+            // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
+            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
+            const double step_prob = u01(r4.x, r4.y);
+            int comp = 1;
+            if (MIX) {
+                const double u_mix = u01(r4.z, r4.w);
+                comp = (u_mix < a.alpha) ? 1 : ((u_mix < a.alpha + (1.0 - a.alpha) / 2.0) ? 2 : 3);
+            }
             // (1) normals of this block's members -> candidate buffer (used as scratch).  Rolled loop, two
             // independent Box-Muller pairs per trip: small code (instruction cache) and ILP 2 on the
             // dependent log / sqrt / sincos chains.
@@ -201,7 +231,14 @@ k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 const double t = cur[k * MUT_THREADS];
-                s[k] = ((mask >> k) & 1u) ? t + s[k] : t;              // s is now theta'
+                if (MIX) {
+                    // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
+                    const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
+                    const double base = (comp == 3) ? c_mut.mu[k] : t;
+                    s[k] = ((mask >> k) & 1u) ? base + inc : t;
+                } else {
+                    s[k] = ((mask >> k) & 1u) ? t + s[k] : t;          // s is now theta'
+                }
                 cand[k * MUT_THREADS] = s[k];
             }
             const bool ok = in_bounds<D>(s);
@@ -211,9 +248,39 @@ k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
             double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
             if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
             // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
-            const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + 0.0);
-            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
-            const double step_prob = u01(r4.x, r4.y);
+            double qdiff = 0.0;
+            if (MIX) {
+                // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
+                // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
+                // fma chains, so one evaluation serves both.
+                const double lognorm = c_mut.lognorm[b];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
+                double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if ((mask >> k) & 1u) {
+                        const double sdk = c_mut.sd[b][k];
+                        const double zs = s[k] / sdk;
+                        ind = ind / (sdk * 0x1.40d931ff62705p+1) * det_exp(-0.5 * (zs * zs));
+                    }
+                const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+                const double w2 = (1.0 - a.alpha) / 2.0;
+                double q0 = a.alpha * e_sym, q1 = a.alpha * e_sym;
+                q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
+                q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
+                q0 = det_log(q0); q1 = det_log(q1);
+                if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
+                qdiff = q0 - q1;
+            }
+            const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + qdiff);
             if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
                 flipped = !flipped;
                 like = ln; lpri = pn; lprev = lo;
@@ -253,7 +320,7 @@ __global__ void __launch_bounds__(128) k_evaluate(double* __restrict__ cloud, in
 // ---- dispatch ------------------------------------------------------------------------------------
 struct KernelEntry {
     int neq, k, stride, coef, sig, d;
-    void (*mut[2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single]
+    void (*mut[2][2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single][mixture]
     void (*eval)(double*, int64_t, int);
 };
 
@@ -262,10 +329,14 @@ static KernelEntry make_entry()
 {
     KernelEntry e;
     e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
-    e.mut[0][0] = k_mutate<LIK, false, false>;
-    e.mut[0][1] = k_mutate<LIK, false, true>;
-    e.mut[1][0] = k_mutate<LIK, true, false>;
-    e.mut[1][1] = k_mutate<LIK, true, true>;
+    e.mut[0][0][0] = k_mutate<LIK, false, false, false>;
+    e.mut[0][1][0] = k_mutate<LIK, false, true, false>;
+    e.mut[1][0][0] = k_mutate<LIK, true, false, false>;
+    e.mut[1][1][0] = k_mutate<LIK, true, true, false>;
+    e.mut[0][0][1] = k_mutate<LIK, false, false, true>;
+    e.mut[0][1][1] = k_mutate<LIK, false, true, true>;
+    e.mut[1][0][1] = k_mutate<LIK, true, false, true>;
+    e.mut[1][1][1] = k_mutate<LIK, true, true, true>;
     e.eval = k_evaluate<LIK>;
     return e;
 }
@@ -334,7 +405,7 @@ int mutate_upload_proposal(Ctx* ctx, bool from_device)
     return SMCB200_OK;
 }
 
-int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage)
+int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage)
 {
     const KernelEntry* e = find_entry(ctx);
     if (!e || !mutate_supported(ctx, has_old)) {
@@ -342,12 +413,12 @@ int mutate_launch(Ctx* ctx, double phi_n, int n_mh_steps, bool has_old, uint64_t
         return SMCB200_ERR_UNSUPPORTED;
     }
     MutArgs a;
-    a.phi_n = phi_n; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
+    a.phi_n = phi_n; a.alpha = alpha; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
     a.seed = seed; a.stage = stage;
     const bool single = (a.n_blocks == 1);
     const unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
     const size_t smem = sizeof(double) * 2 * (size_t)e->d * MUT_THREADS;
-    auto kern = e->mut[has_old ? 1 : 0][single ? 1 : 0];
+    auto kern = e->mut[has_old ? 1 : 0][single ? 1 : 0][alpha < 1.0 ? 1 : 0];
     if (smem > 48 * 1024)
         SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, MUT_THREADS, smem, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);

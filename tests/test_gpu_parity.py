@@ -201,7 +201,7 @@ def test_selection_and_moments_bitexact(eng, N, d):
     assert np.all(got[:, -1] == 1.0)
 
 
-def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, stage):
+def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, stage, alpha=1.0):
     N, d = P.shape[0], spec.d
     free = spec.free_inds
     mean = np.average(P[:, :d], axis=0, weights=P[:, -1])
@@ -212,7 +212,7 @@ def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, 
     eng.cloud_create(N, d)
     eng.set_model(spec)
     eng.upload(P)
-    acc = eng.mutate(mean_fr, cov_fr, blocks_free, blocks_all, phi_n, phi_n1, c=c, alpha=1.0, n_mh_steps=n_mh,
+    acc = eng.mutate(mean_fr, cov_fr, blocks_free, blocks_all, phi_n, phi_n1, c=c, alpha=alpha, n_mh_steps=n_mh,
                      has_old_data=has_old, seed=seed, stage=stage)
     got = eng.download()
     L = O.lib()
@@ -223,7 +223,7 @@ def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, 
                                np.concatenate(blocks_all).astype(np.int32), c, C.byref(st))
     assert pr and st.value == 0
     buf = O.cloud_f(P)
-    L.orc_mutate(mod.h, pr, buf, N, 0, phi_n, phi_n1, 1.0, n_mh, len(free), int(has_old), seed, stage, 0)
+    L.orc_mutate(mod.h, pr, buf, N, 0, phi_n, phi_n1, alpha, n_mh, len(free), int(has_old), seed, stage, 0)
     L.orc_proposal_free(pr)
     want = O.cloud_m(buf, N, d)
     oacc = L.orc_mean_accept(buf, N, d)
@@ -302,6 +302,45 @@ def test_mutation_three_equation_blocks_and_old_data_bitexact(eng):
     assert acc == oacc and acc > 0.0
 
 
+@pytest.mark.parametrize("d,n_mh,alpha", [(20, 2, 0.9), (8, 3, 0.5), (2, 1, 0.0)])
+def test_mutation_mixture_proposal_bitexact(eng, d, n_mh, alpha):
+    """alpha < 1: three-component mixture draw (helpers.jl:87-100) and proposal densities (:128-164)."""
+    params, lk, _ = W.linear_gaussian(d=d, T=64)
+    spec = M.make_spec(params, lk)
+    rng = np.random.default_rng(100 + d)
+    N = 4096 + 11
+    P = _evaluated_cloud(eng, spec, params, N, rng)
+    P[:, -1] = rng.uniform(0.5, 1.5, N)
+    got, want, acc, oacc = _mutation_case(eng, spec, P, [np.arange(d)], 0.05, 0.02, 0.4, n_mh, False, 1793, 5, alpha=alpha)
+    assert np.array_equal(got, want)
+    assert acc == oacc and acc > 0.0
+    # the mixture moved particles differently from the pure random walk
+    got1, _, _, _ = _mutation_case(eng, spec, P, [np.arange(d)], 0.05, 0.02, 0.4, n_mh, False, 1793, 5, alpha=1.0)
+    assert not np.array_equal(got, got1)
+
+
+def test_mutation_mixture_blocks_old_data_bitexact(eng):
+    """The reference's test-suite settings (alpha = 0.9, test/smc.jl:29) with 3 random blocks and old data."""
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters()
+    spec = M.make_spec(params, M.LinearEquationsLogLik(data, X), M.LinearEquationsLogLik(data[:, :50], X))
+    rng = np.random.default_rng(5)
+    N = 3000
+    P = W.initial_cloud(params, N, rng)
+    P[:, :9] = np.abs(rng.normal(1.5, 0.5, (N, 9)))
+    eng.cloud_create(N, 9)
+    eng.set_model(spec)
+    eng.upload(P)
+    eng.evaluate(0)
+    P = eng.download()
+    mod = O.Model(spec)
+    P[:, 11] = [mod.loglik(np.ascontiguousarray(P[r, :9]), 1) for r in range(N)]
+    blocks = [np.array([6, 1, 4]), np.array([0, 8, 3]), np.array([2, 7, 5])]
+    got, want, acc, oacc = _mutation_case(eng, spec, P, blocks, 0.3, 0.2, 0.3, 2, True, 7, 11, alpha=0.9)
+    assert np.array_equal(got, want)
+    assert acc == oacc and acc > 0.0
+
+
 def test_mutation_golden(eng, golden):
     """Reference golden test/mutation.jl:1-59 through the CUDA path (reject-all pass-through, accept = 0)."""
     g = golden("mutation.npz")
@@ -332,7 +371,7 @@ def test_not_posdef_is_an_error(eng):
         eng.mutate(np.zeros(4), bad, [np.arange(4)], [np.arange(4)], 0.1, 0.0)
 
 
-def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False):
+def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False, alpha=1.0):
     """Run stages on the GPU (fused smcb200_stage) and in the oracle (orc_stage); compare everything."""
     from smc_jl_b200._lib import StageConfig, StageState
     N, d = P0.shape[0], spec.d
@@ -340,7 +379,7 @@ def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False):
     eng.set_model(spec)
     eng.upload(P0)
     state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2, resampled_last_period=0)
-    io = O.StageIO(threshold_ratio=0.5, target=0.25, alpha=1.0, tempering_target=0.95, pw=0.0, log_prob_old_data=0.0,
+    io = O.StageIO(threshold_ratio=0.5, target=0.25, alpha=alpha, tempering_target=0.95, pw=0.0, log_prob_old_data=0.0,
                    n_mh_steps=cfg_kw["n_mh_steps"], n_blocks=cfg_kw["n_blocks"], resample_method=0, adaptive=int(adaptive),
                    has_old=cfg_kw.get("has_old", 0), nthreads=0, seed=1793, c=0.5, accept=0.25, ess_prev=float(N),
                    resampled_last=0, j=2, phi_prop=0.0)
@@ -352,7 +391,7 @@ def _run_stages(eng, spec, P0, sched, n_stage, cfg_kw, adaptive=False):
     for s in range(n_stage):
         stage = s + 2
         phi_n = float(sched[s + 1])
-        cfg = StageConfig(phi_n1=phi_prev, phi_n=phi_n, threshold_ratio=0.5, target=0.25, alpha=1.0, tempering_target=0.95,
+        cfg = StageConfig(phi_n1=phi_prev, phi_n=phi_n, threshold_ratio=0.5, target=0.25, alpha=alpha, tempering_target=0.95,
                           prior_weight=0.0, log_prob_old_data=0.0, n_mh_steps=cfg_kw["n_mh_steps"], n_blocks=cfg_kw["n_blocks"],
                           resample_method=0, adaptive=int(adaptive), has_old_data=cfg_kw.get("has_old", 0), seed=1793, stage=stage)
         res, inc, nw = eng.stage(cfg, state, schedule=sched, want_inc=True, want_normw=True)
@@ -401,6 +440,18 @@ def test_stage_trajectory_blocks_old_data_bitexact(eng):
     P0[:, 11] = [mod.loglik(np.ascontiguousarray(P0[r, :9]), 1) for r in range(N)]
     sched = (np.arange(25) / 24.0) ** 2.0
     n_res, phi = _run_stages(eng, spec, P0, sched, 24, dict(n_mh_steps=2, n_blocks=3, has_old=1))
+    assert phi == 1.0 and n_res >= 2
+
+
+def test_stage_trajectory_mixture_blocks_bitexact(eng):
+    """test/smc.jl:13-87 settings (3-equation model, alpha = 0.9) with 3 blocks: whole trajectory bit-exact."""
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters(prior_para=10.0)
+    spec = M.make_spec(params, M.LinearEquationsLogLik(data, X))
+    N = 5000
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(18))
+    sched = (np.arange(25) / 24.0) ** 2.1
+    n_res, phi = _run_stages(eng, spec, P0, sched, 24, dict(n_mh_steps=1, n_blocks=3), alpha=0.9)
     assert phi == 1.0 and n_res >= 2
 
 
