@@ -598,7 +598,7 @@ ORC_API int orc_cholesky(const double *A, int n, double *L)
 /* Model: priors (ModelConstructors.prior / update! semantics) + likelihoods     */
 /* ------------------------------------------------------------------------------------------ */
 enum { PRIOR_NORMAL = 0, PRIOR_UNIFORM = 1, PRIOR_GAMMA = 2, PRIOR_ROOT_INV_GAMMA = 3, PRIOR_BETA = 4, PRIOR_INV_GAMMA = 5 };
-enum { LIK_NONE = 0, LIK_GAUSSREG = 1 };
+enum { LIK_NONE = 0, LIK_GAUSSREG = 1, LIK_AS_DSGE = 2 };
 #define MAX_D 64
 #define MAX_EQ 8
 
@@ -615,6 +615,7 @@ typedef struct {
     double lo[MAX_D], hi[MAX_D], p1[MAX_D], p2[MAX_D], cst[MAX_D], a1[MAX_D], a2[MAX_D];
     int lik_kind[2];
     gaussreg gr[2];
+    struct { int T, npre; double *data; } as[2];   /* An-Schorfheide DSGE likelihood (as_model.c) */
 } orc_model;
 
 ORC_API orc_model *orc_model_create(int d)
@@ -629,6 +630,7 @@ ORC_API void orc_model_free(orc_model *m)
     if (!m) return;
     for (int s = 0; s < 2; ++s)
         for (int e = 0; e < MAX_EQ; ++e) { free(m->gr[s].bhat[e]); free(m->gr[s].U[e]); }
+    free(m->as[0].data); free(m->as[1].data);
     free(m);
 }
 
@@ -747,9 +749,22 @@ static double gaussreg_ll(const gaussreg *g, const double *theta)
     }
     return ll;
 }
+/* An-Schorfheide DSGE likelihood (config C4): data 3 x T column-major, first npre periods unscored */
+double orc_as_loglik(const double *th, const double *data, int T, int npre);   /* as_model.c */
+ORC_API int orc_model_set_as(orc_model *m, int slot, int T, int npre, const double *data)
+{
+    if (slot < 0 || slot > 1 || m->d != 16 || T < 1 || npre < 0) return 3;
+    free(m->as[slot].data);
+    m->as[slot].data = (double *)malloc(sizeof(double) * 3 * (size_t)T);
+    memcpy(m->as[slot].data, data, sizeof(double) * 3 * (size_t)T);
+    m->as[slot].T = T; m->as[slot].npre = npre;
+    m->lik_kind[slot] = LIK_AS_DSGE;
+    return 0;
+}
 ORC_API double orc_loglik(const orc_model *m, int slot, const double *theta)
 {
     if (m->lik_kind[slot] == LIK_GAUSSREG) return gaussreg_ll(&m->gr[slot], theta);
+    if (m->lik_kind[slot] == LIK_AS_DSGE) return orc_as_loglik(theta, m->as[slot].data, m->as[slot].T, m->as[slot].npre);
     return NAN;
 }
 

@@ -14,7 +14,7 @@ import numpy as np
 
 # prior kinds (values are part of the C ABI, include/smcb200.h)
 PRIOR_NORMAL, PRIOR_UNIFORM, PRIOR_GAMMA, PRIOR_ROOT_INV_GAMMA, PRIOR_BETA, PRIOR_INV_GAMMA = range(6)
-LIK_NONE, LIK_GAUSSREG = 0, 1
+LIK_NONE, LIK_GAUSSREG, LIK_AS_DSGE = 0, 1, 2
 
 
 @dataclass(frozen=True)
@@ -190,6 +190,35 @@ def CAPMLogLik(lik_data, market_data, as_written=False):
     return GaussRegLogLik(neq, 1, 3, 0, 2, np.concatenate(eqs), 3 * neq)
 
 
+@dataclass
+class AnSchorfheideLogLik:
+    """Log-likelihood of the three-equation An-Schorfheide DSGE model (BASELINE config C4):
+    examples/dsge_models/small_dsge_model.jl:35-50 -> `DSGE.likelihood(m, data; sampler=false,
+    catch_errors=true, use_chand_recursion=true)`.  `data` is 3 x T (gdp growth, inflation, nominal rate),
+    the first `n_presample` periods are filtered but not scored.  The ParameterVector must be the model's
+    16 parameters (tau, kappa, psi_1, psi_2, rA, pi_star, gamma_Q, rho_R, rho_g, rho_z, sigma_R, sigma_g,
+    sigma_z, e_y, e_pi, e_R).  Solved and filtered on the device (csrc/aslik.cuh)."""
+    data: np.ndarray
+    n_presample: int = 2
+    n_para: int = 16
+    kind: int = LIK_AS_DSGE
+
+    def __post_init__(self):
+        self.data = np.ascontiguousarray(np.asarray(self.data, dtype=np.float64))
+        if self.data.ndim != 2 or self.data.shape[0] != 3 or self.data.shape[1] < 1:
+            raise ValueError("An-Schorfheide data must be 3 x T")
+        if not np.all(np.isfinite(self.data)):
+            raise ValueError("missing observations (NaN) are not supported by the device Kalman filter")
+
+    def iparams(self):
+        return np.array([self.data.shape[1], self.n_presample], dtype=np.int32)
+
+    @property
+    def eqdata(self):
+        """column-major 3 x T (the Julia matrix bytes)"""
+        return np.ascontiguousarray(self.data.T).ravel()
+
+
 # ------------------------------------------------------------------------------------------------
 # flat model spec handed to the C ABI (and, in tests, to the oracle)
 # ------------------------------------------------------------------------------------------------
@@ -204,7 +233,7 @@ class ModelSpec:
     p2: np.ndarray
     values: np.ndarray
     keys: List[str]
-    liks: List[Optional[GaussRegLogLik]] = field(default_factory=lambda: [None, None])
+    liks: List[Optional[object]] = field(default_factory=lambda: [None, None])
 
     @property
     def free_inds(self):
@@ -230,7 +259,7 @@ def make_spec(parameters: Sequence[Parameter], loglikelihood=None, old_loglikeli
             p1[i], p2[i] = p.prior.params()
     for lk in (loglikelihood, old_loglikelihood):
         if lk is not None:
-            if not isinstance(lk, GaussRegLogLik):
+            if not isinstance(lk, (GaussRegLogLik, AnSchorfheideLogLik)):
                 raise TypeError("loglikelihood must be a device likelihood descriptor (e.g. LinearGaussianLogLik); "
                                 "arbitrary host callables cannot run on the GPU and there is no CPU fallback")
             if lk.n_para != d:

@@ -52,6 +52,23 @@ def synthetic_three_equation(T=100, seed=1793):
     return a * X + a + err, X
 
 
+def an_schorfheide_parameters():
+    """Config C4: the An-Schorfheide ParameterVector stored in the reference's fixtures
+    (test/reference/one_draw_in.jld2): 13 free parameters, 3 fixed measurement errors."""
+    big, rho_hi = (1e-20, 1e5), (1e-20, 0.9999999)
+    spec = [("τ", 1.6735264339099827, big, M.Gamma(16.0, 0.125)), ("κ", 0.017686826714964354, (1e-20, 10.0), M.Uniform(0.0, 1.0)),
+            ("ψ_1", 1.405751678057145, big, M.Gamma(36.0, 1.0 / 24.0)), ("ψ_2", 0.21072315533472247, big, M.Gamma(4.0, 0.125)),
+            ("rA", 0.09536887782738207, big, M.Gamma(1.0, 0.5)), ("π_star", 2.536422981325555, big, M.Gamma(12.25, 0.5714285714285714)),
+            ("γ_Q", 0.6164762411216859, big, M.Normal(0.4, 0.2)), ("ρ_R", 0.1600060971420918, rho_hi, M.Uniform(0.0, 1.0)),
+            ("ρ_g", 0.4229562655081418, rho_hi, M.Uniform(0.0, 1.0)), ("ρ_z", 0.602297580266383, rho_hi, M.Uniform(0.0, 1.0)),
+            ("σ_R", 0.40411072598543146, big, M.RootInverseGamma(4.0, 0.4)), ("σ_g", 1.3307835750296042, big, M.RootInverseGamma(4.0, 1.0)),
+            ("σ_z", 0.22539373793338302, big, M.RootInverseGamma(4.0, 0.5))]
+    ps = [M.parameter(k, v, b, b, None, pr) for k, v, b, pr in spec]
+    for k, v in (("e_y", 0.1159846), ("e_π", 0.2941664), ("e_R", 0.4475874)):
+        ps.append(M.parameter(k, v, (v, v), (v, v), None, None, fixed=True))
+    return ps
+
+
 def prior_draw(parameters, n, rng):
     """rand(parameters, n) (src/initialization.jl:27): every free parameter from its prior, redrawn until
     inside its valuebounds; fixed parameters keep their value.  Returns n x n_para."""

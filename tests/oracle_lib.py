@@ -15,8 +15,8 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = os.path.join(ORACLE_DIR, "smc_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("smc_oracle.c", "as_model.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], env={**os.environ, "CC": "gcc"})
     return _SO
 
@@ -67,6 +67,8 @@ def lib():
         "orc_model_create": (vp, [C.c_int]), "orc_model_free": (None, [vp]),
         "orc_model_set_params": (C.c_int, [vp, i32p, f64p, f64p, i32p, f64p, f64p]),
         "orc_model_set_gaussreg": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p]),
+        "orc_model_set_as": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64p]),
+        "orc_as_loglik": (d, [f64p, f64p, C.c_int, C.c_int]),
         "orc_logprior": (d, [vp, f64p]), "orc_loglik": (d, [vp, C.c_int, f64p]),
         "orc_loglik_lineq_direct": (d, [f64p, f64p, f64p, C.c_int, C.c_int]),
         "orc_loglik_linreg_direct": (d, [f64p, f64p, f64p, C.c_int, C.c_int, d]),
@@ -106,8 +108,11 @@ class Model:
         for slot, lk in enumerate(spec.liks):
             if lk is None:
                 continue
-            st = L.orc_model_set_gaussreg(self.h, slot, lk.neq, lk.k, lk.stride, lk.coef_off, lk.sig_off,
-                                          np.ascontiguousarray(lk.eqdata))
+            if lk.kind == 2:    # An-Schorfheide DSGE
+                st = L.orc_model_set_as(self.h, slot, lk.data.shape[1], lk.n_presample, lk.eqdata)
+            else:
+                st = L.orc_model_set_gaussreg(self.h, slot, lk.neq, lk.k, lk.stride, lk.coef_off, lk.sig_off,
+                                              np.ascontiguousarray(lk.eqdata))
             assert st == 0
 
     def __del__(self):

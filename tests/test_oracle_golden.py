@@ -11,6 +11,7 @@ import pytest
 
 import oracle_lib as O
 from smc_jl_b200 import model as M
+from smc_jl_b200 import workloads as W
 
 
 def linear_test_model(data, X, old_data=None):
@@ -187,6 +188,57 @@ def test_as_priors_golden(golden):
         P = g[name]
         for r in range(P.shape[0]):
             assert mod.logprior(np.ascontiguousarray(P[r, :16])) == pytest.approx(P[r, 17], rel=1e-13, abs=2e-13)
+
+
+def test_as_parameter_vector_matches_fixture(golden):
+    g = golden("as_clouds.npz")
+    spec = M.make_spec(W.an_schorfheide_parameters())
+    assert np.array_equal(spec.fixed, g["fixed"]) and np.array_equal(spec.kind[:13], g["prior_kind"][:13])
+    assert np.array_equal(spec.p1[:13], g["prior_p1"][:13]) and np.array_equal(spec.p2[:13], g["prior_p2"][:13])
+    assert np.array_equal(spec.lo, g["lo"]) and np.array_equal(spec.hi, g["hi"]) and np.array_equal(spec.values, g["value"])
+
+
+def test_as_loglik_golden(golden):
+    """An-Schorfheide DSGE log-likelihood (config C4; the model lives in DSGE.jl, not in the reference tree):
+    the oracle's reduced solver + 6-state Kalman filter reproduces all 2 000 reference-produced
+    (theta -> loglh) rows and the 600 old_loglh rows (old data = first 115 columns) -- SURVEY 4 / App. A."""
+    g = golden("as_clouds.npz")
+    data = g["data"]
+    L = O.lib()
+
+    def ll(theta, T):
+        return L.orc_as_loglik(np.ascontiguousarray(theta), np.ascontiguousarray(data[:, :T].T).ravel(), T, 2)
+    for name, col, T, rtol in (("cloud1000", 16, 115, 2e-11), ("cloud600", 16, 230, 2e-11), ("cloud600", 18, 115, 2e-11),
+                               ("prior_draws", 16, 230, 1e-6)):
+        P = g[name]
+        got = np.array([ll(P[r, :16], T) for r in range(P.shape[0])])
+        rel = np.abs(got - P[:, col]) / np.maximum(1.0, np.abs(P[:, col]))
+        assert np.all(np.isfinite(got))
+        assert np.median(rel) < 1e-14, (name, np.median(rel))
+        assert rel.max() < rtol, (name, col, rel.max(), int(rel.argmax()))
+    # prior draws: everything but the near-unit-root row (rho_z = 0.999999: the reference's own Lyapunov
+    # initialisation is ill-conditioned there) agrees to 1e-11
+    P = g["prior_draws"]
+    got = np.array([ll(P[r, :16], 230) for r in range(P.shape[0])])
+    rel = np.abs(got - P[:, 16]) / np.maximum(1.0, np.abs(P[:, 16]))
+    assert np.sort(rel)[-2] < 1e-11
+    # through the model object (slot 1 = old data)
+    ps = W.an_schorfheide_parameters()
+    mod = O.Model(M.make_spec(ps, M.AnSchorfheideLogLik(data), M.AnSchorfheideLogLik(data[:, :115])))
+    P = g["cloud600"]
+    assert mod.loglik(P[3, :16], 0) == ll(P[3, :16], 230) and mod.loglik(P[3, :16], 1) == ll(P[3, :16], 115)
+
+
+def test_as_loglik_indeterminacy_is_minus_inf(golden):
+    """psi_1 < 1 with a small psi_2 violates the Taylor principle: two stable roots => gensys reports
+    indeterminacy => DSGE.likelihood(catch_errors=true) returns -Inf (unpinned by any fixture row)."""
+    g = golden("as_clouds.npz")
+    th = g["cloud600"][0, :16].copy()
+    th[2], th[3] = 0.5, 0.01
+    d = np.ascontiguousarray(g["data"].T).ravel()
+    assert O.lib().orc_as_loglik(th, d, 230, 2) == -np.inf
+    th[2] = 1.5
+    assert np.isfinite(O.lib().orc_as_loglik(th, d, 230, 2))
 
 
 def test_detmath_vs_libm():
