@@ -59,11 +59,17 @@ enum {
 /* likelihood families with a device functor */
 enum {
     SMCB200_LIK_NONE = 0,
-    SMCB200_LIK_GAUSSREG = 1 /* Gaussian regression family in centred sufficient-statistic form:
+    SMCB200_LIK_GAUSSREG = 1, /* Gaussian regression family in centred sufficient-statistic form:
                                 iparams = {n_eq, k, stride, coef_off, sig_off(-1 = sigma known)},
                                 dparams = per equation {T, qscale, rss, sigma_fixed, bhat[k], U[k*k] (upper, row-major)}.
                                 Covers examples/regression_model (:46-53), test/modelsetup.jl:119-138 and
                                 examples/capm_model (:48-69). */
+    SMCB200_LIK_AS_DSGE = 2  /* three-equation An-Schorfheide DSGE model (BASELINE config C4): the user likelihood
+                                `DSGE.likelihood(m, data; sampler=false, catch_errors=true)` of
+                                examples/dsge_models/small_dsge_model.jl:35-50, solved (closed-form decision rule) and
+                                Kalman-filtered on the device.  n_para = 16 in DSGE.jl's AnSchorfheide order;
+                                iparams = {n_periods, n_presample (filtered, not scored)},
+                                dparams = data, 3 x n_periods column-major (gdp growth, inflation, nominal rate). */
 };
 
 enum { SMCB200_RESAMPLE_SYSTEMATIC = 0, SMCB200_RESAMPLE_MULTINOMIAL = 1 };

@@ -62,6 +62,25 @@ struct BlockSpec {              // host-built, passed by value to the proposal-p
 struct LikDesc {                // host copy of a likelihood slot's shape
     int kind = 0, neq = 0, k = 0, stride = 0, coef_off = 0, sig_off = -1;
 };
+struct ASConst {                // An-Schorfheide DSGE likelihood slot: 3 x T data (column-major) in global memory
+    const double* data;
+    int32_t T, npre;
+};
+struct MutArgs {
+    double phi_n, alpha;
+    int n_mh_steps, n_blocks, n_free;
+    uint64_t seed;
+    uint32_t stage;
+};
+struct Ctx;
+struct KernelEntry {            // one likelihood functor's kernels + the constant-memory uploaders of its translation unit
+    int kind, neq, k, stride, coef, sig, d;
+    void (*mut[2][2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single block][mixture]
+    void (*eval)(double*, int64_t, int);
+    void (*draw)(double*, int64_t, int64_t, const double*, uint64_t, int, int*);
+    int (*upload_model)(Ctx*);
+    int (*upload_proposal)(Ctx*, bool);
+};
 
 struct Ctx {
     int device = 0;
@@ -106,6 +125,8 @@ struct Ctx {
     PriorConst prior{};
     LikDesc lik[2];
     LikSlot lik_host[2]{};
+    ASConst as_host[2]{};
+    double* as_data[2] = {nullptr, nullptr};   // device copies of the An-Schorfheide data
     int n_free = 0;
     int free_idx[DMAX]{};
     // bookkeeping
@@ -130,6 +151,16 @@ inline int ilog2(int64_t n) { int k = 0; while ((int64_t(1) << k) < n) ++k; retu
 
 // column pointers of the struct-of-arrays cloud
 __host__ __device__ inline size_t col_off(int64_t N, int j) { return (size_t)j * (size_t)N; }
+
+// mutation kernel launch shape
+#ifndef SMC_MUT_THREADS
+#define SMC_MUT_THREADS 128
+#endif
+#ifndef SMC_MUT_WARPS_PER_SM
+#define SMC_MUT_WARPS_PER_SM 20
+#endif
+constexpr int MUT_THREADS = SMC_MUT_THREADS;
+constexpr int MUT_MINB20 = SMC_MUT_WARPS_PER_SM * 32 / MUT_THREADS;   // resident blocks asked of ptxas for D <= 20
 
 // ---- mutation dispatch (mutate.cu) ---------------------------------------------------------------
 int mutate_upload_model(Ctx* ctx);                      // priors + likelihood slots -> __constant__

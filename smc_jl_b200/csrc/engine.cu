@@ -465,6 +465,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFree(c->counters); cudaFree(c->scal); cudaFreeHost(c->h_scal); cudaFree(c->phi_state); cudaFreeHost(c->h_phi_state);
     cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
+    cudaFree(c->as_data[0]); cudaFree(c->as_data[1]);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -667,6 +668,21 @@ int32_t smcb200_set_likelihood(smcb200_ctx* c, int32_t slot, int32_t kind, const
                                int64_t n_dp)
 {
     if (!c || slot < 0 || slot > 1) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "slot must be 0 or 1") : SMCB200_ERR_BAD_ARGUMENT;
+    if (kind == SMCB200_LIK_AS_DSGE) {
+        if (n_ip < 2 || !ip || !dp) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "AS_DSGE needs iparams {n_periods, n_presample}");
+        const int T = ip[0], npre = ip[1];
+        if (T < 1 || npre < 0 || n_dp != (int64_t)3 * T) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "AS_DSGE data must be 3 x n_periods");
+        for (int64_t i = 0; i < n_dp; ++i)
+            if (!(dp[i] - dp[i] == 0.0)) return fail(c, SMCB200_ERR_UNSUPPORTED, "AS_DSGE: missing / non-finite observations are not supported");
+        cudaSetDevice(c->device);
+        if (c->as_data[slot]) { cudaFree(c->as_data[slot]); c->as_data[slot] = nullptr; }
+        SMC_CUDA(c, cudaMalloc(&c->as_data[slot], sizeof(double) * 3 * (size_t)T));
+        SMC_CUDA(c, cudaMemcpy(c->as_data[slot], dp, sizeof(double) * 3 * (size_t)T, cudaMemcpyHostToDevice));
+        c->as_host[slot].data = c->as_data[slot]; c->as_host[slot].T = T; c->as_host[slot].npre = npre;
+        LikDesc L; L.kind = kind;
+        c->lik[slot] = L;
+        return mutate_upload_model(c);
+    }
     if (kind != SMCB200_LIK_GAUSSREG) return fail(c, SMCB200_ERR_UNSUPPORTED, "likelihood family has no device functor");
     if (n_ip < 5 || !ip || !dp) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "GAUSSREG needs 5 iparams");
     LikDesc L; L.kind = kind; L.neq = ip[0]; L.k = ip[1]; L.stride = ip[2]; L.coef_off = ip[3]; L.sig_off = ip[4];

@@ -1,0 +1,359 @@
+// mutate_kernel.cuh -- K7: random-walk Metropolis-Hastings mutation of every particle, plus the stage-0
+// likelihood/prior evaluators that share its device functors.
+//
+// Replaces src/mutation.jl:56-138 fanned out at src/smc_main.jl:471-484 (one Distributed.jl task
+// per particle, 1 Cholesky + 4 SVD per MH step) with ONE kernel per stage:
+//   * one thread per particle: the cloud is a struct-of-arrays [n_para+5][N], so a warp's loads and
+//     stores of any column are 256 contiguous bytes; the particle lives in registers for all
+//     n_mh_steps * n_blocks steps, so HBM traffic is 8(2d+7) B/particle/stage regardless of n_mh_steps;
+//   * the scaled Cholesky factor c*L (factored ONCE per stage), the likelihood's sufficient statistics
+//     and the prior table live in __constant__ memory and enter the DFMAs as constant-bank operands
+//     (fully unrolled loops => immediate offsets): no shared-memory or register traffic for them;
+//   * counter-based Philox4x32-10 keyed on the GLOBAL particle index => results are invariant to the
+//     launch shape and to the number of GPUs.
+// The kernel is FP64-pipe bound (see DESIGN.md roofline), not HBM bound, for d >~ 8.
+//
+// This header is included by several translation units (mut_*.cu), each instantiating the kernels of a
+// few likelihood functors so that they compile in parallel.  Without relocatable device code every
+// translation unit owns its copies of the __constant__ blocks below; KernelEntry carries the upload
+// functions of the unit that owns the selected kernel.
+#pragma once
+#include "common.cuh"
+#include "aslik.cuh"
+
+namespace smc {
+namespace {
+
+__constant__ MutConst c_mut;
+__constant__ LikSlot c_lik[2];
+__constant__ PriorConst c_pri;
+
+// ---- priors (ModelConstructors.prior: sum over free parameters) ------------------
+// Families other than Normal sit behind a call so that the unrolled per-parameter code stays small
+// (the instruction cache matters: this kernel is latency bound).
+__device__ __noinline__ double logpdf_general(int k, double x)
+{
+    switch (c_pri.kind[k]) {
+    case SMCB200_PRIOR_UNIFORM:
+        return (x >= c_pri.p1[k] && x <= c_pri.p2[k]) ? c_pri.cst[k] : -dinf();
+    case SMCB200_PRIOR_GAMMA:
+        if (!(x > 0.0)) return (x == 0.0 && c_pri.a1[k] == 0.0) ? c_pri.cst[k] : -dinf();
+        return fma(c_pri.a1[k], det_log(x), c_pri.cst[k]) - x * c_pri.a2[k];
+    case SMCB200_PRIOR_ROOT_INV_GAMMA: {
+        if (!(x > 0.0)) return -dinf();
+        const double x2 = x * x;
+        return fma(-c_pri.a1[k], det_log(x2), c_pri.cst[k]) - c_pri.a2[k] / x2;
+    }
+    case SMCB200_PRIOR_BETA:
+        if (!(x > 0.0 && x < 1.0)) return -dinf();
+        return fma(c_pri.a2[k], det_log(1.0 - x), fma(c_pri.a1[k], det_log(x), c_pri.cst[k]));
+    case SMCB200_PRIOR_INV_GAMMA:
+        if (!(x > 0.0)) return -dinf();
+        return fma(-c_pri.a1[k], det_log(x), c_pri.cst[k]) - c_pri.a2[k] / x;
+    }
+    return dnan();
+}
+__device__ __forceinline__ double logpdf1(int k, double x)
+{
+    if (c_pri.kind[k] == SMCB200_PRIOR_NORMAL) {
+        const double z = (x - c_pri.p1[k]) * c_pri.a1[k];
+        return fma(-0.5 * z, z, c_pri.cst[k]);
+    }
+    return logpdf_general(k, x);
+}
+
+template <int D>
+__device__ __forceinline__ double logprior(const double (&th)[D])
+{
+    double lp = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (!c_pri.fixed[k]) lp = lp + logpdf1(k, th[k]);
+    return lp;
+}
+template <int D>
+__device__ __forceinline__ bool in_bounds(const double (&th)[D])
+{
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (!c_pri.fixed[k]) ok = ok && (th[k] >= c_pri.lo[k] && th[k] <= c_pri.hi[k]);
+    return ok;
+}
+
+
+// ---- Gaussian regression family (centred sufficient statistics) ---------------------------------
+template <int NEQ_, int K_, int STRIDE_, int COEF_, int SIG_>
+struct GaussReg {
+    static constexpr int KIND = SMCB200_LIK_GAUSSREG;
+    static constexpr int NEQ = NEQ_, K = K_, STRIDE = STRIDE_, COEF = COEF_, SIG = SIG_;
+    static constexpr int KP = K * (K + 1) / 2;
+    static constexpr int D_COEF = COEF + (NEQ - 1) * STRIDE + K;
+    static constexpr int D_SIG = (SIG >= 0) ? SIG + (NEQ - 1) * STRIDE + 1 : 0;
+    static constexpr int D = (D_COEF > D_SIG) ? D_COEF : D_SIG;
+    static constexpr int MINB = (D <= 20) ? MUT_MINB20 : ((D <= 24) ? MUT_MINB20 * 4 / 5 : MUT_MINB20 * 3 / 5);
+
+    template <int SLOT>
+    static __device__ __forceinline__ double ll(const double (&th)[D])
+    {
+        const LikSlot& L = c_lik[SLOT];
+        double ll = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) {
+            double dl[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) dl[j] = th[COEF + e * STRIDE + j] - L.bhat[e * K + j];
+            double q = L.rss[e];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                double r = 0.0;
+#pragma unroll
+                for (int j = i; j < K; ++j) r = fma(L.U[e * KP + i * K - (i * (i - 1)) / 2 + (j - i)], dl[j], r);
+                q = fma(r, r, q);
+            }
+            double logs, inv_s2;
+            if (SIG >= 0) {
+                const double s = th[(SIG >= 0 ? SIG : 0) + e * STRIDE];
+                bad = bad || !(s > 0.0);
+                logs = det_log(s);
+                inv_s2 = 1.0 / (s * s);
+            } else {
+                logs = L.logs[e];
+                inv_s2 = L.inv_s2[e];
+            }
+            const double le = fma(-L.T[e], logs, L.cT[e]) - (0.5 * L.qscale[e] * q) * inv_s2;
+            ll = ll + le;
+        }
+        return bad ? -dinf() : ll;
+    }
+};
+
+// Quadratic form v' (c^2 Sigma_b)^{-1} v through the scaled factor embedded in parameter order: forward
+// substitution row by row (each y_i one fma chain over ascending j, then ONE division), v is overwritten by
+// y.  Entries of v outside the block must be 0 (their factor entries are 0, so the chain passes through).
+template <int D>
+__device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
+{
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if ((mask >> i) & 1u) {
+            double s = v[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) s = fma(-c_mut.L[b][(i * (i + 1)) / 2 + j], v[j], s);
+            v[i] = s / c_mut.L[b][(i * (i + 1)) / 2 + i];
+            q = fma(v[i], v[i], q);
+        }
+    }
+    return q;
+}
+
+
+// One MH chain per thread.  The chain's current state lives in shared memory ([2][D][128] doubles:
+// current and candidate buffer, thread-private columns => conflict-free); registers hold only the working
+// vector, which is in turn the proposal increment, the candidate and (inside the likelihood) the centred
+// candidate.  Accepting a move flips which buffer is current.  This keeps the kernel under ~100 registers
+// (5 blocks = 20 warps per SM) -- it is FP64-latency bound, so resident warps are what buys throughput.
+// SINGLE = (n_blocks == 1): block index is a literal, so factor entries load as LDCU.128 pairs.
+
+// MIX = (alpha < 1): the three-component mixture proposal of mvnormal_mixture_draw (helpers.jl:87-100) and
+// the proposal densities of compute_proposal_densities (helpers.jl:128-164).
+template <class LIK, bool HAS_OLD, bool SINGLE, bool MIX>
+__global__ void __launch_bounds__(MUT_THREADS, LIK::MINB)
+k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
+{
+    constexpr int D = LIK::D;
+    extern __shared__ double sm_state[];
+    const int64_t i = (int64_t)blockIdx.x * MUT_THREADS + threadIdx.x;
+    if (i >= N) return;
+    double* buf0 = sm_state + threadIdx.x;
+    double* buf1 = sm_state + D * MUT_THREADS + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < D; ++k) buf0[k * MUT_THREADS] = cloud[col_off(N, k) + i];
+    double like = cloud[col_off(N, D) + i];
+    double lpri = cloud[col_off(N, D + 1) + i];
+    double lprev = cloud[col_off(N, D + 2) + i];
+    double accept = 0.0;
+    bool flipped = false;
+    const uint32_t gp = (uint32_t)(index0 + i);
+    const double phi = a.phi_n, omphi = 1.0 - a.phi_n;
+    const int nb = SINGLE ? 1 : a.n_blocks;
+
+    for (int step = 0; step < a.n_mh_steps; ++step) {
+        for (int bb = 0; bb < nb; ++bb) {
+            const int b = SINGLE ? 0 : bb;
+            const uint32_t sb = (uint32_t)(step * nb + b);
+            const uint32_t mask = c_mut.mask[b];
+            const double* cur = flipped ? buf1 : buf0;
+            double* cand = flipped ? buf0 : buf1;
+            // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
+            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
+            const double step_prob = u01(r4.x, r4.y);
+            int comp = 1;
+            if (MIX) {
+                const double u_mix = u01(r4.z, r4.w);
+                comp = (u_mix < a.alpha) ? 1 : ((u_mix < a.alpha + (1.0 - a.alpha) / 2.0) ? 2 : 3);
+            }
+            // (1) normals of this block's members -> candidate buffer (used as scratch).  Rolled loop, two
+            // independent Box-Muller pairs per trip: small code (instruction cache) and ILP 2 on the
+            // dependent log / sqrt / sincos chains.
+            constexpr int NPAIR = (D + 1) / 2;
+#pragma unroll 1
+            for (int p = 0; p < NPAIR; p += 2) {
+                if ((mask >> (2 * p)) & 15u) {
+                    double z0, z1, z2, z3;
+                    const u32x4 ra = rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)p, PURP_NORMAL);
+                    const u32x4 rb = rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)(p + 1), PURP_NORMAL);
+                    normal_pair(ra, z0, z1);
+                    normal_pair(rb, z2, z3);
+                    cand[(2 * p) * MUT_THREADS] = z0;
+                    if (2 * p + 1 < D) cand[(2 * p + 1) * MUT_THREADS] = z1;
+                    if (2 * p + 2 < D) cand[(2 * p + 2) * MUT_THREADS] = z2;
+                    if (2 * p + 3 < D) cand[(2 * p + 3) * MUT_THREADS] = z3;
+                }
+            }
+            // (2) proposal increment s = (c L) z, column by column (each s[r] sums over ascending columns)
+            double s[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) s[k] = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if ((mask >> j) & 1u) {
+                    const double zj = cand[j * MUT_THREADS];
+#pragma unroll
+                    for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][(r * (r + 1)) / 2 + j], zj, s[r]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const double t = cur[k * MUT_THREADS];
+                if (MIX) {
+                    // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
+                    const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
+                    const double base = (comp == 3) ? c_mut.mu[k] : t;
+                    s[k] = ((mask >> k) & 1u) ? base + inc : t;
+                } else {
+                    s[k] = ((mask >> k) & 1u) ? t + s[k] : t;          // s is now theta'
+                }
+                cand[k * MUT_THREADS] = s[k];
+            }
+            const bool ok = in_bounds<D>(s);
+            double pn = logprior<D>(s);
+            double ln = LIK::template ll<0>(s);
+            if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
+            double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
+            if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
+            // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
+            double qdiff = 0.0;
+            if (MIX) {
+                // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
+                // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
+                // fma chains, so one evaluation serves both.
+                const double lognorm = c_mut.lognorm[b];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
+                double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if ((mask >> k) & 1u) {
+                        const double sdk = c_mut.sd[b][k];
+                        const double zs = s[k] / sdk;
+                        ind = ind / (sdk * 0x1.40d931ff62705p+1) * det_exp(-0.5 * (zs * zs));
+                    }
+                const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+                const double w2 = (1.0 - a.alpha) / 2.0;
+                double q0 = a.alpha * e_sym, q1 = a.alpha * e_sym;
+                q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
+                q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
+                q0 = det_log(q0); q1 = det_log(q1);
+                if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
+                qdiff = q0 - q1;
+            }
+            const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + qdiff);
+            if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
+                flipped = !flipped;
+                like = ln; lpri = pn; lprev = lo;
+                accept += (double)c_mut.bsize[b];
+            }
+        }
+    }
+    const double* cur = flipped ? buf1 : buf0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = cur[k * MUT_THREADS];
+    cloud[col_off(N, D) + i] = like;
+    cloud[col_off(N, D + 1) + i] = lpri;
+    cloud[col_off(N, D + 2) + i] = lprev;
+    cloud[col_off(N, D + 3) + i] = accept / (double)a.n_free;      // particle.jl:410-418
+}
+
+// stage-0 evaluators: mode 0 = draw_likelihood (initialization.jl:129-139); mode 1 =
+// initialize_likelihoods! (:153-186): old_loglh <- loglh, then loglh/logprior on the new data
+template <class LIK>
+__global__ void __launch_bounds__(128) k_evaluate(double* __restrict__ cloud, int64_t N, int mode)
+{
+    constexpr int D = LIK::D;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= N) return;
+    double th[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = cloud[col_off(N, k) + i];
+    if (mode == 1) {
+        cloud[col_off(N, D + 2) + i] = cloud[col_off(N, D) + i];
+        cloud[col_off(N, D) + i] = LIK::template ll<0>(th);
+    } else {
+        cloud[col_off(N, D) + i] = in_bounds<D>(th) ? LIK::template ll<0>(th) : -dinf();
+    }
+    cloud[col_off(N, D + 1) + i] = logprior<D>(th);
+}
+
+// ---- per-translation-unit registration ---------------------------------------------------------------
+static int tu_upload_model(Ctx* ctx)
+{
+    SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_pri, &ctx->prior, sizeof(PriorConst), 0, cudaMemcpyHostToDevice, ctx->stream));
+    SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lik, ctx->lik_host, sizeof(LikSlot) * 2, 0, cudaMemcpyHostToDevice, ctx->stream));
+    SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_as, ctx->as_host, sizeof(ASConst) * 2, 0, cudaMemcpyHostToDevice, ctx->stream));
+    return SMCB200_OK;
+}
+
+static int tu_upload_proposal(Ctx* ctx, bool from_device)
+{
+    if (from_device) {
+        SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_mut, ctx->mutc_dev, sizeof(MutConst), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        SMC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_mut, ctx->mutc_host, sizeof(MutConst), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return SMCB200_OK;
+}
+
+template <class LIK>
+static KernelEntry make_entry()
+{
+    KernelEntry e;
+    e.kind = LIK::KIND;
+    e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
+    e.mut[0][0][0] = k_mutate<LIK, false, false, false>;
+    e.mut[0][1][0] = k_mutate<LIK, false, true, false>;
+    e.mut[1][0][0] = k_mutate<LIK, true, false, false>;
+    e.mut[1][1][0] = k_mutate<LIK, true, true, false>;
+    e.mut[0][0][1] = k_mutate<LIK, false, false, true>;
+    e.mut[0][1][1] = k_mutate<LIK, false, true, true>;
+    e.mut[1][0][1] = k_mutate<LIK, true, false, true>;
+    e.mut[1][1][1] = k_mutate<LIK, true, true, true>;
+    e.eval = k_evaluate<LIK>;
+    e.draw = nullptr;
+    e.upload_model = tu_upload_model;
+    e.upload_proposal = tu_upload_proposal;
+    return e;
+}
+#define LINREG(K) make_entry<GaussReg<1, K, K, 0, -1>>()
+
+}  // namespace
+}  // namespace smc

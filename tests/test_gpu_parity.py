@@ -498,3 +498,83 @@ def test_full_size_properties(eng):
     idx2 = eng.resample("systematic", seed=5, stage=100, u=0.5, want_indices=True)   # uniform weights: identity
     assert np.array_equal(idx2, np.arange(1, N + 1))
     assert np.array_equal(eng.download(), before)
+
+
+# ---- config C4: An-Schorfheide DSGE likelihood (device decision rule + Kalman filter) -------------------
+def _as_spec(g, with_old=False):
+    data = g["data"]
+    ps = W.an_schorfheide_parameters()
+    if with_old:
+        return M.make_spec(ps, M.AnSchorfheideLogLik(data), M.AnSchorfheideLogLik(data[:, :115]))
+    return M.make_spec(ps, M.AnSchorfheideLogLik(data))
+
+
+def test_as_evaluate_golden_and_oracle(eng, golden):
+    """The reference-produced (theta -> loglh, logprior) rows of the saved An-Schorfheide clouds through the CUDA
+    likelihood: relative 2e-11 against the reference's numbers, bit-exact against the oracle."""
+    g = golden("as_clouds.npz")
+    for name, T in (("cloud600", 230), ("cloud1000", 115), ("prior_draws", 230)):
+        P = np.asfortranarray(g[name])
+        N = P.shape[0]
+        ps = W.an_schorfheide_parameters()
+        spec = M.make_spec(ps, M.AnSchorfheideLogLik(g["data"][:, :T]))
+        eng.cloud_create(N, 16)
+        eng.set_model(spec)
+        eng.upload(W_reset(P))
+        eng.evaluate(0)
+        got = eng.download()
+        rel = np.abs(got[:, 16] - P[:, 16]) / np.maximum(1.0, np.abs(P[:, 16]))
+        assert np.median(rel) < 1e-14
+        assert np.sort(rel)[-2] < 2e-11 and rel.max() < 1e-6     # one near-unit-root prior draw (SURVEY 4)
+        np.testing.assert_allclose(got[:, 17], P[:, 17], rtol=1e-13, atol=2e-13)
+        buf = O.cloud_f(W_reset(P))
+        mod = O.Model(spec)
+        O.lib().orc_evaluate(mod.h, buf, N)
+        assert np.array_equal(got, O.cloud_m(buf, N, 16))
+
+
+def test_as_initialize_likelihoods_golden(eng, golden):
+    """Online update: initialize_likelihoods! moves loglh (first vintage, 115 periods) to old_loglh and
+    re-evaluates on the full sample; the saved cloud of the reference's second-vintage run holds both columns."""
+    g = golden("as_clouds.npz")
+    P = np.asfortranarray(g["cloud600"])
+    N = P.shape[0]
+    eng.cloud_create(N, 16)
+    eng.set_model(M.make_spec(W.an_schorfheide_parameters(), M.AnSchorfheideLogLik(g["data"][:, :115])))
+    eng.upload(W_reset(P))
+    eng.evaluate(0)
+    first = eng.download()
+    np.testing.assert_allclose(first[:, 16], P[:, 18], rtol=2e-11)           # loglh on the old data == stored old_loglh
+    eng.set_model(_as_spec(g))
+    eng.evaluate(1)
+    got = eng.download()
+    assert np.array_equal(got[:, 18], first[:, 16])
+    np.testing.assert_allclose(got[:, 16], P[:, 16], rtol=2e-11)
+
+
+@pytest.mark.parametrize("blocks,alpha,n_mh", [(1, 1.0, 2), (3, 0.9, 1)])
+def test_as_mutation_bitexact(eng, golden, blocks, alpha, n_mh):
+    g = golden("as_clouds.npz")
+    spec = _as_spec(g, with_old=True)
+    P = np.asfortranarray(g["cloud600"]).copy(order="F")
+    P[:, -1] = 1.0
+    rng = np.random.default_rng(blocks)
+    perm = rng.permutation(13)
+    blk = [np.sort(b) for b in np.array_split(perm, blocks)]
+    got, want, acc, oacc = _mutation_case(eng, spec, P, blk, 0.6, 0.5, 0.3, n_mh, True, 99, 7, alpha=alpha)
+    assert np.array_equal(got, want)
+    assert acc == oacc and acc > 0.0
+    assert np.array_equal(got[:, 13:16], P[:, 13:16])                       # fixed measurement errors never move
+
+
+def test_as_stage_trajectory_bitexact(eng, golden):
+    """C4-shaped run (13 free parameters, n_mh_steps = 5) from the reference's own prior draws: identical
+    trajectories and clouds, GPU vs oracle."""
+    g = golden("as_clouds.npz")
+    spec = _as_spec(g)
+    P0 = np.asfortranarray(g["prior_draws"]).copy(order="F")
+    P0[:, 18:20] = 0.0
+    P0[:, 20] = 1.0
+    sched = (np.arange(12) / 11.0) ** 3.0
+    n_res, phi = _run_stages(eng, spec, P0, sched, 6, dict(n_mh_steps=5, n_blocks=1))
+    assert n_res >= 1
