@@ -6,7 +6,7 @@
  * TEST INFRASTRUCTURE ONLY (see smc_oracle.c header).  The model itself lives in DSGE.jl /
  * StateSpaceRoutines.jl, which are NOT in /root/reference (unvendored, unpinned dependency); its results
  * are pinned by the (theta -> loglh / old_loglh) columns of the clouds the reference stores under
- * test/reference/solve_adaptive_phi.jld2 and test/save/output_data/an_schorfheide/ss0/estimate/raw/*.jld2
+ * test/reference/solve_adaptive_phi.jld2 and test/save/output_data/an_schorfheide/ss0/estimate/raw/ (the .jld2 clouds)
  * (2 000 rows, extracted to tests/golden/as_clouds.npz; tests/test_oracle_golden.py checks this file
  * against them).  Equations: SURVEY.md Appendix A.
  *

@@ -1059,6 +1059,89 @@ ORC_API void orc_evaluate(const orc_model *m, double *cloud, i64 N)
     }
 }
 
+/* initial_draw! / one_draw (src/initialization.jl:23-119): every free parameter from its prior (redrawn
+ * until strictly inside its valuebounds, ModelConstructors `rand(parameters, 1)`), fixed parameters keep
+ * their value; the whole vector is redrawn while the log-likelihood is not finite (:43-60).  The
+ * reference's dSFMT stream is not reproducible: randomness is a per-particle sequential Philox stream,
+ * counter = (global particle, 0, call number, PURP_INIT), one block per uniform / normal.
+ * Gamma(shape, 1): Marsaglia & Tsang (2000), shape < 1 through shape + 1 and U^(1/shape). */
+typedef struct { uint64_t seed; uint32_t gp, ctr; } draw_rng;
+static double dr_uniform(draw_rng *r) { uint32_t x[4]; rng4(r->seed, r->gp, 0u, r->ctr++, PURP_INIT, x); return u01(x[0], x[1]); }
+static double dr_uniform_open0(draw_rng *r) { uint32_t x[4]; rng4(r->seed, r->gp, 0u, r->ctr++, PURP_INIT, x); return u01_open0(x[0], x[1]); }
+static double dr_normal(draw_rng *r) { uint32_t x[4]; double z0, z1; rng4(r->seed, r->gp, 0u, r->ctr++, PURP_INIT, x); normal_pair(x, &z0, &z1); return z0; }
+static double dr_gamma(draw_rng *r, double shape)
+{
+    int boost = shape < 1.0;
+    double a = boost ? shape + 1.0 : shape;
+    double d = a - 1.0 / 3.0;
+    double c = 1.0 / sqrt(9.0 * d);
+    double g = NAN;
+    for (int it = 0; it < 256; ++it) {
+        double x = dr_normal(r);
+        double t = 1.0 + c * x;
+        if (!(t > 0.0)) continue;
+        double v = (t * t) * t;
+        double u = dr_uniform_open0(r);
+        if (orc_log(u) < ((0.5 * x) * x + d) - d * v + d * orc_log(v)) { g = d * v; break; }
+    }
+    if (boost) {
+        double u = dr_uniform_open0(r);
+        g = g * orc_exp(orc_log(u) / shape);
+    }
+    return g;
+}
+static double dr_prior(const orc_model *m, draw_rng *r, int k)
+{
+    double p1 = m->p1[k], p2 = m->p2[k];
+    switch (m->kind[k]) {
+    case PRIOR_NORMAL: return p1 + p2 * dr_normal(r);
+    case PRIOR_UNIFORM: return p1 + (p2 - p1) * dr_uniform(r);
+    case PRIOR_GAMMA: return p2 * dr_gamma(r, p1);
+    case PRIOR_ROOT_INV_GAMMA: return sqrt(m->a2[k] / dr_gamma(r, 0.5 * p1));
+    case PRIOR_BETA: { double x = dr_gamma(r, p1); double y = dr_gamma(r, p2); return x / (x + y); }
+    case PRIOR_INV_GAMMA: return p2 / dr_gamma(r, p1);
+    }
+    return NAN;
+}
+/* returns the number of particles that found no finite log-likelihood within max_tries */
+ORC_API int orc_initial_draw(const orc_model *m, double *cloud, i64 N, i64 index0, const double *fixed_values,
+                             uint64_t seed, int max_tries)
+{
+    int d = m->d, failed = 0;
+    for (i64 i = 0; i < N; ++i) {
+        draw_rng r = {seed, (uint32_t)(index0 + i), 0u};
+        double th[MAX_D], ll = -INFINITY, lp = -INFINITY;
+        int success = 0;
+        for (int attempt = 0; attempt < max_tries && !success; ++attempt) {
+            for (int k = 0; k < d; ++k) {
+                double x;
+                if (m->fixed[k]) x = fixed_values[k];
+                else {
+                    x = NAN;
+                    for (int it = 0; it < 1000; ++it) {
+                        x = dr_prior(m, &r, k);
+                        if (x > m->lo[k] && x < m->hi[k]) break;
+                        x = NAN;
+                    }
+                }
+                th[k] = x;
+            }
+            ll = orc_loglik(m, 0, th);
+            lp = orc_logprior(m, th);
+            if (!(ll - ll == 0.0)) { ll = -INFINITY; lp = -INFINITY; }
+            else success = 1;
+        }
+        if (!success) ++failed;
+        for (int k = 0; k < d; ++k) COL(cloud, N, k)[i] = th[k];
+        COL(cloud, N, C_LOGLH(d))[i] = ll;
+        COL(cloud, N, C_LOGPRIOR(d))[i] = lp;
+        COL(cloud, N, C_OLDLOGLH(d))[i] = 0.0;
+        COL(cloud, N, C_ACCEPT(d))[i] = 0.0;
+        COL(cloud, N, C_WEIGHT(d))[i] = 1.0;
+    }
+    return failed;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* One full stage (src/smc_main.jl:377-497), fixed or adaptive schedule                        */
 /* ------------------------------------------------------------------------------------------ */

@@ -77,7 +77,7 @@ struct KernelEntry {            // one likelihood functor's kernels + the consta
     int kind, neq, k, stride, coef, sig, d;
     void (*mut[2][2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single block][mixture]
     void (*eval)(double*, int64_t, int);
-    void (*draw)(double*, int64_t, int64_t, const double*, uint64_t, int, int*);
+    void (*draw)(double*, int64_t, int64_t, const double*, uint64_t, int, int*);   // initial_draw!
     int (*upload_model)(Ctx*);
     int (*upload_proposal)(Ctx*, bool);
 };
@@ -168,5 +168,6 @@ int mutate_upload_proposal(Ctx* ctx, bool from_device); // MutConst -> __constan
 bool mutate_supported(const Ctx* ctx, bool has_old);
 int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage);
 int evaluate_launch(Ctx* ctx, int mode);
+int initial_draw_launch(Ctx* ctx, const double* fixed_values_dev, uint64_t seed, int max_tries, int* n_failed_dev);
 
 }  // namespace smc

@@ -718,8 +718,33 @@ int32_t smcb200_evaluate(smcb200_ctx* c, int32_t mode)
 
 int32_t smcb200_initial_draw(smcb200_ctx* c, const double* fixed_values, uint64_t seed, int32_t max_tries)
 {
-    (void)fixed_values; (void)seed; (void)max_tries;
-    return fail(c, SMCB200_ERR_UNSUPPORTED, "initial_draw! on the device is not available in this build");
+    int st = check_ready(c, true); if (st) return st;
+    if (max_tries < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "max_tries must be >= 1");
+    cudaSetDevice(c->device);
+    // scratch: [DMAX] fixed values followed by the failure counter (reuses the device status word's neighbour-free tmp column)
+    double* fv_dev = c->tmp;                                 // N >= 1 doubles; DMAX doubles are needed
+    double* fv_alloc = nullptr;
+    if (c->N < DMAX + 1) { SMC_CUDA(c, cudaMalloc(&fv_alloc, sizeof(double) * (DMAX + 1))); fv_dev = fv_alloc; }
+    double fv[DMAX] = {0};
+    for (int k = 0; k < c->d; ++k) {
+        if (c->prior.fixed[k]) {
+            if (!fixed_values) { cudaFree(fv_alloc); return fail(c, SMCB200_ERR_BAD_ARGUMENT, "fixed parameters need fixed_values"); }
+            fv[k] = fixed_values[k];
+        }
+    }
+    SMC_CUDA(c, cudaMemcpyAsync(fv_dev, fv, sizeof(double) * DMAX, cudaMemcpyHostToDevice, c->stream));
+    SMC_CUDA(c, cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream));
+    st = initial_draw_launch(c, fv_dev, seed, max_tries, c->status_dev);
+    if (st) { cudaFree(fv_alloc); return st; }
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_status, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c);
+    const int n_failed = *c->h_status;
+    cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(fv_alloc);
+    if (st) return st;
+    if (n_failed) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "initial_draw!: some particles found no finite log-likelihood within max_tries prior draws");
+    return SMCB200_OK;
 }
 
 // ---- stage operations -----------------------------------------------------------------------------------

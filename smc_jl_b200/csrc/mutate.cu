@@ -114,4 +114,18 @@ int evaluate_launch(Ctx* ctx, int mode)
     return SMCB200_OK;
 }
 
+int initial_draw_launch(Ctx* ctx, const double* fixed_values_dev, uint64_t seed, int max_tries, int* n_failed_dev)
+{
+    const KernelEntry* e = find_entry(ctx);
+    if (!e) {
+        ctx->err = "no device likelihood functor for this likelihood / n_para";
+        return SMCB200_ERR_UNSUPPORTED;
+    }
+    const unsigned grid = (unsigned)((ctx->N + 127) / 128);
+    e->draw<<<grid, 128, 0, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, fixed_values_dev, seed, max_tries, n_failed_dev);
+    ctx->launches++;
+    SMC_CUDA(ctx, cudaGetLastError());
+    return SMCB200_OK;
+}
+
 }  // namespace smc

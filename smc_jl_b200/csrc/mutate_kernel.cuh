@@ -314,6 +314,100 @@ __global__ void __launch_bounds__(128) k_evaluate(double* __restrict__ cloud, in
     cloud[col_off(N, D + 1) + i] = logprior<D>(th);
 }
 
+// ---- stage 0: initial_draw! / one_draw (src/initialization.jl:23-119) --------------------------------------
+// Every free parameter is drawn from its prior (ModelConstructors `rand(parameters, 1)`: redrawn until strictly
+// inside its valuebounds), fixed parameters take their value; the whole vector is redrawn while the
+// log-likelihood is not finite (:43-60).  Randomness: a per-particle sequential Philox stream
+// (counter = (global particle, 0, call number, PURP_INIT)); one block per uniform / normal (stage 0 only).
+struct DrawRng {
+    uint64_t seed;
+    uint32_t gp, ctr;
+    __device__ __forceinline__ u32x4 next() { return rng4(seed, gp, 0u, ctr++, PURP_INIT); }
+    __device__ __forceinline__ double uniform() { const u32x4 r = next(); return u01(r.x, r.y); }
+    __device__ __forceinline__ double uniform_open0() { const u32x4 r = next(); return u01_open0(r.x, r.y); }
+    __device__ __forceinline__ double normal() { double z0, z1; normal_pair(next(), z0, z1); return z0; }
+};
+
+// Gamma(shape, 1): Marsaglia & Tsang (2000); shape < 1 through shape + 1 and U^(1/shape).  NaN after 256 rejections.
+__device__ __noinline__ double draw_gamma(DrawRng& r, double shape)
+{
+    const bool boost = shape < 1.0;
+    const double a = boost ? shape + 1.0 : shape;
+    const double d = a - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    double g = dnan();
+    for (int it = 0; it < 256; ++it) {
+        const double x = r.normal();
+        const double t = 1.0 + c * x;
+        if (!(t > 0.0)) continue;
+        const double v = (t * t) * t;
+        const double u = r.uniform_open0();
+        if (det_log(u) < ((0.5 * x) * x + d) - d * v + d * det_log(v)) { g = d * v; break; }
+    }
+    if (boost) {
+        const double u = r.uniform_open0();
+        g = g * det_exp(det_log(u) / shape);
+    }
+    return g;
+}
+
+__device__ __noinline__ double draw_prior(DrawRng& r, int k)
+{
+    const double p1 = c_pri.p1[k], p2 = c_pri.p2[k];
+    switch (c_pri.kind[k]) {
+    case SMCB200_PRIOR_NORMAL: return p1 + p2 * r.normal();
+    case SMCB200_PRIOR_UNIFORM: return p1 + (p2 - p1) * r.uniform();
+    case SMCB200_PRIOR_GAMMA: return p2 * draw_gamma(r, p1);
+    case SMCB200_PRIOR_ROOT_INV_GAMMA: return sqrt(c_pri.a2[k] / draw_gamma(r, 0.5 * p1));   // x^2 ~ InvGamma(nu/2, nu tau^2/2)
+    case SMCB200_PRIOR_BETA: { const double x = draw_gamma(r, p1), y = draw_gamma(r, p2); return x / (x + y); }
+    case SMCB200_PRIOR_INV_GAMMA: return p2 / draw_gamma(r, p1);
+    }
+    return dnan();
+}
+
+template <class LIK>
+__global__ void __launch_bounds__(128) k_initial_draw(double* __restrict__ cloud, int64_t N, int64_t index0, const double* __restrict__ fixed_values,
+                                                      uint64_t seed, int max_tries, int* __restrict__ n_failed)
+{
+    constexpr int D = LIK::D;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= N) return;
+    DrawRng r;
+    r.seed = seed; r.gp = (uint32_t)(index0 + i); r.ctr = 0u;
+    double th[D];
+    double ll = -dinf(), lp = -dinf();
+    bool success = false;
+    for (int attempt = 0; attempt < max_tries && !success; ++attempt) {
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            double x;
+            if (c_pri.fixed[k]) {
+                x = fixed_values[k];
+            } else {
+                x = dnan();
+                for (int it = 0; it < 1000; ++it) {
+                    x = draw_prior(r, k);
+                    if (x > c_pri.lo[k] && x < c_pri.hi[k]) break;
+                    x = dnan();
+                }
+            }
+            th[k] = x;
+        }
+        ll = LIK::template ll<0>(th);
+        lp = logprior<D>(th);
+        if (!(ll - ll == 0.0)) { ll = -dinf(); lp = -dinf(); }     // -Inf, +Inf or NaN: redraw (:39-41,56-60)
+        else success = true;
+    }
+    if (!success) atomicAdd(n_failed, 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = th[k];
+    cloud[col_off(N, D) + i] = ll;
+    cloud[col_off(N, D + 1) + i] = lp;
+    cloud[col_off(N, D + 2) + i] = 0.0;        // update_old_loglh!(c, zeros)
+    cloud[col_off(N, D + 3) + i] = 0.0;
+    cloud[col_off(N, D + 4) + i] = 1.0;        // set_weights!(c, ones)
+}
+
 // ---- per-translation-unit registration ---------------------------------------------------------------
 static int tu_upload_model(Ctx* ctx)
 {
@@ -348,7 +442,7 @@ static KernelEntry make_entry()
     e.mut[1][0][1] = k_mutate<LIK, true, false, true>;
     e.mut[1][1][1] = k_mutate<LIK, true, true, true>;
     e.eval = k_evaluate<LIK>;
-    e.draw = nullptr;
+    e.draw = k_initial_draw<LIK>;
     e.upload_model = tu_upload_model;
     e.upload_proposal = tu_upload_proposal;
     return e;

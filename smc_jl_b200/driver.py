@@ -20,7 +20,6 @@ from ._lib import StageConfig, StageState
 from .cloud import Cloud, cloud_isempty
 from .engine import RESAMPLERS, Engine
 from .model import make_spec
-from .workloads import prior_draw
 
 
 def _println(verbose, level, msg):
@@ -29,26 +28,10 @@ def _println(verbose, level, msg):
         print(msg)
 
 
-def initial_draw(engine, parameters, spec, n_parts, rng, max_rounds=50):
-    """initial_draw! (src/initialization.jl:88-119): prior draws (host RNG), loglh / logprior evaluated
-    on the device, redraw while the log-likelihood is -Inf / NaN (one_draw, :43-60)."""
-    d = spec.d
-    P = np.zeros((n_parts, d + 5), order="F")
-    P[:, :d] = prior_draw(parameters, n_parts, rng)
-    P[:, d + 4] = 1.0
-    engine.upload(P)
-    engine.evaluate(0)
-    for _ in range(max_rounds):
-        ll = engine.read_column(d)
-        bad = ~np.isfinite(ll)
-        if not bad.any():
-            break
-        P = engine.download()
-        P[bad, :d] = prior_draw(parameters, int(bad.sum()), rng)
-        engine.upload(P)
-        engine.evaluate(0)
-    else:
-        raise RuntimeError("initial_draw!: could not find finite log-likelihood draws")
+def initial_draw(engine, spec, seed, max_tries=1000):
+    """initial_draw! (src/initialization.jl:88-119) on the device: every particle draws its free parameters from
+    the prior (inside valuebounds) until the log-likelihood is finite (one_draw, :43-60); old_loglh = 0, weight = 1."""
+    engine.initial_draw(spec.values, seed, max_tries)
 
 
 def smc(loglikelihood, parameters, data=None, *, verbose="low", testing=False, data_vintage="", parallel=False,
@@ -83,7 +66,6 @@ def smc(loglikelihood, parameters, data=None, *, verbose="low", testing=False, d
     try:
         eng.cloud_create(n_parts, n_para)
         eng.set_model(spec)
-        rng = np.random.Generator(np.random.Philox(seed))
         _println(verbose, "low", "\n\n SMC " + ("testing " if testing else "") + "starts ....\n\n")
 
         # ---- initialisation (smc_main.jl:244-345) --------------------------------------------------------
@@ -100,7 +82,7 @@ def smc(loglikelihood, parameters, data=None, *, verbose="low", testing=False, d
             W_hist = [w0 * n_parts if w0.sum() <= 1.0 else w0.copy()]
         else:
             cloud = Cloud.empty(n_para, n_parts)
-            initial_draw(eng, parameters, spec, n_parts, rng)
+            initial_draw(eng, spec, seed)
             ess0 = float(n_parts)
             W_hist = [np.ones(n_parts)]
         w_hist = [np.zeros(n_parts)]

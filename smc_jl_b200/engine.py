@@ -140,6 +140,11 @@ class Engine:
             ip, dp = lk.iparams(), _f64(lk.eqdata)
             self._ck(lib.smcb200_set_likelihood(self.h, slot, lk.kind, ptr(ip), len(ip), ptr(dp), dp.size))
 
+    def initial_draw(self, fixed_values, seed, max_tries=1000):
+        """initial_draw! (src/initialization.jl:88-119) on the device."""
+        fv = _f64(fixed_values)
+        self._ck(lib.smcb200_initial_draw(self.h, ptr(fv), int(seed), int(max_tries)))
+
     def evaluate(self, mode=0):
         self._ck(lib.smcb200_evaluate(self.h, mode))
 

@@ -80,6 +80,7 @@ def lib():
         "orc_max_threads": (C.c_int, []),
         "orc_initialize_likelihoods": (None, [vp, f64p, i64]),
         "orc_evaluate": (None, [vp, f64p, i64]),
+        "orc_initial_draw": (C.c_int, [vp, f64p, i64, i64, f64p, u64, C.c_int]),
         "orc_stage": (C.c_int, [vp, f64p, f64p, i64, f64p, C.c_int, C.POINTER(StageIO), vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

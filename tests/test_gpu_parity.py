@@ -578,3 +578,53 @@ def test_as_stage_trajectory_bitexact(eng, golden):
     sched = (np.arange(12) / 11.0) ** 3.0
     n_res, phi = _run_stages(eng, spec, P0, sched, 6, dict(n_mh_steps=5, n_blocks=1))
     assert n_res >= 1
+
+
+# ---- stage 0 on the device: initial_draw! (src/initialization.jl:88-119) ---------------------------------
+def _initial_draw_case(eng, spec, N, seed, max_tries=50):
+    eng.cloud_create(N, spec.d)
+    eng.set_model(spec)
+    eng.initial_draw(spec.values, seed, max_tries)
+    got = eng.download()
+    buf = np.zeros(N * (spec.d + 5))
+    mod = O.Model(spec)
+    assert O.lib().orc_initial_draw(mod.h, buf, N, 0, np.ascontiguousarray(spec.values), seed, max_tries) == 0
+    return got, O.cloud_m(buf, N, spec.d)
+
+
+def test_initial_draw_bitexact_linear_and_three_equation(eng):
+    params, lk, _ = W.linear_gaussian(d=20, T=256)
+    got, want = _initial_draw_case(eng, M.make_spec(params, lk), 5000, 1793)
+    assert np.array_equal(got, want)
+    assert np.all(got[:, -1] == 1.0) and np.all(got[:, 22] == 0.0) and np.all(np.isfinite(got[:, 20]))
+    assert abs(got[:, :20].std() - 10.0) < 0.2                                  # N(0, 10) priors
+    data, X = W.synthetic_three_equation(T=100)
+    spec = M.make_spec(W.three_equation_parameters(), M.LinearEquationsLogLik(data, X))
+    got, want = _initial_draw_case(eng, spec, 4000, 5)
+    assert np.array_equal(got, want)
+    assert np.all((got[:, [2, 5, 8]] > 1e-5) & (got[:, [2, 5, 8]] < 1e3))       # sigma ~ U(0, 1e3) inside valuebounds
+
+
+def test_initial_draw_bitexact_an_schorfheide(eng, golden):
+    """Gamma / RootInverseGamma / Uniform / Normal prior samplers, fixed parameters, and the redraw of draws without a
+    unique stable solution (loglh = -Inf, initialization.jl:56-60)."""
+    g = golden("as_clouds.npz")
+    spec = _as_spec(g)
+    got, want = _initial_draw_case(eng, spec, 3000, 42)
+    assert np.array_equal(got, want)
+    assert np.all(np.isfinite(got[:, 16])) and np.all(got[:, 13:16] == spec.values[13:16])
+    # the prior puts ~2 % of its mass on psi_1 < 1 (indeterminacy): those draws were replaced
+    assert got[:, 2].min() > 0.9
+    assert abs(got[:, 0].mean() - 2.0) < 0.05 and abs(got[:, 2].mean() - 1.5) < 0.03
+
+
+def test_initial_draw_failure_is_reported(eng):
+    """A likelihood that is never finite (sigma fixed at a non-positive value) exhausts max_tries."""
+    data, X = W.synthetic_three_equation(T=20)
+    ps = W.three_equation_parameters()
+    ps[2] = M.parameter("σ1", -1.0, (-1.0, -1.0), (-1.0, -1.0), None, None, fixed=True)
+    spec = M.make_spec(ps, M.LinearEquationsLogLik(data, X))
+    eng.cloud_create(256, 9)
+    eng.set_model(spec)
+    with pytest.raises(ValueError):
+        eng.initial_draw(spec.values, 1, 3)

@@ -130,3 +130,45 @@ def test_oracle_stage_loop_recovers_posterior():
     mean = np.average(got[:, :2], axis=0, weights=got[:, -1])
     assert np.allclose(mean, [1.0, 1.0], atol=0.1)
     assert 0.05 < io.accept < 0.8
+
+
+def test_oracle_initial_draw_distributions():
+    """initial_draw! (src/initialization.jl:88-119) in the oracle: every prior family's sampler has the right first two
+    moments, draws respect valuebounds, fixed parameters keep their value, weights = 1 and old_loglh = 0."""
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((40, 7)); y = X @ np.full(7, 0.1) + rng.standard_normal(40)
+    pri = [M.Normal(1.0, 2.0), M.Uniform(-1.0, 3.0), M.Gamma(2.5, 0.4), M.Gamma(0.6, 2.0), M.RootInverseGamma(6.0, 0.5),
+           M.Beta(2.0, 5.0), M.InverseGamma(5.0, 2.0)]
+    ps = [M.parameter("p%d" % k, 0.5, (-1e5, 1e5), (-1e5, 1e5), None, pr) for k, pr in enumerate(pri)]
+    ps[1] = M.parameter("p1", 0.5, (0.0, 3.0), (0.0, 3.0), None, pri[1])       # truncates Uniform(-1, 3) to (0, 3)
+    ps.append(M.parameter("fx", 0.25, (0.25, 0.25), (0.25, 0.25), None, None, fixed=True))
+    X8 = np.column_stack([X, np.ones(40)])
+    spec = M.make_spec(ps, M.LinearGaussianLogLik(y, X8, 1.0))
+    N = 200_000
+    buf = np.zeros(N * 13)
+    mod = O.Model(spec)
+    assert O.lib().orc_initial_draw(mod.h, buf, N, 0, np.ascontiguousarray(spec.values), 11, 10) == 0
+    P = O.cloud_m(buf, N, 8)
+    assert np.all(P[:, 7] == 0.25) and np.all(P[:, 12] == 1.0) and np.all(P[:, 10] == 0.0)
+    assert np.all(np.isfinite(P[:, 8])) and np.all(np.isfinite(P[:, 9]))
+    assert P[:, 1].min() > 0.0 and P[:, 1].max() < 3.0
+    se = 5.0 / np.sqrt(N)
+    def chk(col, mean, var):
+        assert abs(P[:, col].mean() - mean) < se * np.sqrt(var) + 1e-12, (col, P[:, col].mean(), mean)
+        assert abs(P[:, col].var() - var) < 0.05 * var, (col, P[:, col].var(), var)
+    chk(0, 1.0, 4.0)
+    chk(1, 1.5, 9.0 / 12.0)
+    chk(2, 2.5 * 0.4, 2.5 * 0.16)
+    chk(3, 0.6 * 2.0, 0.6 * 4.0)
+    x2 = P[:, 4] ** 2                                    # x^2 ~ InverseGamma(nu/2 = 3, nu tau^2/2 = 0.75)
+    assert abs(x2.mean() - 0.75 / 2.0) < 5 * np.sqrt((0.75 ** 2 / (4.0 * 1.0)) / N)
+    chk(5, 2.0 / 7.0, 2.0 * 5.0 / (49.0 * 8.0))
+    chk(6, 2.0 / 4.0, 4.0 / (16.0 * 3.0))
+    # the row's loglh / logprior are the model's
+    for r in (0, 17, N - 1):
+        th = np.ascontiguousarray(P[r, :8])
+        assert P[r, 8] == mod.loglik(th) and P[r, 9] == mod.logprior(th)
+    # shard invariance: particles 1000.. drawn as their own shard are identical
+    buf2 = np.zeros(500 * 13)
+    O.lib().orc_initial_draw(mod.h, buf2, 500, 1000, np.ascontiguousarray(spec.values), 11, 10)
+    assert np.array_equal(O.cloud_m(buf2, 500, 8), P[1000:1500])
