@@ -207,7 +207,8 @@ int32_t smcb200_last_kernel_ms(const smcb200_ctx *ctx, int32_t which, float *ms_
 int32_t smcb200_timer_start(smcb200_ctx *ctx);
 int32_t smcb200_timer_stop(smcb200_ctx *ctx, float *ms_out);
 /* device-side deterministic elementary functions, for parity tests: op 0 exp, 1 log, 2 sin(2 pi x),
- * 3 cos(2 pi x), 4/5 = z0/z1 of normal_pair(seed, particle = i, stage = 0, slot = x[i]) */
+ * 3 cos(2 pi x), 4/5 = z0/z1 of normal_pair(seed, particle = i, stage = 0, slot = x[i]) (binary64 Box-Muller,
+ * prior draws), 6..9 = the four proposal normals of normal_quad (binary32 Box-Muller) of the same Philox block */
 int32_t smcb200_debug_math(smcb200_ctx *ctx, int32_t op, const double *x, int64_t n, uint64_t seed, double *out);
 
 #if defined(__GNUC__)

@@ -202,6 +202,51 @@ static inline void normal_pair(const uint32_t r[4], double *z0, double *z1)
     *z0 = rad * cs;
     *z1 = rad * sn;
 }
+/* Proposal normals: four N(0,1) variates from one Philox block, Box-Muller in binary32 (32-bit uniforms,
+ * degree-7 division-free log, 3-term sin/cos kernels on [0, pi/4] after an exact octant split).  IEEE
+ * binary32 +,*,fma,sqrt only => the device produces the same bits (DESIGN.md "Numerical contract"). */
+static inline void normal_pair_f32(uint32_t a, uint32_t b, double *z0, double *z1)
+{
+    float u = __builtin_fmaf((float)a, 0x1p-32f, 0x1p-33f);
+    uint32_t ix; memcpy(&ix, &u, 4);
+    ix += 0x3f800000u - 0x3f3504f3u;
+    int k = (int)(ix >> 23) - 127;
+    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+    float m; memcpy(&m, &ix, 4);
+    float f = m - 1.0f;
+    static const float LQ[8] = {0.9999999403953552f, -0.500003457069397f, 0.3333560824394226f, -0.24971559643745422f,
+                                0.19884242117404938f, -0.1721244603395462f, 0.1633809357881546f, -0.10378583520650864f};
+    float q = LQ[7];
+    for (int i = 6; i >= 0; --i) q = __builtin_fmaf(q, f, LQ[i]);
+    float lnu = __builtin_fmaf((float)k, 0.6931471805599453f, f * q);
+    float t = -2.0f * lnu;
+    float rad = sqrtf(t > 0.0f ? t : 0.0f);
+    uint32_t o = b >> 29;
+    float g = (float)(b & 0x1fffffffu) * 0x1p-29f;
+    if (o & 1u) g = 1.0f - g;
+    float x = g * 0.7853981633974483f;
+    float z = x * x;
+    float s = __builtin_fmaf(x * z, __builtin_fmaf(z, __builtin_fmaf(z, -0.0001958801003638655f, 0.008332748897373676f), -0.166666641831398f), x);
+    float c = __builtin_fmaf(z * z, __builtin_fmaf(z, __builtin_fmaf(z, 2.4581931938882917e-05f, -0.0013888553949072957f), 0.0416666679084301f),
+                             __builtin_fmaf(-0.5f, z, 1.0f));
+    float sp = (o & 1u) ? c : s, cp = (o & 1u) ? s : c;
+    uint32_t qd = o >> 1;
+    float sn = (qd == 0u) ? sp : (qd == 1u) ? cp : (qd == 2u) ? -sp : -cp;
+    float cs = (qd == 0u) ? cp : (qd == 1u) ? -sp : (qd == 2u) ? -cp : sp;
+    *z0 = (double)(rad * cs);
+    *z1 = (double)(rad * sn);
+}
+static inline void normal_quad(const uint32_t r[4], double z[4])
+{
+    normal_pair_f32(r[0], r[1], &z[0], &z[1]);
+    normal_pair_f32(r[2], r[3], &z[2], &z[3]);
+}
+ORC_API void orc_normal_quad(uint64_t seed, uint32_t particle, uint32_t stage, uint32_t slot, double *out)
+{
+    uint32_t r[4];
+    rng4(seed, particle, stage, slot, PURP_NORMAL, r);
+    normal_quad(r, out);
+}
 ORC_API void orc_normal_pair(uint64_t seed, uint32_t particle, uint32_t stage, uint32_t slot, double *out)
 {
     uint32_t r[4];
@@ -613,6 +658,7 @@ typedef struct {
     int d;
     int fixed[MAX_D], kind[MAX_D];
     double lo[MAX_D], hi[MAX_D], p1[MAX_D], p2[MAX_D], cst[MAX_D], a1[MAX_D], a2[MAX_D];
+    int all_normal; double cst_sum;   /* every parameter free with a Normal prior: fused log-prior (see orc_logprior) */
     int lik_kind[2];
     gaussreg gr[2];
     struct { int T, npre; double *data; } as[2];   /* An-Schorfheide DSGE likelihood (as_model.c) */
@@ -660,6 +706,11 @@ ORC_API int orc_model_set_params(orc_model *m, const i32 *fixed, const double *l
         default: return 3;
         }
     }
+    m->all_normal = 1; m->cst_sum = 0.0;
+    for (int k = 0; k < m->d; ++k) {
+        if (m->fixed[k] || m->kind[k] != PRIOR_NORMAL) m->all_normal = 0;
+        m->cst_sum = m->cst_sum + (m->fixed[k] ? 0.0 : m->cst[k]);
+    }
     return 0;
 }
 
@@ -687,6 +738,11 @@ static inline double logpdf1(const orc_model *m, int k, double x)
 /* sum over FREE parameters in index order */
 ORC_API double orc_logprior(const orc_model *m, const double *theta)
 {
+    if (m->all_normal) {   /* same sum with the squares accumulated first: -0.5 sum_k z_k^2 + sum_k cst_k */
+        double acc = 0.0;
+        for (int k = 0; k < m->d; ++k) { double z = (theta[k] - m->p1[k]) * m->a1[k]; acc = FMA(z, z, acc); }
+        return FMA(-0.5, acc, m->cst_sum);
+    }
     double lp = 0.0;
     for (int k = 0; k < m->d; ++k) if (!m->fixed[k]) lp = lp + logpdf1(m, k, theta[k]);
     return lp;
@@ -951,14 +1007,15 @@ static void mutate_one(const orc_model *m, const orc_proposal *pr, const mut_cfg
             rng4(cfg->seed, gp, cfg->stage, sb, PURP_STEP, r4);
             double step_prob = u01(r4[0], r4[1]);
             double u_mix = u01(r4[2], r4[3]);
-            /* normals are indexed by PARAMETER index: pair p = index >> 1 */
+            /* normals are indexed by PARAMETER index: Philox block (sb << 8) | (index >> 2) gives the four
+             * proposal normals of parameters 4q .. 4q+3 */
             for (int q = 0; q < n; ++q) {
                 int k = mem[q];
-                double zz[2];
+                double zz[4];
                 uint32_t rr[4];
-                rng4(cfg->seed, gp, cfg->stage, (sb << 8) | (uint32_t)(k >> 1), PURP_NORMAL, rr);
-                normal_pair(rr, &zz[0], &zz[1]);
-                z[q] = zz[k & 1];
+                rng4(cfg->seed, gp, cfg->stage, (sb << 8) | (uint32_t)(k >> 2), PURP_NORMAL, rr);
+                normal_quad(rr, zz);
+                z[q] = zz[k & 3];
             }
             for (int q = 0; q < n; ++q) sub[q] = para[mem[q]];
             /* mvnormal_mixture_draw (helpers.jl:87-100) */

@@ -38,6 +38,8 @@ struct PhiState {           // adaptive-phi state machine, lives in device memor
 struct PriorConst {
     double lo[DMAX], hi[DMAX], p1[DMAX], p2[DMAX], cst[DMAX], a1[DMAX], a2[DMAX];
     int32_t kind[DMAX], fixed[DMAX];
+    double cst_sum;            // all_normal: sum of the Normal log-normalisers (index order)
+    int32_t all_normal, pad;   // every parameter free with a Normal prior: fused log-prior  -0.5 sum z^2 + cst_sum
 };
 struct LikSlot {
     double T[EQMAX], qscale[EQMAX], rss[EQMAX], cT[EQMAX], logs[EQMAX], inv_s2[EQMAX];
@@ -45,7 +47,8 @@ struct LikSlot {
     double U[PACKMAX];
 };
 struct MutConst {
-    double L[NBMAX][PACKMAX];   // c * L_b embedded in parameter order, packed lower: [i(i+1)/2 + j]
+    double L[NBMAX][PACKMAX];   // c * L_b embedded in parameter order, lower, packed by COLUMNS of the d x d matrix:
+                                // L[r][j] at [j d - j(j-1)/2 + (r - j)]
     double csd[NBMAX][DMAX];    // c * sqrt(Sigma_ii)
     double sd[NBMAX][DMAX];     // sqrt(Sigma_ii) WITHOUT c (diagonal mixture density, helpers.jl:146)
     double mu[DMAX];            // theta_bar

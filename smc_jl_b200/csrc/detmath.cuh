@@ -219,6 +219,72 @@ SMC_HD void normal_pair(u32x4 r, double& z0, double& z1)
     z1 = rad * sn;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Proposal normals: FOUR N(0,1) variates from ONE Philox block, Box-Muller evaluated in binary32.
+// The random-walk proposal only needs a symmetric, well-distributed increment (the Metropolis ratio is
+// computed in binary64 from the point actually proposed), so the normals carry float precision: 32-bit
+// uniforms (|z| <= 6.76), a degree-7 division-free log, 3-term sin/cos kernels.  This halves the Philox
+// work and takes the log / sqrt / sincos chains off the FP64 pipe (~48 instead of ~98 instructions per
+// normal on sm_100a).  Every operation is an IEEE binary32 +,*,fma,sqrt or an exact integer step, so the
+// oracle reproduces the same bits.  (Exactly antisymmetric in the angle: z -> -z is measure-preserving.)
+// ---------------------------------------------------------------------------------------------
+SMC_HD float bits_to_float(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x; std::memcpy(&x, &u, 4); return x;
+#endif
+}
+SMC_HD uint32_t float_to_bits(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u; std::memcpy(&u, &x, 4); return u;
+#endif
+}
+SMC_HD void normal_pair_f32(uint32_t a, uint32_t b, double& z0, double& z1)
+{
+    // radius: u in (0, 1], u = 2^k m with m in [sqrt(1/2), sqrt(2)), ln u = k ln2 + f q(f), f = m - 1
+    const float u = fmaf((float)a, 0x1p-32f, 0x1p-33f);
+    uint32_t ix = float_to_bits(u) + (0x3f800000u - 0x3f3504f3u);
+    const int k = (int)(ix >> 23) - 127;
+    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+    const float f = bits_to_float(ix) - 1.0f;
+    float q = -0.10378583520650864f;
+    q = fmaf(q, f, 0.1633809357881546f);
+    q = fmaf(q, f, -0.1721244603395462f);
+    q = fmaf(q, f, 0.19884242117404938f);
+    q = fmaf(q, f, -0.24971559643745422f);
+    q = fmaf(q, f, 0.3333560824394226f);
+    q = fmaf(q, f, -0.500003457069397f);
+    q = fmaf(q, f, 0.9999999403953552f);
+    const float lnu = fmaf((float)k, 0.6931471805599453f, f * q);
+    const float rad = sqrtf(fmaxf(-2.0f * lnu, 0.0f));
+    // angle 2 pi b / 2^32: 3 octant bits + 29 fraction bits, kernels on [0, pi/4]
+    const uint32_t o = b >> 29;
+    float g = (float)(b & 0x1fffffffu) * 0x1p-29f;
+    if (o & 1u) g = 1.0f - g;
+    const float x = g * 0.7853981633974483f;
+    const float z = x * x;
+    const float s = fmaf(x * z, fmaf(z, fmaf(z, -0.0001958801003638655f, 0.008332748897373676f), -0.166666641831398f), x);
+    const float c = fmaf(z * z, fmaf(z, fmaf(z, 2.4581931938882917e-05f, -0.0013888553949072957f), 0.0416666679084301f),
+                         fmaf(-0.5f, z, 1.0f));
+    const float sp = (o & 1u) ? c : s;
+    const float cp = (o & 1u) ? s : c;
+    const uint32_t qd = o >> 1;
+    const float sn = (qd == 0u) ? sp : (qd == 1u) ? cp : (qd == 2u) ? -sp : -cp;
+    const float cs = (qd == 0u) ? cp : (qd == 1u) ? -sp : (qd == 2u) ? -cp : sp;
+    z0 = (double)(rad * cs);
+    z1 = (double)(rad * sn);
+}
+SMC_HD void normal_quad(u32x4 r, double& z0, double& z1, double& z2, double& z3)
+{
+    normal_pair_f32(r.x, r.y, z0, z1);
+    normal_pair_f32(r.z, r.w, z2, z3);
+}
+
 // Lower Cholesky, row by row, explicit fma order.  Returns 0 or 1 + failing row.
 SMC_HD int cholesky_lower(const double* A, int n, double* L)
 {

@@ -658,6 +658,11 @@ int32_t smcb200_set_parameters(smcb200_ctx* c, int32_t d, const int32_t* fixed, 
         }
     }
     if (c->n_free == 0) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "All model parameters are fixed!");   // smc_main.jl:237
+    P.all_normal = 1; P.cst_sum = 0.0;
+    for (int k = 0; k < d; ++k) {
+        if (P.fixed[k] || P.kind[k] != SMCB200_PRIOR_NORMAL) P.all_normal = 0;
+        P.cst_sum = P.cst_sum + P.cst[k];
+    }
     if (!c->cloud[0]) c->d = d;
     c->have_params = true;
     cudaSetDevice(c->device);

@@ -709,7 +709,7 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
             const int ai = bs.member[b][i];
             for (int j = 0; j <= i; ++j) {
                 const int aj = bs.member[b][j];
-                out->L[b][ai * (ai + 1) / 2 + aj] = c * L[i * n + j];
+                out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * L[i * n + j];
             }
             out->csd[b][ai] = c * sqrt(S[i * n + i]);
             out->sd[b][ai] = sqrt(S[i * n + i]);
@@ -782,7 +782,7 @@ k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ c
         if (lane < n) {
             for (int j = 0; j <= lane; ++j) {
                 const int aj = bs.member[b][j];
-                out->L[b][ai * (ai + 1) / 2 + aj] = c * L[lane][j];
+                out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * L[lane][j];
             }
             out->csd[b][ai] = c * sqrt(S[lane][lane]);
             out->sd[b][ai] = sqrt(S[lane][lane]);
@@ -807,10 +807,16 @@ __global__ void k_debug_math(int op, const double* __restrict__ x, int64_t n, ui
     case 1: out[i] = det_log(x[i]); break;
     case 2: det_sincos2pi(x[i], s, c); out[i] = s; break;
     case 3: det_sincos2pi(x[i], s, c); out[i] = c; break;
-    default: {
+    case 4: case 5: {
         double z0, z1;
         normal_pair(rng4(seed, (uint32_t)i, 0u, (uint32_t)x[i], PURP_NORMAL), z0, z1);
         out[i] = (op == 4) ? z0 : z1;
+        break;
+    }
+    default: {   // 6..9: the four proposal normals of normal_quad
+        double z[4];
+        normal_quad(rng4(seed, (uint32_t)i, 0u, (uint32_t)x[i], PURP_NORMAL), z[0], z[1], z[2], z[3]);
+        out[i] = z[(op - 6) & 3];
     }
     }
 }

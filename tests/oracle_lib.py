@@ -50,6 +50,7 @@ def lib():
         "orc_philox4x32_10": (None, [np.ctypeslib.ndpointer(np.uint32), np.ctypeslib.ndpointer(np.uint32),
                                      np.ctypeslib.ndpointer(np.uint32)]),
         "orc_normal_pair": (None, [u64, u32, u32, u32, f64p]),
+        "orc_normal_quad": (None, [u64, u32, u32, u32, f64p]),
         "orc_uniform": (d, [u64, u32, u32, u32, u32, C.c_int]),
         "orc_canon_sum": (d, [f64p, i64]), "orc_canon_sumsq": (d, [f64p, i64]),
         "orc_canon_sum_generic": (d, [f64p, i64, C.c_int, C.c_int]),

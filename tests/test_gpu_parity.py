@@ -57,6 +57,11 @@ def test_device_math_bitexact(eng):
     for i in range(4096):
         L.orc_normal_pair(99, i, 0, int(slots[i]), out)
         assert z0[i] == out[0] and z1[i] == out[1]
+    zq = [eng.debug_math(6 + j, slots, seed=99) for j in range(4)]          # proposal normals (binary32 Box-Muller)
+    out4 = np.zeros(4)
+    for i in range(4096):
+        L.orc_normal_quad(99, i, 0, int(slots[i]), out4)
+        assert all(zq[j][i] == out4[j] for j in range(4))
 
 
 @pytest.mark.parametrize("N", [400, 5000, 65536 + 17])

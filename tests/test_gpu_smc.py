@@ -27,15 +27,17 @@ def wmean(cloud):
 
 def test_full_run_linear_model(golden):
     """test/smc.jl:13-57: N = 5000, n_Phi = 120, lambda = 2.1, alpha = 0.9 (:26-29); 'mean within 0.5 of truth'
-    (:53-57).  (With alpha = 1 and these 1e3-wide priors a 5000-particle run is seed-fragile in the oracle as well:
-    the mixture proposal's independence component is what rescues a collapsed equation.)"""
+    (:53-57).  With these 1e3-wide priors the first correction step collapses the cloud onto a handful of particles
+    whatever the stream; with the reference's 1 MH step and 1 block the outcome is then seed-dependent (about 4 of
+    12 seeds leave one equation unconverged, in the oracle too -- the reference's own stored run is visibly
+    under-converged), so this test uses 3 MH steps and 3 random blocks (0 of 10 seeds fail)."""
     from smc_jl_b200 import smc
     g = golden("linear_model_rows.npz")
     data, X = g["data"], g["X"]
     params = W.three_equation_parameters()
     cloud, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=5000,
                        n_Φ=120, λ=2.1, resampling_method="systematic", threshold_ratio=0.5, c=0.5, α=0.9, target=0.25,
-                       use_fixed_schedule=True, seed=42)
+                       n_mh_steps=3, n_blocks=3, use_fixed_schedule=True, seed=42)
     truth = np.array([1, 1, 1, 2, 2, 1, 3, 3, 1], dtype=float)     # alpha_i = beta_i = i, sigma = 1
     mean = wmean(cloud)
     assert np.all(np.abs(mean - truth) < 0.5)
@@ -51,7 +53,7 @@ def test_full_run_linear_model(golden):
         else:
             assert np.all(Wm[:, n] == 1.0)
     assert cloud.resamples == int(np.sum(cloud.ESS[1:] < 2500))
-    assert 0.1 < cloud.accept < 0.6
+    assert 0.1 < cloud.accept < 3 * 0.6                      # accept is a SUM over the 3 MH steps (particle.jl:410-418)
     # same statistical anchor as the reference's stored run (under-converged there)
     ref = golden("correction_history.npz")
     assert np.all(np.abs(mean - ref["final_mean"]) < 0.35)
@@ -65,9 +67,9 @@ def test_bridged_run_with_old_data(golden):
     data, X = g["data"], g["X"]
     params = W.three_equation_parameters()
     old = M.LinearEquationsLogLik(data[:, :50], X)
-    c1, _, _ = smc(old, params, data[:, :50], verbose="none", testing=True, n_parts=4000, n_Φ=150, n_mh_steps=3, α=0.9, seed=1)
-    c2, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=4000, n_Φ=60, n_mh_steps=3,
-                    α=0.9, old_data=data[:, :50], old_cloud=c1, old_loglikelihood=old, seed=2)
+    c1, _, _ = smc(old, params, data[:, :50], verbose="none", testing=True, n_parts=16000, n_Φ=150, n_mh_steps=3, n_blocks=3, α=0.9, seed=1)
+    c2, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=16000, n_Φ=60, n_mh_steps=3,
+                    n_blocks=3, α=0.9, old_data=data[:, :50], old_cloud=c1, old_loglikelihood=old, seed=2)
     truth = np.array([1, 1, 1, 2, 2, 1, 3, 3, 1], dtype=float)
     assert np.all(np.abs(wmean(c1) - truth) < 0.5)
     assert np.all(np.abs(wmean(c2) - truth) < 0.5)
@@ -75,7 +77,7 @@ def test_bridged_run_with_old_data(golden):
     # generalised tempering: old_loglh holds the likelihood of the old data at the final draws
     import oracle_lib as O
     mod = O.Model(M.make_spec(params, M.LinearEquationsLogLik(data, X), old))
-    for r in range(0, 4000, 400):
+    for r in range(0, 16000, 1600):
         th = np.ascontiguousarray(c2.particles[r, :9])
         assert c2.particles[r, 11] == mod.loglik(th, 1)
         assert c2.particles[r, 9] == mod.loglik(th, 0)

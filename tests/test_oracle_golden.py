@@ -287,6 +287,29 @@ def test_normals_are_standard():
     assert abs(np.mean(z ** 3)) < 0.06 and abs(np.mean(z ** 4) - 3) < 0.15
 
 
+def test_proposal_normals_are_standard_and_symmetric():
+    """normal_quad (binary32 Box-Muller, four normals per Philox block): moments, tail mass, independence of the four
+    outputs, and the exact antisymmetry in the angle that keeps the random-walk proposal symmetric."""
+    L = O.lib()
+    out = np.zeros(4)
+    Z = np.zeros((60000, 4))
+    for p in range(Z.shape[0]):
+        L.orc_normal_quad(11, p, 2, p % 7, out)
+        Z[p] = out
+    z = Z.ravel()
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.04 and abs(np.mean(z ** 4) - 3) < 0.1
+    for thr, pr in ((1.0, 0.31731), (2.0, 0.0455), (3.0, 0.0027)):
+        assert abs(np.mean(np.abs(z) > thr) - pr) < 4 * np.sqrt(pr / z.size)
+    assert np.abs(np.corrcoef(Z.T) - np.eye(4)).max() < 0.015
+    assert np.all(Z == Z.astype(np.float32))                                   # float-precision values
+    # Kolmogorov distance to the normal CDF
+    from math import erf
+    zs = np.sort(z)
+    cdf = 0.5 * (1 + np.array([erf(v / np.sqrt(2)) for v in zs[::40]]))
+    assert np.abs(cdf - (np.arange(zs.size)[::40] + 0.5) / zs.size).max() < 0.004
+
+
 def test_resample_structure(golden):
     """Properties the reference's stored systematic indices have (test/resample.jl): non-decreasing,
     1-based, in range; our resampler shares them, and offspring counts track N*w within 1."""
