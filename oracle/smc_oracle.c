@@ -587,8 +587,9 @@ ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double
     for (int k = 0; k < d; ++k) mean[k] = tree_inplace(tiles + (size_t)(k + 1) * P, P) / sw;
     free(tiles);
     /* pass 2: centred weighted scatter, lower triangle, then / Sw; symmetric by construction.
-     * Canonical order: sequential fma over each chunk of M2_CH consecutive particles, then the
-     * adjacent-pair tree over chunks (zero padded to a power of two). */
+     * Canonical order: inside each chunk of M2_CH consecutive particles lane l accumulates particles
+     * l, l + 32, ... sequentially with fma, then the adjacent-pair tree over the 32 lanes, then over
+     * chunks (zero padded to a power of two). */
     i64 nch = (N + M2_CH - 1) / M2_CH;
     i64 Pc = next_pow2(nch < 1 ? 1 : nch);
     double *tl = (double *)calloc((size_t)Pc, sizeof(double));
@@ -598,13 +599,18 @@ ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double
             const double *xb = COL(cloud, N, b);
             memset(tl, 0, sizeof(double) * (size_t)Pc);
             for (i64 c = 0; c < nch; ++c) {
-                double acc = 0.0;
-                i64 hi = (c + 1) * M2_CH < N ? (c + 1) * M2_CH : N;
-                for (i64 i = c * M2_CH; i < hi; ++i) {
-                    double da = xa[i] - mean[a], db = xb[i] - mean[b];
-                    acc = FMA(w[i] * da, db, acc);
+                for (int l = 0; l < M_LANES; ++l) {
+                    double acc = 0.0;
+                    for (int r = 0; r < M2_CH / M_LANES; ++r) {
+                        i64 i = c * M2_CH + (i64)r * M_LANES + l;
+                        if (i < N) {
+                            double da = xa[i] - mean[a], db = xb[i] - mean[b];
+                            acc = FMA(w[i] * da, db, acc);
+                        }
+                    }
+                    lane[l] = acc;
                 }
-                tl[c] = acc;
+                tl[c] = tree_inplace(lane, M_LANES);
             }
             double v = tree_inplace(tl, Pc) / sw;
             cov[(size_t)a * d + b] = v;

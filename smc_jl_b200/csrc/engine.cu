@@ -280,10 +280,11 @@ Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt <
 template <int D>
 int launch_m2(Ctx* c, const double* cl, double* partials, const Tiles& t)
 {
-    const size_t smem = sizeof(double) * M2_WARPS * 32 * M2Cfg<D>::STRIDE;
+    const size_t stage = (size_t)(D + 1) * M2_CH, red = (size_t)(D * (D + 1) / 2) * 33;   // the reduction rows alias the staged columns
+    const size_t smem = sizeof(double) * (stage > red ? stage : red);
     if (smem > 48 * 1024)
         SMC_CUDA(c, cudaFuncSetAttribute(k_moments2<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_moments2<D><<<(t.ntiles + M2_WARPS - 1) / M2_WARPS, 32 * M2_WARPS, smem, c->stream>>>(cl, c->N, c->msum, partials, t.P);
+    k_moments2<D><<<t.ntiles, 32 * M2_G, smem, c->stream>>>(cl, c->N, c->msum, partials, t.P);
     return SMCB200_OK;
 }
 
@@ -316,7 +317,7 @@ int launch_moments(Ctx* c)
     case 20: st = launch_m2<20>(c, cl, part, tc); break;
     case 24: st = launch_m2<24>(c, cl, part, tc); break;
     case 32: st = launch_m2<32>(c, cl, part, tc); break;
-    default: k_moments2_generic<<<tc.ntiles, 32, 0, c->stream>>>(cl, c->N, d, c->msum, part, tc.P); break;
+    default: k_moments2_generic<<<tc.ntiles, 128, 0, c->stream>>>(cl, c->N, d, c->msum, part, tc.P); break;
     }
     if (st) return st;
     k_tree_finalize<<<E, 256, 0, c->stream>>>(part, tc.ntiles, tc.P, c->world > 1 ? c->scal_loc + SL_CSUM : c->csum);

@@ -550,112 +550,139 @@ k_moments1(const double* __restrict__ cloud, int64_t N, int d, double* __restric
 }
 
 // pass 2: csum[a(a+1)/2 + b] = sum_i (w_i (x_ia - mean_a)) (x_ib - mean_b), b <= a.
-// Register-tiled SYRK: one warp owns a chunk of M2_CH consecutive particles and accumulates over them
-// sequentially (canonical order); lane (I, J), I >= J, owns the BS x BS block of entries
-// (a, b) = (BS*I + i, BS*J + j).  Particles are staged 32 at a time through shared memory as rows
-// [dx_0..dx_{DP-1} | w*dx_0..w*dx_{DP-1}], so each particle costs a lane 2*BS broadcast LDS and BS*BS DFMA.
+// Canonical order per entry: inside a chunk of M2_CH = 512 consecutive particles lane l accumulates particles
+// l, l + 32, ... sequentially with fma, then the adjacent-pair tree over the 32 lanes, then over chunks.
+// Mapping: one block per chunk.  The chunk's d + 1 columns (86 KB at d = 20) are brought into shared memory by
+// asynchronous copies that are all in flight at once (LDGSTS, no registers; two resident blocks per SM keep
+// ~170 KB outstanding, which is what HBM needs), then lane = particle (conflict-free column reads) and warp g owns
+// the matrix rows [rowb(g), rowb(g+1)) of the lower triangle (balanced entry counts: 55/50/48/57 at d = 20) with
+// its entries in registers: 210 DFMA per particle against 21 x 4 shared loads.
+constexpr int M2_G = 4;                       // row groups (warps) per block
+constexpr int M2_R = M2_CH / 32;              // sequential depth per lane
 template <int D>
-struct M2Cfg {
-    static constexpr int BS = (D + 6) / 7;            // <= 7 block rows  =>  <= 28 lower block pairs
-    static constexpr int DB = (D + BS - 1) / BS;
-    static constexpr int DP = DB * BS;                // padded dimension
-    static constexpr int STRIDE = 2 * DP + 1;         // odd row stride: conflict-free transposed stores
-    static constexpr int NPAIR = DB * (DB + 1) / 2;
-};
-constexpr int M2_WARPS = 4;
+__host__ __device__ constexpr int m2_rowb(int g)
+{
+    // smallest a with a(a+1)/2 >= g * E / G : balances the number of entries per group
+    int a = 0;
+    while (a < D && (a * (a + 1)) / 2 * M2_G < g * (D * (D + 1) / 2)) ++a;
+    return g >= M2_G ? D : a;
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int D, int GRP>
+__device__ __forceinline__ void m2_group(const double* __restrict__ xs /* smem [D+1][M2_CH] */, int64_t N, int64_t c0, int64_t chunk,
+                                         int lane, const double* __restrict__ mean, double* __restrict__ red)
+{
+    constexpr int A0 = m2_rowb<D>(GRP), A1 = m2_rowb<D>(GRP + 1);
+    if (A1 <= A0) { __syncthreads(); return; }     // (keeps the block barrier below matched)
+    constexpr int NR = (A1 > A0) ? (A1 - A0) : 1;
+    double acc[NR][A1];
+#pragma unroll
+    for (int a = 0; a < NR; ++a)
+#pragma unroll
+        for (int b = 0; b < A1; ++b) acc[a][b] = 0.0;
+    double mu[A1];
+#pragma unroll
+    for (int k = 0; k < A1; ++k) mu[k] = mean[k];
+#pragma unroll 2
+    for (int r = 0; r < M2_R; ++r) {
+        const int64_t i = c0 + (int64_t)r * 32 + lane;
+        if (i < N) {
+            double dx[A1];
+#pragma unroll
+            for (int k = 0; k < A1; ++k) dx[k] = xs[k * M2_CH + r * 32 + lane] - mu[k];
+            const double wi = xs[D * M2_CH + r * 32 + lane];
+#pragma unroll
+            for (int a = A0; a < A1; ++a) {
+                const double wa = wi * dx[a];
+#pragma unroll
+                for (int b = 0; b <= a; ++b) acc[a - A0][b] = fma(wa, dx[b], acc[a - A0][b]);
+            }
+        }
+    }
+    // per-lane sums -> shared memory rows [entry][lane] (row stride 33: conflict-free for the row-wise tree below);
+    // the rows alias the staged columns, so every warp of the block must have finished reading them
+    __syncthreads();
+#pragma unroll
+    for (int a = A0; a < A1; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) red[(a * (a + 1) / 2 + b) * 33 + lane] = acc[a - A0][b];
+}
 
 template <int D>
-__global__ void __launch_bounds__(32 * M2_WARPS)
+__global__ void __launch_bounds__(32 * M2_G)
 k_moments2(const double* __restrict__ cloud, int64_t N, const double* __restrict__ msum,
            double* __restrict__ partials, int P)
 {
-    using C = M2Cfg<D>;
-    constexpr int BS = C::BS, DP = C::DP, STRIDE = C::STRIDE;
-    extern __shared__ double sm_m2[];
+    extern __shared__ double sm_m2[];          // [D + 1][M2_CH]: parameter columns, then the weight column
     __shared__ double mean[D];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < D) mean[threadIdx.x] = msum[1 + threadIdx.x] / msum[0];
-    __syncthreads();
-    double* rows = sm_m2 + (size_t)warp * 32 * STRIDE;
-    const int64_t chunk = (int64_t)blockIdx.x * M2_WARPS + warp;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x;
     const int64_t c0 = chunk * M2_CH;
-    if (c0 >= N) return;
-    // lane -> block pair (I, J), I >= J
-    int I = 0;
-    while ((I + 1) * (I + 2) / 2 <= lane) ++I;
-    const int J = lane - I * (I + 1) / 2;
-    const bool active = lane < C::NPAIR;
-    const int ao = active ? DP + BS * I : DP, bo = active ? BS * J : 0;
-    double acc[BS][BS];
+    constexpr int NT = 32 * M2_G, PER = M2_CH / NT;
+    if (c0 + M2_CH <= N) {                     // full chunk: (D + 1) * PER copies per thread, pointer stepping only
+        const double* src = cloud + c0 + threadIdx.x;
+        double* dst = sm_m2 + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < BS; ++i)
+        for (int k = 0; k <= D; ++k) {
+            const double* col = (k < D) ? src + col_off(N, k) : src + col_off(N, D + 4);
 #pragma unroll
-        for (int j = 0; j < BS; ++j) acc[i][j] = 0.0;
-    const double* __restrict__ w = cloud + col_off(N, D + 4);
-
-    double xv[D], wv = 0.0;
-    auto load = [&](int64_t i) {
-        if (i < N) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) xv[k] = cloud[col_off(N, k) + i];
-            wv = w[i];
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) xv[k] = 0.0;
-            wv = 0.0;
+            for (int j = 0; j < PER; ++j) cp_async8(dst + k * M2_CH + j * NT, col + j * NT);
         }
-    };
-    load(c0 + lane);
-    for (int sub = 0; sub < M2_CH / 32; ++sub) {
-        // stage the prefetched particle of this lane
-        double* my = rows + lane * STRIDE;
-#pragma unroll
-        for (int k = 0; k < DP; ++k) {
-            const double dx = (k < D) ? xv[k < D ? k : 0] - mean[k < D ? k : 0] : 0.0;
-            my[k] = dx;
-            my[DP + k] = wv * dx;
+    } else {
+        for (int idx = threadIdx.x; idx < (D + 1) * M2_CH; idx += NT) {
+            const int k = idx / M2_CH, p = idx % M2_CH;
+            const int64_t i = c0 + p;
+            if (i < N) cp_async8(sm_m2 + idx, cloud + col_off(N, k < D ? k : D + 4) + i);
+            else sm_m2[idx] = 0.0;
         }
-        __syncwarp();
-        const int64_t nxt = c0 + (int64_t)(sub + 1) * 32 + lane;
-        if (sub + 1 < M2_CH / 32) load(nxt);                 // prefetch the next 32 particles (in flight during the FMAs)
-        int64_t rem = N - (c0 + (int64_t)sub * 32);
-        const int np = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
-        for (int p = 0; p < np; ++p) {
-            const double* row = rows + p * STRIDE;
-            double av[BS], bv[BS];
-#pragma unroll
-            for (int i = 0; i < BS; ++i) { av[i] = row[ao + i]; bv[i] = row[bo + i]; }
-#pragma unroll
-            for (int i = 0; i < BS; ++i)
-#pragma unroll
-                for (int j = 0; j < BS; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-        }
-        __syncwarp();
     }
-    if (active) {
+    if (threadIdx.x < D) mean[threadIdx.x] = msum[1 + threadIdx.x] / msum[0];
+    cp_async_wait_all();
+    __syncthreads();
+    constexpr int E = D * (D + 1) / 2;
+    double* red = sm_m2;                       // [E][33] per-lane sums, aliasing the staged columns once every warp is done
+    switch (g) {     // warp-uniform: each group is compiled with static row bounds (register-resident accumulators)
+    case 0: m2_group<D, 0>(sm_m2, N, c0, chunk, lane, mean, red); break;
+    case 1: m2_group<D, 1>(sm_m2, N, c0, chunk, lane, mean, red); break;
+    case 2: m2_group<D, 2>(sm_m2, N, c0, chunk, lane, mean, red); break;
+    default: m2_group<D, 3>(sm_m2, N, c0, chunk, lane, mean, red); break;
+    }
+    __syncthreads();
+    // adjacent-pair tree over the 32 lanes of every entry, one thread per entry (registers)
+    for (int e = threadIdx.x; e < E; e += NT) {
+        double v[32];
 #pragma unroll
-        for (int i = 0; i < BS; ++i)
+        for (int l = 0; l < 32; ++l) v[l] = red[e * 33 + l];
 #pragma unroll
-            for (int j = 0; j < BS; ++j) {
-                const int a = BS * I + i, b = BS * J + j;
-                if (a < D && b <= a) partials[(size_t)(a * (a + 1) / 2 + b) * P + chunk] = acc[i][j];
-            }
+        for (int sft = 1; sft < 32; sft <<= 1)
+#pragma unroll
+            for (int l = 0; l < 32; l += 2 * sft) v[l] = v[l] + v[l + sft];
+        partials[(size_t)e * P + chunk] = v[0];
     }
 }
 
-// generic-d fallback of pass 2 (one warp per chunk, lanes over entries; any d <= DMAX)
-__global__ void __launch_bounds__(32)
+// generic-d fallback of pass 2 (one block of 4 warps per chunk, warps over entries; any d <= DMAX); same order
+__global__ void __launch_bounds__(128)
 k_moments2_generic(const double* __restrict__ cloud, int64_t N, int d, const double* __restrict__ msum,
                    double* __restrict__ partials, int P)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t chunk = blockIdx.x;
     const int64_t c0 = chunk * M2_CH;
-    const int64_t c1 = (c0 + M2_CH < N) ? c0 + M2_CH : N;
     const double* w = cloud + col_off(N, d + 4);
     const double sw = msum[0];
     const int E = d * (d + 1) / 2;
-    for (int e = lane; e < E; e += 32) {
+    for (int e = warp; e < E; e += 4) {
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= e) ++a;
         const int b = e - a * (a + 1) / 2;
@@ -663,8 +690,12 @@ k_moments2_generic(const double* __restrict__ cloud, int64_t N, int d, const dou
         const double* xa = cloud + col_off(N, a);
         const double* xb = cloud + col_off(N, b);
         double acc = 0.0;
-        for (int64_t i = c0; i < c1; ++i) acc = fma(w[i] * (xa[i] - ma), xb[i] - mb, acc);
-        partials[(size_t)e * P + chunk] = acc;
+        for (int r = 0; r < M2_R; ++r) {
+            const int64_t i = c0 + (int64_t)r * 32 + lane;
+            if (i < N) acc = fma(w[i] * (xa[i] - ma), xb[i] - mb, acc);
+        }
+        acc = warp_tree(acc);
+        if (lane == 0) partials[(size_t)e * P + chunk] = acc;
     }
 }
 
