@@ -41,10 +41,22 @@ Cloud(n_params::Int, n_parts::Int) =
 Base.length(c::Cloud) = size(c.particles, 1)
 
 # ---- likelihood descriptors: valid `loglikelihood` arguments that name a device functor ------------------
-struct GaussRegLogLik <: Function
+abstract type DeviceLogLik <: Function end
+struct GaussRegLogLik <: DeviceLogLik              # SMCB200_LIK_GAUSSREG
     iparams::Vector{Int32}          # n_eq, k, stride, coef_off, sig_off
     dparams::Vector{Float64}        # per equation: T, qscale, rss, sigma_fixed, bhat[k], U[k*k] (row-major upper)
 end
+lik_kind(::GaussRegLogLik) = Int32(1)
+# Three-equation An-Schorfheide DSGE model (examples/dsge_models/small_dsge_model.jl:35-50): replaces the closure
+#   loglik(p, d) = DSGE.likelihood(m, d; sampler = false, catch_errors = true, use_chand_recursion = true)
+# `parameters` must be DSGE.jl's AnSchorfheide ParameterVector (16 entries); data is 3 x T.
+struct AnSchorfheideLogLik <: DeviceLogLik         # SMCB200_LIK_AS_DSGE
+    iparams::Vector{Int32}          # n_periods, n_presample
+    dparams::Vector{Float64}        # vec(data): 3 x T column-major
+end
+AnSchorfheideLogLik(data::Matrix{Float64}; n_presample::Int = 2) =
+    AnSchorfheideLogLik(Int32[size(data, 2), n_presample], vec(data))
+lik_kind(::AnSchorfheideLogLik) = Int32(2)
 function LinearGaussianLogLik(y::Vector{Float64}, X::Matrix{Float64}; σ2::Float64 = 1.0)
     T, k = size(X)
     F = qr(X); R = Matrix(F.R); s = sign.(diag(R)); R = s .* R
@@ -89,7 +101,7 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
              old_loglikelihood::Function = loglikelihood, tempered_update_prior_weight::Float64 = 0.0,
              log_prob_old_data::Float64 = 0.0, savepath::String = "smc_cloud.jld2", seed::UInt64 = UInt64(1793),
              device::Int = 0, kwargs...)
-    loglikelihood isa GaussRegLogLik ||
+    loglikelihood isa DeviceLogLik ||
         throw(ArgumentError("loglikelihood must be a device likelihood descriptor; there is no CPU fallback"))
     resampling_method in (:systematic, :multinomial) ||
         throw("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
@@ -112,17 +124,20 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
             lk === nothing && continue
             GC.@preserve lk check(h, ccall((:smcb200_set_likelihood, LIB), Int32,
                 (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int64),
-                h, slot, 1, lk.iparams, length(lk.iparams), lk.dparams, length(lk.dparams)))
+                h, slot, lik_kind(lk), lk.iparams, length(lk.iparams), lk.dparams, length(lk.dparams)))
         end
-        # stage 0 (src/initialization.jl:88-119): prior draws on the host, evaluation on the device
+        # stage 0: initial_draw! on the device (src/initialization.jl:88-119), or the online update's
+        # initialize_likelihoods! on the uploaded old cloud (:153-186)
         cloud = isempty(old_data) ? Cloud(n_para, n_parts) : old_cloud
         if isempty(old_data)
-            cloud.particles[:, 1:n_para] = rand(parameters, n_parts)'
-            cloud.particles[:, n_para + 3] .= 0.; cloud.particles[:, n_para + 5] .= 1.
+            values = Float64[p.value for p in parameters]
+            GC.@preserve values check(h, ccall((:smcb200_initial_draw, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, UInt64, Int32),
+                                               h, values, seed, 1000))
+        else
+            GC.@preserve cloud check(h, ccall((:smcb200_cloud_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
+                                              h, cloud.particles, n_parts, 0))
+            check(h, ccall((:smcb200_evaluate, LIB), Int32, (Ptr{Cvoid}, Int32), h, 1))
         end
-        GC.@preserve cloud check(h, ccall((:smcb200_cloud_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
-                                          h, cloud.particles, n_parts, 0))
-        check(h, ccall((:smcb200_evaluate, LIB), Int32, (Ptr{Cvoid}, Int32), h, isempty(old_data) ? 0 : 1))
         schedule = ((collect(1:n_Φ) .- 1) / (n_Φ - 1)) .^ λ
         cloud.tempering_schedule = use_fixed_schedule ? schedule : zeros(1)
         cloud.ESS = [Float64(n_parts)]; cloud.n_Φ = n_Φ; cloud.c = c; cloud.accept = target
