@@ -146,4 +146,4 @@ def test_multi_gpu_sharding_is_bit_invariant():
            "--master-port", "29533", os.path.join(root, "tests", "multigpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("bit-exact") == 2
+    assert out.stdout.count("bit-exact") == 3
