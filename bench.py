@@ -171,6 +171,11 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to fd 1) write to stderr
+    # for the duration of the run, the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from smc_jl_b200 import workloads as W
     from smc_jl_b200._lib import StageState
@@ -300,8 +305,11 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 def main():
