@@ -140,6 +140,11 @@ int32_t smcb200_resample(smcb200_ctx *ctx, int32_t method, uint64_t seed, uint32
  * 1-based indices; cum_out (nullable) receives cumsum(weights ./ sum(weights)). Single GPU. */
 int32_t smcb200_resample_weights(smcb200_ctx *ctx, const double *weights, int64_t n, int32_t method, uint64_t seed,
                                  uint32_t stage, double u_override, int64_t *idx_out, double *cum_out);
+/* `resample(weights; n_parts = n_out, method)`: n_out ancestors out of n weights, thresholds (i - 1 + u) / n_out
+ * (bridge initialisation, src/smc_main.jl:262-268).  All n weights are searched (the reference's systematic
+ * search stops at cumulative[n_parts], src/resample.jl:54, which makes n_parts < n unusable there). */
+int32_t smcb200_resample_weights_n(smcb200_ctx *ctx, const double *weights, int64_t n, int64_t n_out, int32_t method,
+                                   uint64_t seed, uint32_t stage, double u_override, int64_t *idx_out, double *cum_out);
 /* weighted_mean / weighted_cov (src/particle.jl:481-486,526-532): mean[n_para], cov[n_para^2]. */
 int32_t smcb200_moments(smcb200_ctx *ctx, double *mean, double *cov);
 /* mutation of every particle (src/mutation.jl:56-138 through the fan-out at smc_main.jl:471-484).

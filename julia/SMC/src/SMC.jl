@@ -181,15 +181,15 @@ function resample(weights::Vector{Float64}; n_parts::Int = length(weights), meth
     method in (:systematic, :multinomial) || throw("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     ccall((:smcb200_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32), ctx, device) == 0 || error("no GPU")
-    idx = Vector{Int64}(undef, length(weights))
+    idx = Vector{Int64}(undef, n_parts)
     try
-        GC.@preserve weights idx check(ctx[], ccall((:smcb200_resample_weights, LIB), Int32,
-            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, UInt64, UInt32, Float64, Ptr{Int64}, Ptr{Float64}),
-            ctx[], weights, length(weights), method == :systematic ? 0 : 1, seed, 0, -1.0, idx, C_NULL))
+        GC.@preserve weights idx check(ctx[], ccall((:smcb200_resample_weights_n, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int32, UInt64, UInt32, Float64, Ptr{Int64}, Ptr{Float64}),
+            ctx[], weights, length(weights), n_parts, method == :systematic ? 0 : 1, seed, 0, -1.0, idx, C_NULL))
     finally
         ccall((:smcb200_destroy, LIB), Int32, (Ptr{Cvoid},), ctx[])
     end
-    idx[1:n_parts]
+    idx
 end
 
 get_cloud(path::String) = load(path, "cloud")

@@ -491,19 +491,30 @@ enum { RESAMPLE_SYSTEMATIC = 0, RESAMPLE_MULTINOMIAL = 1 };
  * cum_out (nullable) receives cumsum(weights ./ sum(weights)).
  * Deviation: where resample.jl:60 would return 0 ("no index found", then crash in the gather)
  * we return N.  u_override >= 0 replaces the Philox draw of the systematic offset. */
+ORC_API int orc_resample_n(const double *weights_in, i64 N, i64 n_out, int method, uint64_t seed, uint32_t stage,
+                           double u_override, i64 *idx, double *cum_out);
 ORC_API int orc_resample(const double *weights_in, i64 N, int method, uint64_t seed, uint32_t stage,
                          double u_override, i64 *idx, double *cum_out)
+{
+    return orc_resample_n(weights_in, N, N, method, seed, stage, u_override, idx, cum_out);
+}
+/* resample(weights; n_parts = n_out, method): n_out ancestors out of N weights (bridge initialisation,
+ * smc_main.jl:262-268).  Thresholds are (i - 1 + u) / n_out.  Deviation: the reference's systematic search
+ * only scans cumulative[1:n_parts] (resample.jl:54, so with n_parts < length(weights) the tail of the old cloud
+ * is unreachable and the last thresholds find nothing); here all N weights are searched. */
+ORC_API int orc_resample_n(const double *weights_in, i64 N, i64 n_out, int method, uint64_t seed, uint32_t stage,
+                           double u_override, i64 *idx, double *cum_out)
 {
     double *x = (double *)malloc(sizeof(double) * (size_t)N);
     double *cum = cum_out ? cum_out : (double *)malloc(sizeof(double) * (size_t)N);
     double S = orc_canon_sum(weights_in, N);
     for (i64 i = 0; i < N; ++i) x[i] = weights_in[i] / S;
     orc_cumsum(x, N, cum);
-    double n = (double)N;
+    double n = (double)n_out;
     if (method == RESAMPLE_SYSTEMATIC) {
         double offset = (u_override >= 0.0) ? u_override : orc_uniform(seed, 0u, stage, 0u, PURP_RESAMPLE, 0);
         i64 start = 1;
-        for (i64 i = 1; i <= N; ++i) {
+        for (i64 i = 1; i <= n_out; ++i) {
             double threshold = ((double)(i - 1) + offset) / n;
             i64 found = 0;
             for (i64 j = start; j <= N; ++j)
@@ -517,7 +528,7 @@ ORC_API int orc_resample(const double *weights_in, i64 N, int method, uint64_t s
         double *m = (double *)malloc(sizeof(double) * (size_t)N);
         double mx = -INFINITY;
         for (i64 i = 0; i < N; ++i) { if (cum[i] > mx) mx = cum[i]; m[i] = mx; }
-        for (i64 i = 0; i < N; ++i) {
+        for (i64 i = 0; i < n_out; ++i) {
             double off = orc_uniform(seed, (uint32_t)i, stage, 1u, PURP_RESAMPLE, 0);
             i64 lo = 0, hi = N; /* first k with m[k] > off */
             while (lo < hi) { i64 mid = (lo + hi) >> 1; if (m[mid] > off) hi = mid; else lo = mid + 1; }

@@ -81,6 +81,7 @@ def _load():
         "smcb200_solve_adaptive_phi": (i32, [vp, vp, i32, pi64, pd, d, d, d, i32, pd]),
         "smcb200_resample": (i32, [vp, i32, u64, u32, d, vp]),
         "smcb200_resample_weights": (i32, [vp, vp, i64, i32, u64, u32, d, vp, vp]),
+        "smcb200_resample_weights_n": (i32, [vp, vp, i64, i64, i32, u64, u32, d, vp, vp]),
         "smcb200_moments": (i32, [vp, vp, vp]),
         "smcb200_mutate": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, d, d, d, d, i32, i32, u64, u32, pd]),
         "smcb200_stage": (i32, [vp, C.POINTER(StageConfig), C.POINTER(StageState), vp, i32, vp, vp, C.POINTER(StageResult)]),

@@ -178,8 +178,9 @@ int ensure_scan_buffers(Ctx* c, int nb)
 // Single-shard version (also serves the exported resample(weights) on host vectors).
 int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int method, uint64_t seed, uint32_t stage,
                             double u_override, double* rmax, double* craw, int64_t* idx, double* partials,
-                            unsigned* counter, double* sres)
+                            unsigned* counter, double* sres, int64_t n_out = -1)
 {
+    if (n_out < 0) n_out = n;
     if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
         return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
     const ScanGeom g = scan_geom(n);
@@ -201,8 +202,8 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
         const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
         u = u01(r.x, r.y);
     }
-    k_search<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(rmax, c->scan_bmax, g.nb, g.B, n, n, 0, method, seed, stage,
-                                                                 u, nd, idx);
+    k_search<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(rmax, c->scan_bmax, g.nb, g.B, n, n_out, 0, method, seed, stage,
+                                                                     u, (double)n_out, idx);
     c->launches += 7;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
@@ -845,7 +846,13 @@ int32_t smcb200_resample(smcb200_ctx* c, int32_t method, uint64_t seed, uint32_t
 int32_t smcb200_resample_weights(smcb200_ctx* c, const double* weights, int64_t n, int32_t method, uint64_t seed, uint32_t stage,
                                  double u_override, int64_t* idx_out, double* cum_out)
 {
-    if (!c || !weights || n < 1 || !idx_out) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument") : SMCB200_ERR_BAD_ARGUMENT;
+    return smcb200_resample_weights_n(c, weights, n, n, method, seed, stage, u_override, idx_out, cum_out);
+}
+
+int32_t smcb200_resample_weights_n(smcb200_ctx* c, const double* weights, int64_t n, int64_t n_out, int32_t method, uint64_t seed,
+                                   uint32_t stage, double u_override, int64_t* idx_out, double* cum_out)
+{
+    if (!c || !weights || n < 1 || n_out < 1 || !idx_out) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument") : SMCB200_ERR_BAD_ARGUMENT;
     cudaSetDevice(c->device);
     double *w = nullptr, *r = nullptr, *cr = nullptr, *part = nullptr;
     int64_t* idx = nullptr;
@@ -853,13 +860,13 @@ int32_t smcb200_resample_weights(smcb200_ctx* c, const double* weights, int64_t 
     SMC_CUDA(c, cudaMalloc(&w, sizeof(double) * n));
     SMC_CUDA(c, cudaMalloc(&r, sizeof(double) * n));
     SMC_CUDA(c, cudaMalloc(&cr, sizeof(double) * n));
-    SMC_CUDA(c, cudaMalloc(&idx, sizeof(int64_t) * n));
+    SMC_CUDA(c, cudaMalloc(&idx, sizeof(int64_t) * n_out));
     SMC_CUDA(c, cudaMalloc(&part, sizeof(double) * t.P));
     SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * t.P, c->stream));
     SMC_CUDA(c, cudaMemcpyAsync(w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    int st = launch_resample_indices(c, w, 0, n, method, seed, stage, u_override, r, cr, idx, part, c->counters + 4, c->scal + SC_SRES);
+    int st = launch_resample_indices(c, w, 0, n, method, seed, stage, u_override, r, cr, idx, part, c->counters + 4, c->scal + SC_SRES, n_out);
     if (st == SMCB200_OK) {
-        cudaMemcpyAsync(idx_out, idx, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(idx_out, idx, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, c->stream);
         if (cum_out) cudaMemcpyAsync(cum_out, cr, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
         st = sync(c);
     }

@@ -176,13 +176,15 @@ class Engine:
         self._ck(lib.smcb200_resample(self.h, RESAMPLERS[method], seed, stage, u, ptr(idx)))
         return idx
 
-    def resample_weights(self, weights, method="systematic", seed=0, stage=0, u=-1.0, want_cum=False):
+    def resample_weights(self, weights, method="systematic", seed=0, stage=0, u=-1.0, want_cum=False, n_parts=None):
+        """`resample(weights; n_parts = length(weights), method)` (src/resample.jl:23): 1-based ancestor indices."""
         if method not in RESAMPLERS:
             raise ValueError("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
         w = _f64(weights)
-        idx = np.zeros(len(w), np.int64)
+        n_out = len(w) if n_parts is None else int(n_parts)
+        idx = np.zeros(n_out, np.int64)
         cum = np.zeros(len(w)) if want_cum else None
-        self._ck(lib.smcb200_resample_weights(self.h, ptr(w), len(w), RESAMPLERS[method], seed, stage, u, ptr(idx), ptr(cum)))
+        self._ck(lib.smcb200_resample_weights_n(self.h, ptr(w), len(w), n_out, RESAMPLERS[method], seed, stage, u, ptr(idx), ptr(cum)))
         return (idx, cum) if want_cum else idx
 
     def moments(self):

@@ -60,6 +60,7 @@ def lib():
         "orc_solve_adaptive_phi": (C.c_int, [f64p, i64, C.c_int, f64p, C.c_int, C.POINTER(i64), C.POINTER(d), d, d, d,
                                             C.c_int, C.POINTER(d), C.POINTER(i64)]),
         "orc_resample": (C.c_int, [f64p, i64, C.c_int, u64, u32, d, i64p, vp]),
+        "orc_resample_n": (C.c_int, [f64p, i64, i64, C.c_int, u64, u32, d, i64p, vp]),
         "orc_gather": (None, [f64p, f64p, i64, C.c_int, i64p]),
         "orc_update_c": (d, [d, d, d]),
         "orc_moments": (None, [f64p, i64, C.c_int, f64p, f64p]),

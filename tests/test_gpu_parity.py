@@ -180,6 +180,24 @@ def test_resample_explicit_offset_edges(eng):
         eng.resample_weights(w, "polyalgo")
 
 
+@pytest.mark.parametrize("method", ["systematic", "multinomial"])
+def test_resample_with_n_parts_bitexact(eng, method):
+    """`resample(weights; n_parts = n_out)` with n_out != length(weights) (bridge, smc_main.jl:262-268)."""
+    rng = np.random.default_rng(77)
+    w = rng.gamma(0.7, 1.0, 5000)
+    for n_out in (1, 2500, 5000, 12000):
+        idx = eng.resample_weights(w, method, seed=5, stage=3, n_parts=n_out)
+        oidx = np.zeros(n_out, np.int64)
+        assert O.lib().orc_resample_n(w, 5000, n_out, 0 if method == "systematic" else 1, 5, 3, -1.0, oidx, None) == 0
+        assert idx.shape == (n_out,) and np.array_equal(idx, oidx)
+        assert idx.min() >= 1 and idx.max() <= 5000
+        if method == "systematic":
+            assert np.all(np.diff(idx) >= 0)
+            if n_out >= 2500:                      # offspring counts track n_out * w within 1
+                counts = np.bincount(idx - 1, minlength=5000)
+                assert np.all(np.abs(counts - n_out * w / w.sum()) < 1 + 1e-9)
+
+
 @pytest.mark.parametrize("N,d", [(5000, 9), (4096, 20), (70000, 2), (3000, 5)])
 def test_selection_and_moments_bitexact(eng, N, d):
     rng = np.random.default_rng(N + d)

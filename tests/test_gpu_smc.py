@@ -117,6 +117,52 @@ def test_full_run_an_schorfheide(golden):
     assert abs(np.average(P[:, 16], weights=P[:, -1]) - np.average(ref[:, 16], weights=ref[:, -1])) < 5.0
 
 
+def test_bridge_with_prior_mixing(golden):
+    """test/smc.jl:92-143 as written there: first vintage with 1000 particles, second run with 5000 particles and
+    tempered_update_prior_weight = 0.5 => the bridge branch (smc_main.jl:260-329): half of the new cloud is resampled
+    from the old one, half drawn from the prior and scored with the old likelihood."""
+    from smc_jl_b200 import smc
+    g = golden("linear_model_rows.npz")
+    data, X = g["data"], g["X"]
+    params = W.three_equation_parameters()
+    old = M.LinearEquationsLogLik(data[:, :50], X)
+    c1, _, _ = smc(old, params, data[:, :50], verbose="none", testing=True, n_parts=1000, n_Φ=100, n_mh_steps=3, n_blocks=3,
+                   α=0.9, resampling_method="multinomial", seed=11)
+    c2, w, Wm = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=5000, n_Φ=100,
+                    n_mh_steps=3, n_blocks=3, α=0.9, resampling_method="multinomial", old_data=data[:, :50], old_cloud=c1,
+                    old_loglikelihood=old, tempered_update_prior_weight=0.5, seed=12)
+    truth = np.array([1, 1, 1, 2, 2, 1, 3, 3, 1], dtype=float)
+    assert len(c2) == 5000 and c2.ESS[0] == 5000.0 and np.all(Wm[:, 0] == 1.0)
+    assert np.all(np.abs(wmean(c2) - truth) < 0.5)                          # test/smc.jl:136-140
+    assert np.all(np.abs(wmean(c2) - ols_truth(data, X)) < 0.2)
+    assert np.all(np.isfinite(c2.particles[:, 9])) and np.all(np.isfinite(c2.particles[:, 11]))
+    # n_parts alone differing (prior weight 0) also goes through the bridge: every particle comes from the old cloud
+    c3, _, _ = smc(M.LinearEquationsLogLik(data, X), params, data, verbose="none", testing=True, n_parts=2048, n_Φ=50,
+                   n_mh_steps=2, n_blocks=3, α=0.9, old_data=data[:, :50], old_cloud=c1, old_loglikelihood=old, seed=13)
+    assert len(c3) == 2048 and np.all(np.abs(wmean(c3) - truth) < 0.5)
+
+
+def test_checkpoint_and_resume_is_bit_exact(tmp_path):
+    """save_intermediate / continue_intermediate (smc_main.jl:334-361,499-507): a run resumed from the stage-10
+    checkpoint ends in exactly the cloud, ESS history and weight history of the uninterrupted run."""
+    from smc_jl_b200 import smc
+    from smc_jl_b200.driver import load_cloud
+    params, lk, _ = W.linear_gaussian(d=8, T=64, prior_sd=2.0)
+    kw = dict(verbose="none", n_parts=3000, n_Φ=25, n_mh_steps=2, n_blocks=2, α=0.9, seed=21)
+    base = str(tmp_path / "run.npz")
+    full, w_full, W_full = smc(lk, params, None, savepath=base, particle_store_path=str(tmp_path / "p.npz"),
+                               save_intermediate=True, intermediate_stage_increment=10, **kw)
+    ck = str(tmp_path / "run_stage=10.npz")
+    cloud10, w10, W10, j10 = load_cloud(ck)
+    assert cloud10.stage_index == 10 and w10.shape == (3000, 10) and len(cloud10.ESS) == 10
+    res, w_res, W_res = smc(lk, params, None, testing=True, continue_intermediate=True, loadpath=ck, **kw)
+    assert np.array_equal(res.particles, full.particles)
+    assert np.array_equal(res.ESS, full.ESS) and res.resamples == full.resamples and res.c == full.c
+    assert np.array_equal(w_res, w_full) and np.array_equal(W_res, W_full)
+    saved, w_s, W_s, _ = load_cloud(base)
+    assert np.array_equal(saved.particles, full.particles) and np.array_equal(W_s, W_full)
+
+
 def test_errors_mirror_the_reference():
     from smc_jl_b200 import smc
     params, lk, _ = W.regression_example()
