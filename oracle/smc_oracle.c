@@ -431,9 +431,10 @@ ORC_API double orc_compute_ess(const double *loglh, const double *w, const doubl
         double inc = orc_exp((phi_n1 - phi_n) * old[i] + (phi_n - phi_n1) * loglh[i]);
         tmp[i] = w[i] * inc;
     }
-    double S = orc_canon_sum(tmp, N), n = (double)N;
-    for (i64 i = 0; i < N; ++i) tmp[i] = (n * tmp[i]) / S;
-    return (n * n) / orc_canon_sumsq(tmp, N);
+    /* ESS = N^2 / sum (N x_i / S)^2 with S = sum x_i: N cancels, so the trial-phi evaluations of the adaptive
+     * solve use the one-pass form S^2 / sum x_i^2 (orc_correct keeps the reference's normalise-then-square order) */
+    double S = orc_canon_sum(tmp, N);
+    return (S * S) / orc_canon_sumsq(tmp, N);
 }
 
 /* solve_adaptive_phi (src/helpers.jl:9-56).  j is the 1-based schedule cursor as in the reference.

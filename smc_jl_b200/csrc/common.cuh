@@ -26,8 +26,10 @@ constexpr int EQMAX = 8;
 // device scalar slots (ctx->scal)
 enum { SC_S = 0, SC_Q = 1, SC_S2 = 2, SC_SRES = 3, SC_ACC = 4, SC_COUNT = 16 };
 
+constexpr int ESS_K = 15;   // trial phi per pass of the adaptive-phi solve: the 15 nodes of a depth-4 bisection tree
 struct PhiState {           // adaptive-phi state machine, lives in device memory
     double lo, hi, phi_prop, ess_bar, phi_cur, phi_n1, phi_n, g_last;
+    double trial[ESS_K];    // phase 0: phi_prop followed by the next schedule points; phase 1: bisection-tree nodes (heap order)
     long long j;
     int phase;              // 0 walk schedule, 1 bisect
     int done;
@@ -112,6 +114,8 @@ struct Ctx {
     unsigned* counters = nullptr;  // last-block counters
     double* scal = nullptr;        // SC_COUNT device scalars
     double* h_scal = nullptr;      // pinned mirror
+    double* ess_partials = nullptr;  // [2 * ESS_K][P_w] tile partials of the multi-trial ESS pass
+    double* ess_sq = nullptr;        // [2 * ESS_K] S_k then Q_k
     PhiState* phi_state = nullptr;
     PhiState* h_phi_state = nullptr;
     double* sched_dev = nullptr; int sched_cap = 0;

@@ -64,7 +64,8 @@ NcclApi* nccl_api()
         }                                                                                          \
     } while (0)
 
-constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601, SL_COUNT = 640;   // slots of scal_loc
+constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601, SL_ESS = 604, SL_COUNT = 640;   // slots of scal_loc
+static_assert(SL_ESS + 2 * ESS_K <= SL_COUNT, "scal_loc too small");
 // where a kernel should write shard-local roots, and the cross-rank tree that follows
 inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
 int reduce_ranks(Ctx* c, double* final_dst, const double* local_src, int nq)
@@ -80,7 +81,7 @@ int reduce_ranks(Ctx* c, double* final_dst, const double* local_src, int nq)
 void free_cloud(Ctx* c)
 {
     cudaFree(c->cloud[0]); cudaFree(c->cloud[1]); cudaFree(c->tmp); cudaFree(c->rmax); cudaFree(c->idx);
-    cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
+    cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->ess_partials); c->ess_partials = nullptr; cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
     cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
     for (int b = 0; b < 2; ++b)
         for (int r = 0; r < 16; ++r)
@@ -127,26 +128,18 @@ int launch_correct(Ctx* c, double phi_n1, double phi_n, double pw, double lpod, 
     return SMCB200_OK;
 }
 
-// one evaluation of compute_ESS at a trial phi (host value or the device state machine's current trial)
-int launch_ess_eval(Ctx* c, const CorrArgs& a, PhiState* st_dev, const double* sched_dev)
+// one multi-trial pass of compute_ESS: S_k, Q_k for the ESS_K trial phi in `trials` (device) -> c->ess_sq
+int launch_ess_multi(Ctx* c, double phi_n1, const double* trials_dev, const int* done_dev)
 {
     const int d = c->d;
     double* cl = c->cloud[c->cur];
     const Tiles t = weight_tiles(c->N);
-    const double n = (double)c->N_global;
-    double* lo = local_out(c);
-    k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4),
-                                                 c->tmp, nullptr, c->N, a, st_dev, c->partials, t.ntiles, t.P, c->counters, lo);
-    int st = reduce_ranks(c, c->scal + SC_S, lo + SC_S, 1); if (st) return st;
-    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(c->tmp, nullptr, c->N, n, 0, st_dev, sched_dev, c->partials, t.ntiles, t.P,
-                                                 c->counters, c->scal, lo, c->world > 1 ? 1 : 0);
-    st = reduce_ranks(c, c->scal + SC_Q, lo + SC_Q, 2); if (st) return st;
+    k_ess_multi<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4), c->N,
+                                                 phi_n1, trials_dev, done_dev, c->ess_partials, t.P);
+    k_tree_finalize<<<2 * ESS_K, 256, 0, c->stream>>>(c->ess_partials, t.ntiles, t.P, c->world > 1 ? c->scal_loc + SL_ESS : c->ess_sq);
     c->launches += 2;
-    if (st_dev && c->world > 1) {
-        k_phi_step<<<1, 32, 0, c->stream>>>(st_dev, sched_dev, c->scal, n);
-        c->launches += 1;
-    }
-    return SMCB200_OK;
+    SMC_CUDA(c, cudaGetLastError());
+    return reduce_ranks(c, c->ess_sq, c->scal_loc + SL_ESS, 2 * ESS_K);
 }
 
 // ---- resampling on explicit buffers -----------------------------------------------------------------
@@ -432,6 +425,7 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&c->counters, sizeof(unsigned) * 16) == cudaSuccess;
     ok = ok && cudaMemset(c->counters, 0, sizeof(unsigned) * 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->ess_sq, sizeof(double) * 2 * ESS_K) == cudaSuccess;
     ok = ok && cudaMalloc(&c->scal, sizeof(double) * SC_COUNT) == cudaSuccess;
     ok = ok && cudaMemset(c->scal, 0, sizeof(double) * SC_COUNT) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * SC_COUNT) == cudaSuccess;
@@ -467,7 +461,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFree(c->counters); cudaFree(c->scal); cudaFreeHost(c->h_scal); cudaFree(c->phi_state); cudaFreeHost(c->h_phi_state);
     cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
-    cudaFree(c->as_data[0]); cudaFree(c->as_data[1]);
+    cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -542,6 +536,8 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMemset(c->partials, 0, sizeof(double) * len));
     SMC_CUDA(c, cudaMalloc(&c->mpartials, sizeof(double) * lm));
     SMC_CUDA(c, cudaMemset(c->mpartials, 0, sizeof(double) * lm));
+    SMC_CUDA(c, cudaMalloc(&c->ess_partials, sizeof(double) * 2 * ESS_K * (size_t)tw.P));
+    SMC_CUDA(c, cudaMemset(c->ess_partials, 0, sizeof(double) * 2 * ESS_K * (size_t)tw.P));
     SMC_CUDA(c, cudaMalloc(&c->msum, sizeof(double) * (1 + DMAX)));
     SMC_CUDA(c, cudaMalloc(&c->csum, sizeof(double) * PACKMAX));
     SMC_CUDA(c, cudaMemset(c->cloud[0], 0, sizeof(double) * cols * c->N));
@@ -784,13 +780,16 @@ int32_t smcb200_ess_at(smcb200_ctx* c, const double* phi, int32_t K, double phi_
     int st = check_ready(c, false); if (st) return st;
     if (K < 0 || (K > 0 && (!phi || !ess_out))) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad phi vector");
     cudaSetDevice(c->device);
-    const double n = (double)c->N_global;
-    for (int k = 0; k < K; ++k) {
-        CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = phi[k]; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
-        st = launch_ess_eval(c, a, nullptr, nullptr); if (st) return st;
-        SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    for (int k0 = 0; k0 < K; k0 += ESS_K) {
+        double tr[ESS_K];
+        for (int k = 0; k < ESS_K; ++k) tr[k] = phi[(k0 + k < K) ? k0 + k : K - 1];
+        // the trial vector travels through the state block's trial[] array
+        SMC_CUDA(c, cudaMemcpyAsync(c->phi_state->trial, tr, sizeof(tr), cudaMemcpyHostToDevice, c->stream));
+        st = launch_ess_multi(c, phi_n1, c->phi_state->trial, nullptr); if (st) return st;
+        double sq[2 * ESS_K];
+        SMC_CUDA(c, cudaMemcpyAsync(sq, c->ess_sq, sizeof(sq), cudaMemcpyDeviceToHost, c->stream));
         st = sync(c); if (st) return st;
-        ess_out[k] = (n * n) / c->h_scal[SC_Q];
+        for (int k = 0; k < ESS_K && k0 + k < K; ++k) ess_out[k0 + k] = (sq[k] * sq[k]) / sq[ESS_K + k];
     }
     return SMCB200_OK;
 }
@@ -812,13 +811,20 @@ int32_t smcb200_solve_adaptive_phi(smcb200_ctx* c, const double* sched, int32_t 
     const double n = (double)c->N_global;
     h->ess_bar = resampled_last ? tempering_target * n : tempering_target * ess_prev;   // helpers.jl:14-20
     h->phi_prop = *phi_prop_io; h->phi_cur = *phi_prop_io; h->phi_n1 = phi_n1; h->j = *j_io; h->n_phi = n_phi;
+    h->trial[0] = h->phi_prop;                               // phase 0 trials: phi_prop, then the next schedule points
+    for (int k = 1; k < ESS_K; ++k) {
+        long long idx = h->j - 1 + (k - 1);
+        if (idx > n_phi - 1) idx = n_phi - 1;
+        h->trial[k] = sched[idx];
+    }
     SMC_CUDA(c, cudaMemcpyAsync(c->phi_state, h, sizeof(PhiState), cudaMemcpyHostToDevice, c->stream));
-    CorrArgs a; a.phi_n1 = phi_n1; a.phi_n = 0.0; a.pw = 0.0; a.lpod = 0.0; a.log_1m_pw = 0.0; a.mode = 0;
-    // every evaluation of g() = two kernels; the bracket walk and the bisection advance on the device, the host
-    // only polls the `done` flag between batches
+    // every pass evaluates g() at ESS_K trial phi (one sweep over three columns) and advances the schedule walk /
+    // four bisection levels on the device; the host only polls the `done` flag between batches of passes
     for (int round = 0; round < 64; ++round) {
-        for (int e = 0; e < 72; ++e) {
-            st = launch_ess_eval(c, a, c->phi_state, c->sched_dev); if (st) return st;
+        for (int e = 0; e < (round == 0 ? 15 : 4); ++e) {     // 1 schedule-walk pass + ceil(53 / 4) bisection passes is the usual total
+            st = launch_ess_multi(c, phi_n1, c->phi_state->trial, &c->phi_state->done); if (st) return st;
+            k_phi_step_multi<<<1, 32, 0, c->stream>>>(c->phi_state, c->sched_dev, c->ess_sq);
+            c->launches += 1;
         }
         SMC_CUDA(c, cudaGetLastError());
         SMC_CUDA(c, cudaMemcpyAsync(h, c->phi_state, sizeof(PhiState), cudaMemcpyDeviceToHost, c->stream));

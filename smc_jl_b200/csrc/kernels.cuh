@@ -217,6 +217,123 @@ __global__ void k_phi_step(PhiState* st, const double* __restrict__ sched, const
     if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) phi_transition(st, sched, (n_parts * n_parts) / scal[SC_Q]);
 }
 
+// -------------------------------------------------------------------------------------------------
+// K2: compute_ESS (src/helpers.jl:173-181) at ESS_K trial phi in ONE pass over the three columns.
+// ESS(phi) = N^2 / sum (N x_i / S)^2 with x_i = w_i inc_i(phi), S = sum x_i -- N cancels, so one pass gives
+// S_k = sum x and Q_k = sum x^2 for every trial and ESS_k = S_k^2 / Q_k (the correction step itself keeps the
+// reference's normalise-then-square order).  Quantity q < K is S_q, q >= K is Q_{q-K}; each follows the canonical
+// weight-sum order (4 elements per lane, 256-lane tree here, tile tree in k_tree_finalize).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ess_multi(const double* __restrict__ ll, const double* __restrict__ old, const double* __restrict__ w, int64_t N,
+            double phi_n1, const double* __restrict__ trials, const int* __restrict__ done_flag,
+            double* __restrict__ partials, int P)
+{
+    __shared__ double sm[2 * ESS_K][8];
+    if (done_flag && *done_flag) return;
+    double phi[ESS_K];
+#pragma unroll
+    for (int k = 0; k < ESS_K; ++k) phi[k] = trials[k];
+    double aS[ESS_K], aQ[ESS_K];
+#pragma unroll
+    for (int k = 0; k < ESS_K; ++k) { aS[k] = 0.0; aQ[k] = 0.0; }
+    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < W_R; ++r) {
+        const int64_t i = base + (int64_t)r * W_LANES;
+        if (i < N) {
+            const double l = ll[i], o = old[i], wi = w[i];
+#pragma unroll
+            for (int k = 0; k < ESS_K; ++k) {
+                const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
+                aS[k] = aS[k] + x;
+                aQ[k] = aQ[k] + x * x;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ESS_K; ++k) { aS[k] = aS[k] + 0.0; aQ[k] = aQ[k] + 0.0 * 0.0; }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < ESS_K; ++k) {
+        const double s = warp_tree(aS[k]), q = warp_tree(aQ[k]);
+        if (lane == 0) { sm[k][warp] = s; sm[ESS_K + k][warp] = q; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * ESS_K) {
+        const double* v = sm[threadIdx.x];
+        partials[(size_t)threadIdx.x * P + blockIdx.x] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+}
+
+__device__ inline void phi_build_tree(PhiState* st)
+{
+    double a[ESS_K], b[ESS_K];
+    a[0] = st->lo; b[0] = st->hi;
+    for (int n = 0; n < ESS_K; ++n) {
+        const double mid = 0.5 * (a[n] + b[n]);
+        st->trial[n] = mid;
+        if (2 * n + 2 < ESS_K) { a[2 * n + 1] = a[n]; b[2 * n + 1] = mid; a[2 * n + 2] = mid; b[2 * n + 2] = b[n]; }
+    }
+}
+__device__ inline void phi_fill_walk(PhiState* st, const double* sched)
+{
+    st->trial[0] = st->phi_prop;
+    for (int k = 1; k < ESS_K; ++k) {
+        long long idx = st->j - 1 + (k - 1);
+        if (idx > st->n_phi - 1) idx = st->n_phi - 1;
+        st->trial[k] = sched[idx];
+    }
+}
+// Transition of solve_adaptive_phi (src/helpers.jl:26-54) over one multi-trial pass: consumes as many of the ESS_K
+// evaluations as the sequential algorithm would have made (the schedule walk, then up to 4 bisection levels), i.e. the
+// result is the one of the one-evaluation-at-a-time loop, bit for bit.  One thread.
+__global__ void k_phi_step_multi(PhiState* st, const double* __restrict__ sched, const double* __restrict__ sq)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+    bool finish = false;
+    if (st->phase == 0) {
+        int k = 0;
+        double g;
+        for (;;) {
+            g = (sq[k] * sq[k]) / sq[ESS_K + k] - st->ess_bar;
+            st->evals += 1; st->g_last = g;
+            if (g >= 0.0 && st->j <= st->n_phi) {
+                st->phi_prop = sched[st->j - 1];
+                st->j += 1;
+                st->phi_cur = st->phi_prop;
+                if (++k == ESS_K) { phi_fill_walk(st, sched); return; }     // more schedule points next pass
+                continue;
+            }
+            break;
+        }
+        if (st->phi_prop != 1.0 || g < 0.0) {
+            st->lo = st->phi_n1; st->hi = st->phi_prop; st->phase = 1;
+        } else {
+            st->phi_n = 1.0; st->done = 1;
+            return;
+        }
+    } else {
+        int node = 0;
+        for (int level = 0; level < 4 && !finish; ++level) {
+            const double mid = 0.5 * (st->lo + st->hi);
+            if (!(mid > st->lo && mid < st->hi)) { finish = true; break; }
+            const double g = (sq[node] * sq[node]) / sq[ESS_K + node] - st->ess_bar;
+            st->evals += 1; st->g_last = g;
+            if (g == 0.0) { st->lo = mid; finish = true; }
+            else if (g > 0.0) { st->lo = mid; node = 2 * node + 2; }      // continue in (mid, hi): right child
+            else { st->hi = mid; node = 2 * node + 1; }                   // continue in (lo, mid): left child
+        }
+    }
+    if (!finish) {
+        const double mid = 0.5 * (st->lo + st->hi);
+        if (mid > st->lo && mid < st->hi) { st->phi_cur = mid; phi_build_tree(st); return; }
+    }
+    st->phi_n = (st->lo == st->phi_n1) ? st->hi : st->lo;
+    st->done = 1;
+}
+
 // canonical sum of one column (optionally divided by a constant first): out = sum_i x_i / div
 __global__ void __launch_bounds__(256)
 k_colsum(const double* __restrict__ x, int64_t N, double div, int use_div, double* partials, int ntiles, int P,
