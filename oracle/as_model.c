@@ -19,8 +19,8 @@
  *   2. State (y, pi, R, y_lag, g, z) -- the reference's 8-state vector without the two expectation states,
  *      which neither feed back nor are observed.  Stationary covariance in closed form.
  *   3. Kalman filter over all periods; the first `npre` (presample) periods are filtered but not scored.
- *      The 3x3 innovation covariance is factored by Cholesky; the covariance update is P - G G',
- *      G = P Z' L^{-T}.
+ *      The 3x3 innovation covariance is factored as L D L' (no square roots); the covariance update is
+ *      P - H D^{-1} H', H = P Z' L^{-T}.
  * Every product/sum below is written in a fixed order with explicit fma (the device kernel
  * smc_jl_b200/csrc/aslik.cuh was written independently against this same description).
  */
@@ -172,6 +172,7 @@ ORC_API double orc_as_loglik(const double *th, const double *data, int T, int np
     const double E0 = ey * ey, E1 = epi * epi, E2 = eR * eR;
     double x[NS] = {0, 0, 0, 0, 0, 0};
     double ll = 0.0;
+    int bad = 0;
     for (int t = 0; t < T; ++t) {
         /* predict */
         double xn[NS], TP[NS][NS], Pn[NS][NS];
@@ -208,34 +209,39 @@ ORC_API double orc_as_loglik(const double *th, const double *data, int T, int np
         const double n0 = (yt[0] - ((xn[SY] - xn[SYL]) + xn[SZ])) - D0;
         const double n1 = (yt[1] - 4.0 * xn[SPI]) - D1;
         const double n2 = (yt[2] - 4.0 * xn[SR]) - D2;
-        /* Cholesky of F (reciprocal diagonals) */
-        const double l00 = sqrt(F00), i00 = 1.0 / l00;
-        const double l10 = F10 * i00, l20 = F20 * i00;
-        const double l11 = sqrt(FMA(-l10, l10, F11)), i11 = 1.0 / l11;
-        const double l21 = FMA(-l20, l10, F21) * i11;
-        const double l22 = sqrt(FMA(-l21, l21, FMA(-l20, l20, F22))), i22 = 1.0 / l22;
-        const double w0 = n0 * i00;
-        const double w1 = FMA(-l10, w0, n1) * i11;
-        const double w2 = FMA(-l21, w1, FMA(-l20, w0, n2)) * i22;
+        /* F = L D L' (unit lower L, no square roots): d_k > 0 <=> F positive definite */
+        const double d0 = F00, r0 = 1.0 / d0;
+        const double l10 = F10 * r0, l20 = F20 * r0;
+        const double d1 = FMA(-l10, F10, F11), r1 = 1.0 / d1;
+        const double t21 = FMA(-l20, F10, F21);
+        const double l21 = t21 * r1;
+        const double d2 = FMA(-l21, t21, FMA(-l20, F20, F22)), r2 = 1.0 / d2;
+        if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) bad = 1;
+        const double w0 = n0;
+        const double w1 = FMA(-l10, w0, n1);
+        const double w2 = FMA(-l21, w1, FMA(-l20, w0, n2));
+        const double v0 = w0 * r0, v1 = w1 * r1, v2 = w2 * r2;
         if (t >= npre) {
-            const double logdet = 2.0 * orc_log((l00 * l11) * l22);
-            const double quad = FMA(w2, w2, FMA(w1, w1, w0 * w0));
+            const double logdet = orc_log((d0 * d1) * d2);
+            const double quad = FMA(w2, v2, FMA(w1, v1, w0 * v0));
             ll = ll + -0.5 * ((3.0 * 1.8378770664093453 + logdet) + quad);
         }
-        /* update: G = PZ L^{-T}; x += G w; P -= G G' */
-        double G[NS][3];
+        /* update: H = PZ L^{-T}; x += H D^{-1} w; P -= H D^{-1} H' */
+        double H[NS][3], HR[NS][3];
         for (int i = 0; i < NS; ++i) {
-            G[i][0] = PZ[i][0] * i00;
-            G[i][1] = FMA(-l10, G[i][0], PZ[i][1]) * i11;
-            G[i][2] = FMA(-l21, G[i][1], FMA(-l20, G[i][0], PZ[i][2])) * i22;
-            x[i] = FMA(G[i][2], w2, FMA(G[i][1], w1, FMA(G[i][0], w0, xn[i])));
+            H[i][0] = PZ[i][0];
+            H[i][1] = FMA(-l10, H[i][0], PZ[i][1]);
+            H[i][2] = FMA(-l21, H[i][1], FMA(-l20, H[i][0], PZ[i][2]));
+            HR[i][0] = H[i][0] * r0; HR[i][1] = H[i][1] * r1; HR[i][2] = H[i][2] * r2;
+            x[i] = FMA(H[i][2], v2, FMA(H[i][1], v1, FMA(H[i][0], v0, xn[i])));
         }
         for (int i = 0; i < NS; ++i)
             for (int j = 0; j <= i; ++j) {
-                const double w = FMA(-G[i][2], G[j][2], FMA(-G[i][1], G[j][1], FMA(-G[i][0], G[j][0], Pn[i][j])));
+                const double w = FMA(-HR[i][2], H[j][2], FMA(-HR[i][1], H[j][1], FMA(-HR[i][0], H[j][0], Pn[i][j])));
                 P[i][j] = w; P[j][i] = w;
             }
     }
+    if (bad) return -INFINITY;           /* innovation covariance not positive definite: an error in the reference => -Inf */
     if (!(ll == ll)) return -INFINITY;   /* NaN (non-PD innovation covariance etc.): an error in the reference => -Inf */
     return ll;
 }

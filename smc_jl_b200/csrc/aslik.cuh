@@ -10,8 +10,8 @@
 //   2. 6-state form (y, pi, R, y_lag, g, z): the reference's 8 states minus the two expectation states
 //      (unobserved, no feedback); stationary covariance in closed form (no Lyapunov iteration);
 //   3. Kalman filter with the transition matrix's sparsity (10 non-zeros of 36) and the selection-type
-//      measurement matrix unrolled at compile time; 3x3 innovation covariance by Cholesky; covariance
-//      update P - G G'.  About 400 FP64 instructions per period instead of ~4 500 for dense 8-state
+//      measurement matrix unrolled at compile time; 3x3 innovation covariance as L D L' (three reciprocals, no
+//      square roots); covariance update P - H D^-1 H'.  About 400 FP64 instructions per period instead of ~4 500 for dense 8-state
 //      algebra; a dense DMMA formulation would spend ~10x the flops on structural zeros, and B200's FP64
 //      tensor rate is no higher than its FP64 FMA rate, so tensor cores are deliberately not used here.
 // The operation order is fixed (explicit fma) and mirrored by the oracle (oracle/as_model.c).
@@ -166,6 +166,7 @@ __device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th
     const int T = c_as[slot].T, npre = c_as[slot].npre;
     double x[NS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double ll = 0.0;
+    bool bad = false;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         const double y0 = __ldg(data + 3 * t), y1 = __ldg(data + 3 * t + 1), y2 = __ldg(data + 3 * t + 2);
@@ -212,33 +213,40 @@ __device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th
         const double n0 = (y0 - ((xn[SY] - xn[SYL]) + xn[SZ])) - D0;
         const double n1 = (y1 - 4.0 * xn[SPI]) - D1;
         const double n2 = (y2 - 4.0 * xn[SR]) - D2;
-        const double l00 = sqrt(F00), i00 = 1.0 / l00;
-        const double l10 = F10 * i00, l20 = F20 * i00;
-        const double l11 = sqrt(fma(-l10, l10, F11)), i11 = 1.0 / l11;
-        const double l21 = fma(-l20, l10, F21) * i11;
-        const double l22 = sqrt(fma(-l21, l21, fma(-l20, l20, F22))), i22 = 1.0 / l22;
-        const double w0 = n0 * i00;
-        const double w1 = fma(-l10, w0, n1) * i11;
-        const double w2 = fma(-l21, w1, fma(-l20, w0, n2)) * i22;
+        // F = L D L' (unit lower L): three reciprocals, no square roots; d_k > 0 <=> F positive definite
+        const double d0 = F00, r0 = 1.0 / d0;
+        const double l10 = F10 * r0, l20 = F20 * r0;
+        const double d1 = fma(-l10, F10, F11), r1 = 1.0 / d1;
+        const double t21 = fma(-l20, F10, F21);
+        const double l21 = t21 * r1;
+        const double d2 = fma(-l21, t21, fma(-l20, F20, F22)), r2 = 1.0 / d2;
+        if (!(d0 > 0.0 && d1 > 0.0 && d2 > 0.0)) bad = true;
+        const double w0 = n0;
+        const double w1 = fma(-l10, w0, n1);
+        const double w2 = fma(-l21, w1, fma(-l20, w0, n2));
+        const double v0 = w0 * r0, v1 = w1 * r1, v2 = w2 * r2;
         if (t >= npre) {
-            const double logdet = 2.0 * det_log((l00 * l11) * l22);
-            const double quad = fma(w2, w2, fma(w1, w1, w0 * w0));
+            const double logdet = det_log((d0 * d1) * d2);
+            const double quad = fma(w2, v2, fma(w1, v1, w0 * v0));
             ll = ll + -0.5 * ((3.0 * 1.8378770664093453 + logdet) + quad);
         }
-        double G[NS][3];
+        // update: H = PZ L^{-T}; x += H D^{-1} w; P -= H D^{-1} H'
+        double H[NS][3], HR[NS][3];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            G[i][0] = PZ[i][0] * i00;
-            G[i][1] = fma(-l10, G[i][0], PZ[i][1]) * i11;
-            G[i][2] = fma(-l21, G[i][1], fma(-l20, G[i][0], PZ[i][2])) * i22;
-            x[i] = fma(G[i][2], w2, fma(G[i][1], w1, fma(G[i][0], w0, xn[i])));
+            H[i][0] = PZ[i][0];
+            H[i][1] = fma(-l10, H[i][0], PZ[i][1]);
+            H[i][2] = fma(-l21, H[i][1], fma(-l20, H[i][0], PZ[i][2]));
+            HR[i][0] = H[i][0] * r0; HR[i][1] = H[i][1] * r1; HR[i][2] = H[i][2] * r2;
+            x[i] = fma(H[i][2], v2, fma(H[i][1], v1, fma(H[i][0], v0, xn[i])));
         }
 #pragma unroll
         for (int i = 0; i < NS; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j)
-                P[lo(i, j)] = fma(-G[i][2], G[j][2], fma(-G[i][1], G[j][1], fma(-G[i][0], G[j][0], Pn[lo(i, j)])));
+                P[lo(i, j)] = fma(-HR[i][2], H[j][2], fma(-HR[i][1], H[j][1], fma(-HR[i][0], H[j][0], Pn[lo(i, j)])));
     }
+    if (bad) return -dinf();
     if (!(ll == ll)) return -dinf();
     return ll;
 }
@@ -247,7 +255,7 @@ struct ASLik {
     static constexpr int KIND = SMCB200_LIK_AS_DSGE;
     static constexpr int NEQ = 0, K = 0, STRIDE = 0, COEF = 0, SIG = -1;
     static constexpr int D = 16;
-    static constexpr int MINB = 2;     // resident blocks of 128 threads asked of ptxas (the filter wants ~250 registers)
+    static constexpr int MINB = 4;     // resident blocks of 128 threads: 128 registers + ~130 B of L1-resident spills beat 2 blocks x 214 registers (measured 6.4 vs 7.6 ms)
     template <int SLOT>
     static __device__ __forceinline__ double ll(const double (&th)[D]) { return as_loglik(SLOT, th); }
 };
