@@ -22,6 +22,7 @@ constexpr int DMAX = 32;               // max n_para with a device mutation kern
 constexpr int NBMAX = 8;               // max n_blocks
 constexpr int PACKMAX = DMAX * (DMAX + 1) / 2;
 constexpr int EQMAX = 8;
+constexpr int MB_NQ = 640;             // doubles per rank and mailbox slot (>= PACKMAX + DMAX + 1)
 
 // device scalar slots (ctx->scal)
 enum { SC_S = 0, SC_Q = 1, SC_S2 = 2, SC_SRES = 3, SC_ACC = 4, SC_COUNT = 16 };
@@ -98,6 +99,13 @@ struct Ctx {
     double* gath = nullptr;        // [world][256] gathered roots
     double* rmax_g = nullptr;      // [world * per] running max of the global cumsum (world > 1)
     double* bmax_g = nullptr;      // [world * nb_local]
+    // small-reduction mailboxes: every rank owns an inbox [2 parities][world][MB_NQ] doubles + [2][world] epoch flags that
+    // its peers write directly over NVLink (CUDA IPC mappings); see k_peer_exchange
+    double* mbox = nullptr;
+    double** mbox_tab = nullptr;   // device table [world]: every rank's inbox
+    void* mbox_open[16] = {};      // opened peer mappings (host)
+    unsigned long long mb_epoch = 0;
+    int* mb_err = nullptr;         // device flag: a peer never showed up (time-out)
     double** peer_tab = nullptr;   // device table [2][world] of peers' cloud buffers (CUDA IPC)
     int64_t* peer_cnt = nullptr;   // device [world] particles held by each rank
     void* ipc_open[2][16] = {};    // opened peer mappings (host)

@@ -68,14 +68,20 @@ constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601,
 static_assert(SL_ESS + 2 * ESS_K <= SL_COUNT, "scal_loc too small");
 // where a kernel should write shard-local roots, and the cross-rank tree that follows
 inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
-int reduce_ranks(Ctx* c, double* final_dst, const double* local_src, int nq)
+// cross-rank tree of nq shard-local roots (combine) or their [world][nq] layout (gather into c->gath): one
+// k_peer_exchange launch over the NVLink mailboxes
+int peer_exchange(Ctx* c, double* dst, const double* local_src, int nq, int combine)
 {
-    if (c->world == 1) return SMCB200_OK;
-    SMC_NCCL(c, nccl_api()->AllGather(local_src, c->gath, (size_t)nq, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
-    k_combine_ranks<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->gath, c->world, nq, final_dst);
+    if (nq > MB_NQ) { c->err = "peer_exchange: too many quantities"; return SMCB200_ERR_BAD_ARGUMENT; }
+    k_peer_exchange<<<1, 256, 0, c->stream>>>(local_src, nq, c->rank, c->world, c->mbox_tab, ++c->mb_epoch, combine, dst, c->mb_err);
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
+}
+int reduce_ranks(Ctx* c, double* final_dst, const double* local_src, int nq)
+{
+    if (c->world == 1) return SMCB200_OK;
+    return peer_exchange(c, final_dst, local_src, nq, 1);
 }
 
 void free_cloud(Ctx* c)
@@ -118,10 +124,10 @@ int launch_correct(Ctx* c, double phi_n1, double phi_n, double pw, double lpod, 
     double* w = cl + col_off(c->N, d + 4);
     double* lo = local_out(c);
     k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), w, w, inc_dev, c->N, a,
-                                                 nullptr, c->partials, t.ntiles, t.P, c->counters, lo);
+                                                 c->partials, t.ntiles, t.P, c->counters, lo);
     int st = reduce_ranks(c, c->scal + SC_S, lo + SC_S, 1); if (st) return st;
-    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(w, normw_dev, c->N, (double)c->N_global, 1, nullptr, nullptr,
-                                                 c->partials, t.ntiles, t.P, c->counters, c->scal, lo, 0);
+    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(w, normw_dev, c->N, (double)c->N_global, 1,
+                                                 c->partials, t.ntiles, t.P, c->counters, c->scal, lo);
     st = reduce_ranks(c, c->scal + SC_Q, lo + SC_Q, 2); if (st) return st;
     c->launches += 2;
     SMC_CUDA(c, cudaGetLastError());
@@ -224,7 +230,7 @@ int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t st
     k_scan<false><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, c->scan_blocktot, nullptr,
                                                             nullptr, nullptr, nullptr);
     k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT);
-    SMC_NCCL(c, nc->AllGather(c->scal_loc + SL_SCAN_ROOT, c->gath, 1, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_ROOT, 1, 0); if (st) return st;
     k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, nb, c->gath, c->world, c->rank, c->scan_blockoff);
     double* rloc = c->rmax_g + (size_t)c->rank * c->per;
     double* bloc = c->bmax_g + (size_t)c->rank * nb;
@@ -233,7 +239,7 @@ int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t st
     k_prefix_max<<<1, 256, 0, c->stream>>>(bloc, nb);
     // shard maxima -> carry of the lower ranks, then every rank gets the global running max + block maxima
     SMC_CUDA(c, cudaMemcpyAsync(c->scal_loc + SL_SCAN_MAX, bloc + nb - 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    SMC_NCCL(c, nc->AllGather(c->scal_loc + SL_SCAN_MAX, c->gath, 1, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+    st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_MAX, 1, 0); if (st) return st;
     k_apply_rank_carry<<<1, 256, 0, c->stream>>>(bloc, nb, c->gath, c->rank);
     SMC_NCCL(c, nc->AllGather(bloc, c->bmax_g, (size_t)nb, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
     SMC_NCCL(c, nc->AllGather(rloc, c->rmax_g, (size_t)c->per, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
@@ -438,7 +444,8 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     ok = ok && cudaMallocHost(&c->mutc_host, sizeof(MutConst)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->status_dev, sizeof(int)) == cudaSuccess;
     ok = ok && cudaMemset(c->status_dev, 0, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&c->h_status, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_status, 2 * sizeof(int)) == cudaSuccess;
+    if (ok) c->h_status[1] = 0;
     ok = ok && cudaMallocHost(&c->h_moments, sizeof(double) * (1 + DMAX + PACKMAX)) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&c->tev[i]) == cudaSuccess;
@@ -462,6 +469,8 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFree(c->mutc_dev); cudaFreeHost(c->mutc_host); cudaFree(c->status_dev); cudaFreeHost(c->h_status);
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
+    for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -575,6 +584,34 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
         SMC_CUDA(c, cudaMalloc(&c->peer_cnt, sizeof(int64_t) * W));
         SMC_CUDA(c, cudaMemcpy(c->peer_tab, tab.data(), sizeof(double*) * 2 * W, cudaMemcpyHostToDevice));
         SMC_CUDA(c, cudaMemcpy(c->peer_cnt, cnt.data(), sizeof(int64_t) * W, cudaMemcpyHostToDevice));
+        // reduction mailboxes (allocated once per context, zeroed: epoch 0 = nothing published)
+        if (!c->mbox) {
+            const size_t bytes = sizeof(double) * 2 * W * MB_NQ + sizeof(unsigned long long) * 2 * W;
+            SMC_CUDA(c, cudaMalloc(&c->mbox, bytes));
+            SMC_CUDA(c, cudaMemset(c->mbox, 0, bytes));
+            SMC_CUDA(c, cudaMalloc(&c->mb_err, sizeof(int)));
+            SMC_CUDA(c, cudaMemset(c->mb_err, 0, sizeof(int)));
+            cudaIpcMemHandle_t mh, *mh_all_dev = nullptr, *mh_dev = nullptr;
+            std::vector<cudaIpcMemHandle_t> mh_all(W);
+            SMC_CUDA(c, cudaIpcGetMemHandle(&mh, c->mbox));
+            SMC_CUDA(c, cudaMalloc(&mh_all_dev, sizeof(mh) * W));
+            SMC_CUDA(c, cudaMalloc(&mh_dev, sizeof(mh)));
+            SMC_CUDA(c, cudaMemcpyAsync(mh_dev, &mh, sizeof(mh), cudaMemcpyHostToDevice, c->stream));
+            SMC_NCCL(c, nc->AllGather(mh_dev, mh_all_dev, sizeof(mh), ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
+            SMC_CUDA(c, cudaMemcpyAsync(mh_all.data(), mh_all_dev, sizeof(mh) * W, cudaMemcpyDeviceToHost, c->stream));
+            SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(mh_all_dev); cudaFree(mh_dev);
+            std::vector<double*> mt(W);
+            for (int r = 0; r < W; ++r) {
+                if (r == c->rank) { mt[r] = c->mbox; continue; }
+                void* p = nullptr;
+                SMC_CUDA(c, cudaIpcOpenMemHandle(&p, mh_all[r], cudaIpcMemLazyEnablePeerAccess));
+                c->mbox_open[r] = p;
+                mt[r] = (double*)p;
+            }
+            SMC_CUDA(c, cudaMalloc(&c->mbox_tab, sizeof(double*) * W));
+            SMC_CUDA(c, cudaMemcpy(c->mbox_tab, mt.data(), sizeof(double*) * W, cudaMemcpyHostToDevice));
+        }
         SMC_CUDA(c, cudaMalloc(&c->rmax_g, sizeof(double) * (size_t)per * W));
         SMC_CUDA(c, cudaMalloc(&c->bmax_g, sizeof(double) * (size_t)(per / SCAN_TILE) * W));
     }
@@ -1001,7 +1038,9 @@ int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_s
     st = mean_accept(c); if (st) return st;
     SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
     SMC_CUDA(c, cudaMemcpyAsync(c->h_status, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (c->world > 1) SMC_CUDA(c, cudaMemcpyAsync(c->h_status + 1, c->mb_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     st = sync(c); if (st) return st;
+    if (c->world > 1 && c->h_status[1]) return fail(c, SMCB200_ERR_NCCL, "a peer rank never reached a cross-GPU reduction (time-out)");
     if (*c->h_status) {
         cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream);
         res->status = *c->h_status;

@@ -78,22 +78,50 @@ __device__ __forceinline__ bool finish_tiles(const double (&v)[NQ], double* part
 }
 
 // =================================================================================================
-// cross-rank combination: out[q] = adjacent-pair tree over ranks of gath[r][q] (rank order; world is a
-// power of two).  Every rank evaluates the same tree on the same gathered values => identical bits.
+// Small cross-GPU reductions without a collective library: ONE launch per reduction.  Every rank pushes its nq
+// shard-local roots straight into every peer's inbox over NVLink (plain remote stores through CUDA-IPC mappings),
+// publishes an epoch flag behind a system-scope fence, waits for the peers' flags in its own inbox and combines the
+// world x nq values in the fixed rank-order tree (combine != 0) or lays them out as [world][nq] (gather).
+// Inbox slots alternate with the epoch's parity: a rank can only reach epoch e + 1 after it has seen every peer's
+// epoch-e flag, and a peer publishes e only after it has consumed e - 1, so two slots never collide.
+// A peer that never arrives (a crashed rank) trips a clock-based time-out instead of hanging the GPU.
 // =================================================================================================
-__global__ void k_combine_ranks(const double* __restrict__ gath, int world, int nq, double* __restrict__ out)
+__global__ void __launch_bounds__(256)
+k_peer_exchange(const double* __restrict__ local_src, int nq, int rank, int world, double* const* __restrict__ inbox,
+                unsigned long long epoch, int combine, double* __restrict__ dst, int* __restrict__ err)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    double v[16];
-    for (int r = 0; r < world; ++r) v[r] = gath[(size_t)r * nq + q];
-    for (int s = 1; s < world; s <<= 1)
-        for (int i = 0; i + s < world; i += 2 * s) v[i] = v[i] + v[i + s];
-    out[q] = v[0];
+    const int par = (int)(epoch & 1ull);
+    const size_t flag_off = (size_t)2 * world * MB_NQ;               // flags follow the value slots (as doubles' worth of u64)
+    for (int r = 0; r < world; ++r) {
+        double* slot = inbox[r] + ((size_t)par * world + rank) * MB_NQ;
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) slot[q] = local_src[q];
+    }
+    __syncthreads();                     // the block's remote stores happen-before the (cumulative) fences below
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(inbox[threadIdx.x] + flag_off) + (size_t)par * world + rank;
+        *f = epoch;
+        volatile unsigned long long* g = reinterpret_cast<volatile unsigned long long*>(inbox[rank] + flag_off) + (size_t)par * world + threadIdx.x;
+        const long long t0 = clock64();
+        while (*g < epoch) {
+            if (clock64() - t0 > 20000000000ll) { *err = 1; break; }    // ~10 s at 2 GHz
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const double* mine = inbox[rank] + (size_t)par * world * MB_NQ;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        if (combine) {
+            double v[16];
+            for (int r = 0; r < world; ++r) v[r] = __ldcg(mine + (size_t)r * MB_NQ + q);
+            for (int s = 1; s < world; s <<= 1)
+                for (int i = 0; i + s < world; i += 2 * s) v[i] = v[i] + v[i + s];
+            dst[q] = v[0];
+        } else {
+            for (int r = 0; r < world; ++r) dst[(size_t)r * nq + q] = __ldcg(mine + (size_t)r * MB_NQ + q);
+        }
+    }
 }
-
-// adaptive-phi transition as its own launch (multi-GPU: it must run after the cross-rank combination)
-__global__ void k_phi_step(PhiState* st, const double* __restrict__ sched, const double* __restrict__ scal, double n_parts);
 
 // =================================================================================================
 // K1 / K2: correction and ESS  (src/smc_main.jl:400-427, src/helpers.jl:173-181)
@@ -111,20 +139,14 @@ __device__ __forceinline__ double inc_weight(double ll, double old, const CorrAr
     return det_exp((a.phi_n1 - phi_n) * inner + (phi_n - a.phi_n1) * ll);
 }
 
-// pass A: w~ = w * inc; S = canonical sum of w~.   wout = w (correction, in place) or a scratch
-// column (compute_ESS).  phi_state != nullptr: trial phi comes from the device state machine.
+// pass A: w~ = w * inc; S = canonical sum of w~ (in place on the weight column).
 __global__ void __launch_bounds__(256)
 k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const double* w,
             double* wout, double* __restrict__ inc_out, int64_t N, CorrArgs a,
-            const PhiState* __restrict__ phi_state, double* partials, int ntiles, int P, unsigned* counter,
-            double* out)
+            double* partials, int ntiles, int P, unsigned* counter, double* out)
 {
     __shared__ double sm[8];
-    double phi_n = a.phi_n;
-    if (phi_state) {
-        if (phi_state->done) return;
-        phi_n = phi_state->phi_cur;
-    }
+    const double phi_n = a.phi_n;
     const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
     double x[W_R];
 #pragma unroll
@@ -145,47 +167,12 @@ k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const
     finish_tiles<1>(v, partials, ntiles, P, counter, out + SC_S, sm);
 }
 
-// device transition of solve_adaptive_phi (src/helpers.jl:26-54); executed by one thread
-__device__ inline void phi_transition(PhiState* st, const double* sched, double ess)
-{
-    const double g = ess - st->ess_bar;
-    st->evals += 1;
-    st->g_last = g;
-    bool finish = false;
-    if (st->phase == 0) {
-        if (g >= 0.0 && st->j <= st->n_phi) {
-            st->phi_prop = sched[st->j - 1];
-            st->j += 1;
-            st->phi_cur = st->phi_prop;
-            return;
-        }
-        if (st->phi_prop != 1.0 || g < 0.0) {
-            st->lo = st->phi_n1; st->hi = st->phi_prop; st->phase = 1;
-        } else {
-            st->phi_n = 1.0; st->done = 1;
-            return;
-        }
-    } else {
-        if (g == 0.0) { st->lo = st->phi_cur; finish = true; }
-        else if (g > 0.0) st->lo = st->phi_cur;
-        else st->hi = st->phi_cur;
-    }
-    if (!finish) {
-        const double mid = 0.5 * (st->lo + st->hi);
-        if (mid > st->lo && mid < st->hi) { st->phi_cur = mid; return; }
-    }
-    st->phi_n = (st->lo == st->phi_n1) ? st->hi : st->lo;
-    st->done = 1;
-}
-
 // pass B: W = (w~ * N) / S; Q = sum W^2, S2 = sum W.  store != 0 writes W back (normalize_weights!).
 __global__ void __launch_bounds__(256)
 k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts, int store,
-            PhiState* phi_state, const double* __restrict__ sched, double* partials, int ntiles, int P,
-            unsigned* counter, double* scal, double* out, int defer_transition)
+            double* partials, int ntiles, int P, unsigned* counter, double* scal, double* out)
 {
     __shared__ double sm[8];
-    if (phi_state && phi_state->done) return;
     const double S = scal[SC_S];
     const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
     double x[W_R];
@@ -205,16 +192,7 @@ k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts
     double v[2];
     v[0] = block_tree_256(q, sm);
     v[1] = block_tree_256(s2, sm);
-    const bool last = finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, out + SC_Q, sm);
-    if (last && phi_state && !defer_transition && threadIdx.x == 0) {
-        const double ess = (n_parts * n_parts) / out[SC_Q];
-        phi_transition(phi_state, sched, ess);
-    }
-}
-
-__global__ void k_phi_step(PhiState* st, const double* __restrict__ sched, const double* __restrict__ scal, double n_parts)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) phi_transition(st, sched, (n_parts * n_parts) / scal[SC_Q]);
+    finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, out + SC_Q, sm);
 }
 
 // -------------------------------------------------------------------------------------------------
