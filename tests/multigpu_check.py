@@ -35,7 +35,7 @@ def main():
 
     cases = [("linreg20", 1 << 17, 12, dict(n_mh_steps=2, n_blocks=1, adaptive=0)),
              ("threeeq_blocks_adaptive", 65000, 16, dict(n_mh_steps=1, n_blocks=3, adaptive=1)),
-             ("an_schorfheide_mixture", 40000, 5, dict(n_mh_steps=2, n_blocks=1, adaptive=1, alpha=0.9, device_draw=True))]
+             ("an_schorfheide_mixture", 65000, 5, dict(n_mh_steps=2, n_blocks=1, adaptive=1, alpha=0.9, device_draw=True))]
     for name, N, n_stage, kw in cases:
         if name == "an_schorfheide_mixture":
             g = np.load(os.path.join(ROOT, "tests", "golden", "as_clouds.npz"))

@@ -21,6 +21,43 @@ from smc_jl_b200 import workloads as W  # noqa: E402
 from smc_jl_b200._lib import StageConfig, StageState  # noqa: E402
 from smc_jl_b200.engine import Engine  # noqa: E402
 
+# one process per GPU under torchrun: the SAME global cloud is sharded over the ranks (strong scaling)
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+dist = None
+if WORLD > 1:
+    import torch
+    import torch.distributed as dist
+    _fd1 = os.dup(1); os.dup2(2, 1)                      # NCCL prints its banner to stdout
+    torch.cuda.set_device(LOCAL)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+
+
+def make_engine():
+    eng = Engine(LOCAL)
+    if WORLD > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if RANK == 0:
+            idt.copy_(torch.frombuffer(bytearray(Engine.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(RANK, WORLD, bytes(idt.cpu().numpy().tobytes()))
+    return eng
+
+
+def max_over_ranks(x):
+    if WORLD == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def emit(obj):
+    if WORLD > 1:
+        sys.stdout.flush(); os.dup2(_fd1, 1)
+        dist.barrier(); dist.destroy_process_group()
+    if RANK == 0:
+        print(json.dumps(obj), flush=True)
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--stages", type=int, default=12)
 ap.add_argument("--n", type=int, default=1 << 18)
@@ -32,7 +69,7 @@ g = np.load(os.path.join(ROOT, "tests", "golden", "as_clouds.npz"))
 params = W.an_schorfheide_parameters()
 spec = M.make_spec(params, M.AnSchorfheideLogLik(g["data"]))
 N = args.n
-eng = Engine(0)
+eng = make_engine()
 eng.cloud_create(N, 16)
 eng.set_model(spec)
 eng.timer_start()
@@ -46,7 +83,7 @@ for s in range(args.stages):
                       n_mh_steps=args.n_mh, n_blocks=1, resample_method=0, adaptive=1, seed=1793, stage=s + 2)
     eng.timer_start()
     res, _, _ = eng.stage(cfg, state, schedule=sched)
-    ms = eng.timer_stop()
+    ms = max_over_ranks(eng.timer_stop())
     phi_prev = res.phi_n
     rows.append((ms, res.ms_correct, res.ms_resample, res.ms_moments, res.ms_mutate, res.ess, res.accept, res.phi_n))
     if phi_prev >= 1.0:
@@ -56,7 +93,8 @@ timed = rows[2:] if len(rows) > 4 else rows
 ms_stage, ms_mut = timed[:, 0].mean(), timed[:, 4].mean()
 out = {
     "workload": "C4 An-Schorfheide DSGE, device Kalman loglik (T=230), n_particles=%d, n_mh_steps=%d, 13 free parameters, "
-                "alpha=0.9, adaptive phi (tempering_target 0.97), 1 GPU" % (N, args.n_mh),
+                "alpha=0.9, adaptive phi (tempering_target 0.97), %d GPU(s), one global cloud sharded" % (N, args.n_mh, WORLD),
+    "n_gpus": WORLD,
     "stages_timed": int(len(timed)), "ms_per_stage": float(ms_stage), "ms_mutate": float(ms_mut),
     "ms_initial_draw": float(ms_init),
     "particle_mh_steps_per_sec_per_stage": float(N * args.n_mh / (ms_stage * 1e-3)),
@@ -67,7 +105,7 @@ out = {
                  "moments": float(timed[:, 3].mean()), "mutate": float(ms_mut)},
 }
 eng.close()
-if args.cpu:
+if args.cpu and RANK == 0:
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import ctypes as C
 
@@ -87,4 +125,4 @@ if args.cpu:
         t.append(time.perf_counter() - t0)
     out["cpu_oracle"] = {"particle_mh_steps_per_sec_per_stage": float(n * args.n_mh / np.mean(t[1:])), "cores": os.cpu_count(),
                          "sample": "N=2^12, 2 timed stages (oracle/, OpenMP)"}
-print(json.dumps(out))
+emit(out)

@@ -27,6 +27,43 @@ from smc_jl_b200 import workloads as W  # noqa: E402
 from smc_jl_b200._lib import StageConfig, StageState  # noqa: E402
 from smc_jl_b200.engine import Engine  # noqa: E402
 
+# one process per GPU under torchrun: the SAME global cloud is sharded over the ranks (strong scaling)
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+dist = None
+if WORLD > 1:
+    import torch
+    import torch.distributed as dist
+    _fd1 = os.dup(1); os.dup2(2, 1)                      # NCCL prints its banner to stdout
+    torch.cuda.set_device(LOCAL)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+
+
+def make_engine():
+    eng = Engine(LOCAL)
+    if WORLD > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if RANK == 0:
+            idt.copy_(torch.frombuffer(bytearray(Engine.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(RANK, WORLD, bytes(idt.cpu().numpy().tobytes()))
+    return eng
+
+
+def max_over_ranks(x):
+    if WORLD == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def emit(obj):
+    if WORLD > 1:
+        sys.stdout.flush(); os.dup2(_fd1, 1)
+        dist.barrier(); dist.destroy_process_group()
+    if RANK == 0:
+        print(json.dumps(obj), flush=True)
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c5", choices=["c3", "c5"])
 ap.add_argument("--n", type=int, default=1 << 20)
@@ -48,7 +85,7 @@ else:
     adaptive, thr, what = 0, 0.9, "C5 online update, 3-equation model (old data = 50 of 100 periods), threshold_ratio 0.9 (resample-heavy)"
 N = args.n
 sched = (np.arange(300) / 299.0) ** 2.1
-eng = Engine(0)
+eng = make_engine()
 eng.cloud_create(N, 9)
 
 
@@ -62,7 +99,7 @@ def run(spec, has_old, n_stage, ess0, timed):
         if timed:
             eng.timer_start()
         res, _, _ = eng.stage(cfg, state, schedule=sched)
-        ms = eng.timer_stop() if timed else 0.0
+        ms = max_over_ranks(eng.timer_stop()) if timed else 0.0
         rows.append((ms, res.ms_correct, res.ms_resample, res.ms_moments, res.ms_mutate, res.ess, res.resampled, res.phi_n))
         phi_prev = res.phi_n
         if phi_prev >= 1.0:
@@ -84,8 +121,9 @@ eng.evaluate(1)
 rows_b, _ = run(spec_new, 1, args.stages, float(rows_a[-1, 5]), True)
 timed = rows_b[2:] if len(rows_b) > 4 else rows_b
 ms = float(timed[:, 0].mean())
-print(json.dumps({
-    "workload": what + ", n_particles=%d, n_mh_steps=%d, 3 blocks, alpha=0.9, 1 GPU" % (N, args.n_mh),
+out = {
+    "workload": what + ", n_particles=%d, n_mh_steps=%d, 3 blocks, alpha=0.9, %d GPU(s), one global cloud sharded" % (N, args.n_mh, WORLD),
+    "n_gpus": WORLD,
     "stages_timed": int(len(timed)), "ms_per_stage": ms,
     "particle_mh_steps_per_sec_per_stage": float(N * args.n_mh * 3 / (ms * 1e-3)),
     "resamples_in_timed_stages": int(timed[:, 6].sum()),
@@ -93,5 +131,6 @@ print(json.dumps({
                  "moments": float(timed[:, 3].mean()), "mutate": float(timed[:, 4].mean())},
     "phi": [float(v) for v in rows_b[:, 7]], "ess": [float(v) for v in rows_b[:, 5]],
     "first_vintage": {"stages": int(len(rows_a)), "final_ess": float(rows_a[-1, 5])},
-}))
+}
 eng.close()
+emit(out)
