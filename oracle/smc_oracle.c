@@ -968,7 +968,7 @@ static double mvn_logpdf(const double *Lc, int n, double logdet, const double *x
     for (int i = 0; i < n; ++i) {
         double s = x[i] - mu[i];
         for (int j = 0; j < i; ++j) s = FMA(-Lc[(size_t)i * n + j], y[j], s);
-        y[i] = s / Lc[(size_t)i * n + i];
+        y[i] = s * (1.0 / Lc[(size_t)i * n + i]);      /* reciprocal diagonal (the device precomputes it once per stage) */
         q = FMA(y[i], y[i], q);
     }
     return -0.5 * (((double)n * (2.0 * HALF_LOG_2PI) + logdet) + q);
@@ -982,8 +982,11 @@ ORC_API void orc_proposal_densities(const double *Lc, const double *sd, const do
     double q1 = alpha * orc_exp(mvn_logpdf(Lc, n, logdet, para_draw, para_subset));
     double ind = 1.0;
     for (int i = 0; i < n; ++i) {
-        double zs = (para_subset[i] - para_draw[i]) / sd[i];
-        ind = ind / (sd[i] * sqrt(2.0 * M_PI)) * orc_exp(-0.5 * (zs * zs));
+        /* zstat = (theta_i - vartheta_i) / Sigma_ii^(1/2); ind_pdf *= exp(-zstat^2 / 2) / (Sigma_ii^(1/2) sqrt(2 pi)),
+         * helpers.jl:145-148, with the reciprocal standard deviation formed once */
+        double isd = 1.0 / sd[i];
+        double zs = (para_subset[i] - para_draw[i]) * isd;
+        ind = (ind * (isd * 0x1.9884533d43651p-2)) * orc_exp(-0.5 * (zs * zs));
     }
     q0 += (1.0 - alpha) / 2.0 * ind;
     q1 += (1.0 - alpha) / 2.0 * ind;

@@ -53,7 +53,9 @@ struct MutConst {
     double L[NBMAX][PACKMAX];   // c * L_b embedded in parameter order, lower, packed by COLUMNS of the d x d matrix:
                                 // L[r][j] at [j d - j(j-1)/2 + (r - j)]
     double csd[NBMAX][DMAX];    // c * sqrt(Sigma_ii)
-    double sd[NBMAX][DMAX];     // sqrt(Sigma_ii) WITHOUT c (diagonal mixture density, helpers.jl:146)
+    double isd[NBMAX][DMAX];    // 1 / sqrt(Sigma_ii), WITHOUT c (diagonal mixture density, helpers.jl:146)
+    double isdn[NBMAX][DMAX];   // isd / sqrt(2 pi)
+    double rl[NBMAX][DMAX];     // 1 / (c L_ii): reciprocal diagonal of the scaled factor (forward substitutions)
     double mu[DMAX];            // theta_bar
     double lognorm[NBMAX];      // n_b log(2 pi) + log det(c^2 Sigma_b)
     uint32_t mask[NBMAX];

@@ -819,7 +819,7 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
         out->bsize[b] = n;
         uint32_t mask = 0;
         for (int e = 0; e < PACKMAX; ++e) out->L[b][e] = 0.0;
-        for (int k = 0; k < DMAX; ++k) { out->csd[b][k] = 0.0; out->sd[b][k] = 0.0; }
+        for (int k = 0; k < DMAX; ++k) { out->csd[b][k] = 0.0; out->isd[b][k] = 0.0; out->isdn[b][k] = 0.0; out->rl[b][k] = 0.0; }
         for (int i = 0; i < n; ++i) {
             mask |= 1u << bs.member[b][i];
             for (int j = 0; j < n; ++j) {
@@ -838,7 +838,10 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
                 out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * L[i * n + j];
             }
             out->csd[b][ai] = c * sqrt(S[i * n + i]);
-            out->sd[b][ai] = sqrt(S[i * n + i]);
+            const double isd = 1.0 / sqrt(S[i * n + i]);
+            out->isd[b][ai] = isd;
+            out->isdn[b][ai] = isd * 0x1.9884533d43651p-2;
+            out->rl[b][ai] = 1.0 / (c * L[i * n + i]);
         }
         // log-normaliser of N(.; ., c^2 Sigma_b): n log(2 pi) + 2 sum_i log(c L_ii)  (members ascending)
         double ld = 0.0;
@@ -875,7 +878,7 @@ k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ c
         const int n = bs.bsize[b];
         for (int e = lane; e < PACKMAX; e += 32) out->L[b][e] = 0.0;
         out->csd[b][lane] = 0.0;
-        out->sd[b][lane] = 0.0;
+        out->isd[b][lane] = 0.0; out->isdn[b][lane] = 0.0; out->rl[b][lane] = 0.0;
         uint32_t mask = 0;
         for (int i = 0; i < n; ++i) mask |= 1u << bs.member[b][i];
         if (lane == 0) { out->mask[b] = mask; out->bsize[b] = n; }
@@ -911,7 +914,10 @@ k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ c
                 out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * L[lane][j];
             }
             out->csd[b][ai] = c * sqrt(S[lane][lane]);
-            out->sd[b][ai] = sqrt(S[lane][lane]);
+            const double isd = 1.0 / sqrt(S[lane][lane]);
+            out->isd[b][ai] = isd;
+            out->isdn[b][ai] = isd * 0x1.9884533d43651p-2;
+            out->rl[b][ai] = 1.0 / (c * L[lane][lane]);
         }
         if (lane == 0) {
             double ld = 0.0;

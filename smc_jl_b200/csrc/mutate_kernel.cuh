@@ -144,7 +144,7 @@ struct GaussReg {
 };
 
 // Quadratic form v' (c^2 Sigma_b)^{-1} v through the scaled factor embedded in parameter order: forward
-// substitution row by row (each y_i one fma chain over ascending j, then ONE division), v is overwritten by
+// substitution row by row (each y_i one fma chain over ascending j, times the reciprocal diagonal), v is overwritten by
 // y.  Entries of v outside the block must be 0 (their factor entries are 0, so the chain passes through).
 // position of L[r][j] (r >= j) in the column-packed lower factor: column j is contiguous in r, so the unrolled
 // mat-vec fetches two entries per LDCU.128
@@ -161,7 +161,7 @@ __device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
             double s = v[i];
 #pragma unroll
             for (int j = 0; j < i; ++j) s = fma(-c_mut.L[b][lcol<D>(i, j)], v[j], s);
-            v[i] = s / c_mut.L[b][lcol<D>(i, i)];
+            v[i] = s * c_mut.rl[b][i];
             q = fma(v[i], v[i], q);
         }
     }
@@ -274,9 +274,8 @@ k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 #pragma unroll
                 for (int k = 0; k < D; ++k)
                     if ((mask >> k) & 1u) {
-                        const double sdk = c_mut.sd[b][k];
-                        const double zs = s[k] / sdk;
-                        ind = ind / (sdk * 0x1.40d931ff62705p+1) * det_exp(-0.5 * (zs * zs));
+                        const double zs = s[k] * c_mut.isd[b][k];
+                        ind = (ind * c_mut.isdn[b][k]) * det_exp(-0.5 * (zs * zs));
                     }
                 const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
 #pragma unroll
