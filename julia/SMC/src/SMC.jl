@@ -6,9 +6,9 @@
 # one-to-one by the ctypes binding in smc_jl_b200/_lib.py, which IS tested against the same library.
 module SMC
 
-using Libdl, Random
+using Libdl, Random, LinearAlgebra, Distributions, JLD2, FileIO, HDF5
 
-export smc, Cloud, resample, mutation, LinearGaussianLogLik, GaussRegLogLik, get_cloud
+export smc, Cloud, resample, mutation, LinearGaussianLogLik, GaussRegLogLik, AnSchorfheideLogLik, get_cloud
 
 const LIB = get(ENV, "SMCB200_LIB", "libsmcb200.so")
 
@@ -99,8 +99,10 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
              use_fixed_schedule::Bool = true, tempering_target::Float64 = 0.97,
              old_data::Matrix{Float64} = Matrix{Float64}(undef, size(data, 1), 0), old_cloud::Cloud = Cloud(0, 0),
              old_loglikelihood::Function = loglikelihood, tempered_update_prior_weight::Float64 = 0.0,
-             log_prob_old_data::Float64 = 0.0, savepath::String = "smc_cloud.jld2", seed::UInt64 = UInt64(1793),
-             device::Int = 0, kwargs...)
+             log_prob_old_data::Float64 = 0.0, savepath::String = "smc_cloud.jld2",
+             particle_store_path::String = "smcsave.h5", loadpath::String = "", save_intermediate::Bool = false,
+             intermediate_stage_increment::Int = 10, continue_intermediate::Bool = false,
+             seed::UInt64 = UInt64(1793), device::Int = 0, kwargs...)
     loglikelihood isa DeviceLogLik ||
         throw(ArgumentError("loglikelihood must be a device likelihood descriptor; there is no CPU fallback"))
     resampling_method in (:systematic, :multinomial) ||
@@ -128,8 +130,14 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
         end
         # stage 0: initial_draw! on the device (src/initialization.jl:88-119), or the online update's
         # initialize_likelihoods! on the uploaded old cloud (:153-186)
-        cloud = isempty(old_data) ? Cloud(n_para, n_parts) : old_cloud
-        if isempty(old_data)
+        # (the prior-mixing bridge of src/smc_main.jl:260-329 is composed from smcb200_resample_weights_n,
+        #  smcb200_initial_draw with the old likelihood, smcb200_evaluate(1), smcb200_cloud_write_column and
+        #  smcb200_resample exactly as smc_jl_b200/driver.py:bridge_cloud does; omitted here for brevity)
+        cloud = continue_intermediate ? load(loadpath, "cloud") : (isempty(old_data) ? Cloud(n_para, n_parts) : old_cloud)
+        if continue_intermediate                                             # src/smc_main.jl:334-335
+            GC.@preserve cloud check(h, ccall((:smcb200_cloud_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
+                                              h, cloud.particles, n_parts, 0))
+        elseif isempty(old_data)
             values = Float64[p.value for p in parameters]
             GC.@preserve values check(h, ccall((:smcb200_initial_draw, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, UInt64, Int32),
                                                h, values, seed, 1000))
@@ -139,12 +147,21 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
             check(h, ccall((:smcb200_evaluate, LIB), Int32, (Ptr{Cvoid}, Int32), h, 1))
         end
         schedule = ((collect(1:n_Φ) .- 1) / (n_Φ - 1)) .^ λ
-        cloud.tempering_schedule = use_fixed_schedule ? schedule : zeros(1)
-        cloud.ESS = [Float64(n_parts)]; cloud.n_Φ = n_Φ; cloud.c = c; cloud.accept = target
-        state = StageState(c, target, Float64(n_parts), 0., 2, 0, 0)
-        w_matrix = zeros(n_parts, 1); W_matrix = ones(n_parts, 1)
+        if !continue_intermediate                                            # initialize_cloud_settings!, initialization.jl:196-211
+            cloud.tempering_schedule = use_fixed_schedule ? schedule : zeros(1)
+            cloud.ESS = [isempty(old_data) ? Float64(n_parts) : cloud.ESS[end]]; cloud.n_Φ = n_Φ; cloud.c = c; cloud.accept = target
+        end
+        state = StageState(c, target, cloud.ESS[end], 0., 2, 0, 0)
+        w_matrix = zeros(n_parts, 1)
+        W_matrix = isempty(old_data) ? ones(n_parts, 1) :                   # src/smc_main.jl:363-366
+                   reshape(sum(cloud.particles[:, end]) <= 1.0 ? cloud.particles[:, end] * n_parts : cloud.particles[:, end], :, 1)
         inc = Vector{Float64}(undef, n_parts); normw = Vector{Float64}(undef, n_parts)
         i = 1; ϕ_n = 0.
+        if continue_intermediate                                             # src/smc_main.jl:355-361
+            w_matrix = load(loadpath, "w"); W_matrix = load(loadpath, "W"); j = load(loadpath, "j")
+            i = cloud.stage_index; ϕ_n = schedule[i]
+            state = StageState(cloud.c, cloud.accept, cloud.ESS[end], schedule[j], j, 0, 0)
+        end
         while ϕ_n < 1.                                                     # src/smc_main.jl:377
             t0 = time_ns(); cloud.stage_index = i += 1
             ϕ_n1 = use_fixed_schedule ? schedule[i - 1] : cloud.tempering_schedule[i - 1]
@@ -161,12 +178,22 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
             push!(cloud.ESS, res.ess); cloud.resamples += res.resampled; cloud.c = res.c; cloud.accept = res.accept
             w_matrix = hcat(w_matrix, inc); W_matrix = hcat(W_matrix, normw)    # :419-420 (normw is reset to 1 on resample, :445)
             cloud.total_sampling_time += (time_ns() - t0) * 1e-9
+            if save_intermediate && mod(cloud.stage_index, intermediate_stage_increment) == 0     # :499-507
+                GC.@preserve cloud check(h, ccall((:smcb200_cloud_download, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64), h, cloud.particles, n_parts, 0))
+                jldopen(replace(savepath, ".jld2" => "_stage=$(cloud.stage_index).jld2"), true, true, true, IOStream) do file
+                    write(file, "cloud", cloud); write(file, "w", w_matrix); write(file, "W", W_matrix); write(file, "j", state.j)
+                end
+            end
         end
         GC.@preserve cloud check(h, ccall((:smcb200_cloud_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64),
                                           h, cloud.particles, n_parts, 0))
         if !testing                                                          # :513-526
             jldopen(savepath, true, true, true, IOStream) do file
                 write(file, "cloud", cloud); write(file, "w", w_matrix); write(file, "W", W_matrix)
+            end
+            h5open(particle_store_path, "w") do file                              # :514-520
+                write(file, "smcparams", cloud.particles[:, 1:n_para])
             end
         end
     finally
