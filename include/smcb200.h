@@ -72,6 +72,8 @@ enum {
                                 dparams = data, 3 x n_periods column-major (gdp growth, inflation, nominal rate). */
 };
 
+/* :polyalgo (src/resample.jl:73-75, StatsBase.sample: i.i.d. categorical draws through an alias table) has the
+ * multinomial resampler's distribution; the host shims map it to SMCB200_RESAMPLE_MULTINOMIAL. */
 enum { SMCB200_RESAMPLE_SYSTEMATIC = 0, SMCB200_RESAMPLE_MULTINOMIAL = 1 };
 
 /* ---- library / context ---------------------------------------------------------------------- */

@@ -105,7 +105,7 @@ function smc(loglikelihood::Function, parameters, data::Matrix{Float64};
              seed::UInt64 = UInt64(1793), device::Int = 0, kwargs...)
     loglikelihood isa DeviceLogLik ||
         throw(ArgumentError("loglikelihood must be a device likelihood descriptor; there is no CPU fallback"))
-    resampling_method in (:systematic, :multinomial) ||
+    resampling_method in (:systematic, :multinomial, :polyalgo) ||    # :polyalgo (i.i.d. categorical draws) -> multinomial kernel
         throw("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
     n_para = length(parameters)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
@@ -205,7 +205,7 @@ end
 """`resample(weights; method)` (src/resample.jl:23) on the device."""
 function resample(weights::Vector{Float64}; n_parts::Int = length(weights), method::Symbol = :systematic,
                   seed::UInt64 = rand(UInt64), device::Int = 0)
-    method in (:systematic, :multinomial) || throw("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
+    method in (:systematic, :multinomial, :polyalgo) || throw("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     ccall((:smcb200_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32), ctx, device) == 0 || error("no GPU")
     idx = Vector{Int64}(undef, n_parts)

@@ -8,7 +8,8 @@ Differences from the reference, all at the edges of the hot path:
   * the reference returns `nothing` and writes JLD2/HDF5 files; this driver returns the final `Cloud`
     (plus `w`, `W` when `testing=False` it also writes them to `savepath` as .npz -- JLD2 writers are
     SURVEY 8(f)2 "next");
-  * `resampling_method=:polyalgo` and regime switching are not available (NotImplementedError);
+  * `resampling_method=:polyalgo` (StatsBase's alias-table sampler: i.i.d. categorical draws) is served by the
+    multinomial kernel -- same distribution, different (unpinned) random stream; regime switching is not available;
   * checkpoints (`save_intermediate`, `continue_intermediate`, smc_main.jl:334-361,499-507) are `.npz` files with the
     reference's keys (`cloud` fields, `w`, `W`, `j`);
   * randomness is the engine's Philox stream keyed by `seed` (the reference uses the global dSFMT).
@@ -40,6 +41,8 @@ def bridge_cloud(eng, spec, old_spec, old_cloud, n_parts, prior_weight, resampli
     particles from the old cloud, draw the rest from the CURRENT prior scored with the OLD likelihood on the old data
     (device initial_draw!), initialize_likelihoods! on the new data, zero the weights of -Inf particles, normalise,
     resample, reset.  Leaves the bridged cloud on the device (weights 1, ESS = n_parts)."""
+    if eng.world > 1:
+        raise NotImplementedError("bridge initialisation runs on one GPU (stage-0 set-up); shard the run after it")
     d = spec.d
     n_res = int(round((1.0 - prior_weight) * n_parts))
     n_prior = n_parts - n_res
@@ -91,8 +94,6 @@ def smc(loglikelihood, parameters, data=None, *, verbose="low", testing=False, d
         raise NotImplementedError("regime switching is out of scope of the device engine")
     resampling_method = str(resampling_method).lstrip(":")
     if resampling_method not in RESAMPLERS:
-        if resampling_method == "polyalgo":
-            raise NotImplementedError(":polyalgo resampling (StatsBase.sample) has no device kernel")
         raise ValueError("Invalid resampler in SMC. Options are :systematic, :multinomial, or :polyalgo")
     if not (0.0 <= tempered_update_prior_weight <= 1.0):
         raise ValueError("The keyword tempered_update_prior_weight must be within the interval [0, 1] but is currently "

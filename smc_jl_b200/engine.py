@@ -11,7 +11,10 @@ from . import _lib
 from ._lib import StageConfig, StageResult, StageState, lib, ptr
 from .model import ModelSpec
 
-RESAMPLERS = {"systematic": 0, "multinomial": 1}
+# :polyalgo (src/resample.jl:73-75) is `StatsBase.sample(1:n, Weights(w), n)`: n i.i.d. categorical draws through an alias
+# table (or direct sampling for small n) -- the same joint distribution as the multinomial resampler's inverse-CDF draws,
+# on a random stream that is unpinned either way.  It is served by the multinomial kernel.
+RESAMPLERS = {"systematic": 0, "multinomial": 1, "polyalgo": 1}
 
 
 class NotPosDefError(np.linalg.LinAlgError):

@@ -177,7 +177,20 @@ def test_resample_explicit_offset_edges(eng):
         O.lib().orc_resample(w, N, 0, 0, 0, u, oidx, None)
         assert np.array_equal(idx, oidx)
     with pytest.raises(ValueError):
-        eng.resample_weights(w, "polyalgo")
+        eng.resample_weights(w, "stratified")
+
+
+def test_polyalgo_is_served_by_the_multinomial_kernel(eng):
+    """:polyalgo = StatsBase.sample(1:n, Weights(w), n): i.i.d. categorical draws (src/resample.jl:73-75)."""
+    rng = np.random.default_rng(5)
+    w = rng.gamma(0.5, 1.0, 3000)
+    a = eng.resample_weights(w, "polyalgo", seed=9, stage=4)
+    b = eng.resample_weights(w, "multinomial", seed=9, stage=4)
+    assert np.array_equal(a, b)
+    counts = np.bincount(a - 1, minlength=3000)
+    p = w / w.sum()
+    z = (counts - 3000 * p) / np.sqrt(3000 * p * (1 - p) + 1e-12)
+    assert np.abs(z).max() < 6.0 and abs(z.mean()) < 0.1
 
 
 @pytest.mark.parametrize("method", ["systematic", "multinomial"])
