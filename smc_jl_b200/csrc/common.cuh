@@ -83,7 +83,7 @@ struct MutArgs {
 struct Ctx;
 struct KernelEntry {            // one likelihood functor's kernels + the constant-memory uploaders of its translation unit
     int kind, neq, k, stride, coef, sig, d;
-    void (*mut[2][2][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][single block][mixture]
+    void (*mut[2][3][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][0 blocks / 1 single block / 2 single full block][mixture]
     void (*eval)(double*, int64_t, int);
     void (*draw)(double*, int64_t, int64_t, const double*, uint64_t, int, int*);   // initial_draw!
     int (*upload_model)(Ctx*);

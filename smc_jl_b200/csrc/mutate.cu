@@ -91,7 +91,9 @@ int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has
     const bool single = (a.n_blocks == 1);
     const unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
     const size_t smem = sizeof(double) * 2 * (size_t)e->d * MUT_THREADS;
-    auto kern = e->mut[has_old ? 1 : 0][single ? 1 : 0][alpha < 1.0 ? 1 : 0];
+    // one block that holds every parameter (none fixed): compile-time membership mask
+    const bool full = single && ctx->n_free == e->d;      // (a single block always holds all free parameters)
+    auto kern = e->mut[has_old ? 1 : 0][single ? (full ? 2 : 1) : 0][alpha < 1.0 ? 1 : 0];
     if (smem > 48 * 1024)
         SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, MUT_THREADS, smem, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);

@@ -174,11 +174,13 @@ __device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
 // vector, which is in turn the proposal increment, the candidate and (inside the likelihood) the centred
 // candidate.  Accepting a move flips which buffer is current.  This keeps the kernel under ~100 registers
 // (5 blocks = 20 warps per SM) -- it is FP64-latency bound, so resident warps are what buys throughput.
-// SINGLE = (n_blocks == 1): block index is a literal, so factor entries load as LDCU.128 pairs.
+// BLK = 0: several blocks; 1: n_blocks == 1 (block index is a literal, so factor entries load as LDCU.128 pairs);
+// 2: one block holding ALL D parameters (none fixed): the membership mask is a compile-time constant and every
+// per-parameter membership branch / select disappears (config C2).
 
 // MIX = (alpha < 1): the three-component mixture proposal of mvnormal_mixture_draw (helpers.jl:87-100) and
 // the proposal densities of compute_proposal_densities (helpers.jl:128-164).
-template <class LIK, bool HAS_OLD, bool SINGLE, bool MIX>
+template <class LIK, bool HAS_OLD, int BLK, bool MIX>
 __global__ void __launch_bounds__(MUT_THREADS, LIK::MINB)
 k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
 {
@@ -197,13 +199,15 @@ k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
     bool flipped = false;
     const uint32_t gp = (uint32_t)(index0 + i);
     const double phi = a.phi_n, omphi = 1.0 - a.phi_n;
+    constexpr bool SINGLE = BLK != 0;
+    constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
     const int nb = SINGLE ? 1 : a.n_blocks;
 
     for (int step = 0; step < a.n_mh_steps; ++step) {
         for (int bb = 0; bb < nb; ++bb) {
             const int b = SINGLE ? 0 : bb;
             const uint32_t sb = (uint32_t)(step * nb + b);
-            const uint32_t mask = c_mut.mask[b];
+            const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
             const double* cur = flipped ? buf1 : buf0;
             double* cand = flipped ? buf0 : buf1;
             // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
@@ -448,14 +452,18 @@ static KernelEntry make_entry()
     KernelEntry e;
     e.kind = LIK::KIND;
     e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
-    e.mut[0][0][0] = k_mutate<LIK, false, false, false>;
-    e.mut[0][1][0] = k_mutate<LIK, false, true, false>;
-    e.mut[1][0][0] = k_mutate<LIK, true, false, false>;
-    e.mut[1][1][0] = k_mutate<LIK, true, true, false>;
-    e.mut[0][0][1] = k_mutate<LIK, false, false, true>;
-    e.mut[0][1][1] = k_mutate<LIK, false, true, true>;
-    e.mut[1][0][1] = k_mutate<LIK, true, false, true>;
-    e.mut[1][1][1] = k_mutate<LIK, true, true, true>;
+    e.mut[0][0][0] = k_mutate<LIK, false, 0, false>;
+    e.mut[0][1][0] = k_mutate<LIK, false, 1, false>;
+    e.mut[0][2][0] = k_mutate<LIK, false, 2, false>;
+    e.mut[1][0][0] = k_mutate<LIK, true, 0, false>;
+    e.mut[1][1][0] = k_mutate<LIK, true, 1, false>;
+    e.mut[1][2][0] = k_mutate<LIK, true, 2, false>;
+    e.mut[0][0][1] = k_mutate<LIK, false, 0, true>;
+    e.mut[0][1][1] = k_mutate<LIK, false, 1, true>;
+    e.mut[0][2][1] = k_mutate<LIK, false, 2, true>;
+    e.mut[1][0][1] = k_mutate<LIK, true, 0, true>;
+    e.mut[1][1][1] = k_mutate<LIK, true, 1, true>;
+    e.mut[1][2][1] = k_mutate<LIK, true, 2, true>;
     e.eval = k_evaluate<LIK>;
     e.draw = k_initial_draw<LIK>;
     e.upload_model = tu_upload_model;
