@@ -260,6 +260,24 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * N * N_MH * N_BLOCKS / float(e2e_t.item())
 
+    # ---- the per-stage call smc() itself makes: cloud resident, stage summary + the two weight-history columns
+    # (w_matrix / W_matrix, src/smc_main.jl:419-420) read back into pinned host memory every stage ------------
+    hist = torch.empty((2, N), dtype=torch.float64, pin_memory=True).numpy()
+    eng.upload(host)
+    st3 = StageState(c=st2.c, accept=st2.accept, ess_prev=st2.ess_prev, phi_prop=0.0, j=2)
+    s1 = s0 + 1 + k_e2e
+    eng.stage(stage_cfg(sched, s1), st3, inc_out=hist[0], normw_out=hist[1])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(s1 + 1, s1 + 1 + 10):
+        eng.stage(stage_cfg(sched, s), st3, inc_out=hist[0], normw_out=hist[1])
+    torch.cuda.synchronize()
+    res_sec = (time.perf_counter() - t0) / 10
+    res_t = torch.tensor([res_sec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(res_t, op=dist.ReduceOp.MAX)
+    resident_value = world * N * N_MH * N_BLOCKS / float(res_t.item())
+
     # ---- roofline of the dominant kernel (mutation): algorithmic bytes / CUDA-event duration ---------
     peak, peak_src = peaks()
     mut_ms = phase[3] / args.steps
@@ -288,7 +306,11 @@ def run_ours(args):
                                        "row exchange" % (world, world)) if world > 1 else "1 GPU",
                        "resamples_in_timed_region": int(resamples)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(cols * N * 8), "d2h_bytes_per_step": int(cols * N * 8),
-                    "what": "smcb200_stage_host: Cloud in pinned host memory, upload + stage + download each step"},
+                    "what": "smcb200_stage_host: Cloud in pinned host memory, upload + stage + download each step "
+                            "(PCIe-bound: 2 x 210 MB per step)"},
+            "e2e_resident": {"value": resident_value, "unit": UNIT, "h2d_bytes_per_step": 128, "d2h_bytes_per_step": int(2 * N * 8 + 72),
+                             "what": "the per-stage call smc() makes: cloud resident in HBM, wall clock around smcb200_stage incl. the "
+                                     "D2H of the stage summary and of the w/W history columns into pinned host memory"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -208,9 +208,14 @@ class Engine:
                                     phi_n, phi_n1, c, alpha, n_mh_steps, int(bool(has_old_data)), seed, stage, C.byref(acc)))
         return acc.value
 
-    def stage(self, cfg: StageConfig, state: StageState, schedule=None, want_inc=False, want_normw=False):
-        inc = np.zeros(self.count) if want_inc else None
-        nw = np.zeros(self.count) if want_normw else None
+    def stage(self, cfg: StageConfig, state: StageState, schedule=None, want_inc=False, want_normw=False, inc_out=None,
+              normw_out=None):
+        """One fused stage (src/smc_main.jl:377-497).  want_inc / want_normw return the columns the reference appends to
+        w_matrix / W_matrix; inc_out / normw_out let the caller supply (e.g. pinned) float64 buffers of shard length."""
+        inc = inc_out if inc_out is not None else (np.zeros(self.count) if want_inc else None)
+        nw = normw_out if normw_out is not None else (np.zeros(self.count) if want_normw else None)
+        for b in (inc, nw):
+            assert b is None or (b.dtype == np.float64 and b.shape == (self.count,) and b.flags.c_contiguous)
         sched = _f64(schedule) if schedule is not None else None
         res = StageResult()
         self._ck(lib.smcb200_stage(self.h, C.byref(cfg), C.byref(state), ptr(sched), 0 if sched is None else len(sched),
