@@ -761,8 +761,9 @@ int32_t smcb200_initial_draw(smcb200_ctx* c, const double* fixed_values, uint64_
     int st = check_ready(c, true); if (st) return st;
     if (max_tries < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "max_tries must be >= 1");
     cudaSetDevice(c->device);
-    // scratch: [DMAX] fixed values followed by the failure counter (reuses the device status word's neighbour-free tmp column)
-    double* fv_dev = c->tmp;                                 // N >= 1 doubles; DMAX doubles are needed
+    // the fixed parameters' values travel through the scratch column `tmp` (DMAX doubles; a tiny cloud gets its own buffer);
+    // the device status word counts the particles that exhausted max_tries
+    double* fv_dev = c->tmp;
     double* fv_alloc = nullptr;
     if (c->N < DMAX + 1) { SMC_CUDA(c, cudaMalloc(&fv_alloc, sizeof(double) * (DMAX + 1))); fv_dev = fv_alloc; }
     double fv[DMAX] = {0};
