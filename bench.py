@@ -30,7 +30,7 @@ D, T, N_FULL, N_MH, N_BLOCKS, N_PHI, LAM = 20, 256, 1 << 20, 3, 1, 300, 2.1
 SEED = 1793
 METRIC = "particle_mh_steps_per_sec_per_stage"
 UNIT = "particle-MH-steps/s"
-MUTATE_DRAM_BYTES_NCU = 334.1e6   # measured once per kernel change with ncu (profiles/r01_mutate_ncu_v3.md)
+MUTATE_DRAM_BYTES_NCU = 335.8e6   # measured once per kernel change with ncu (profiles/r01_final_summary.md)
 FIRST_STAGE = 30   # timed stages start here in the 300-point schedule (past the burn-in of the prior cloud)
 
 
@@ -317,7 +317,7 @@ def run_ours(args):
                          "traffic": MUTATE_DRAM_BYTES_NCU, "kernel": "k_mutate<GaussReg<1,20,20,0,-1>,false,true,false>",
                          "algorithmic_bytes_per_launch": mut_bytes, "avg_launch_ms": mut_ms, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r01_mutate_ncu_v3.md); per launch at N = 2^20",
+                                           "(profiles/r01_final_summary.md); per launch at N = 2^20",
                          "note": "instruction-issue bound (smsp__issue_active 73 %, FP64 pipe 37 %), see DESIGN.md"},
             "cpu_baseline": cpu,
             "phase_ms_per_step": {"correct": phase[0] / args.steps, "resample": phase[1] / args.steps,
