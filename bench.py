@@ -314,7 +314,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": MUTATE_DRAM_BYTES_NCU, "kernel": "k_mutate<GaussReg<1,20,20,0,-1>,false,true,false>",
+                         "traffic": MUTATE_DRAM_BYTES_NCU, "kernel": "k_mutate<GaussReg<1,20,20,0,-1>, HAS_OLD=false, BLK=2, MIX=false>",
                          "algorithmic_bytes_per_launch": mut_bytes, "avg_launch_ms": mut_ms, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
                                            "(profiles/r01_final_summary.md); per launch at N = 2^20",
