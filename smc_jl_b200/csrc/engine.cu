@@ -1,6 +1,6 @@
 // engine.cu -- the C ABI of libsmcb200 (include/smcb200.h) and the host-side orchestration of one
 // SMC stage on one GPU shard.  Host code here only sequences kernels and moves scalars; all
-// per-particle arithmetic runs in the kernels of kernels.cuh / mutate.cu.
+// per-particle arithmetic runs in the kernels of kernels.cuh / mutate_kernel.cuh (instantiated in mut_*.cu).
 #include <dlfcn.h>
 #include <nccl.h>
 

@@ -1,5 +1,6 @@
-// kernels.cuh -- K1..K6: correction/ESS, adaptive-phi state machine, resampling (scan + search +
-// gather) and moments.  All of them are single-pass streaming kernels over struct-of-arrays columns
+// kernels.cuh -- K1..K6: correction/ESS, the multi-trial adaptive-phi sweep and its device state machine,
+// resampling (scan + search + gather), moments, proposal preparation, and the NVLink mailbox exchange
+// that carries the small cross-GPU reductions.  The streaming kernels run over struct-of-arrays columns
 // (HBM-bound); every reduction follows the canonical orders of DESIGN.md "Numerical contract".
 #pragma once
 #include "common.cuh"
