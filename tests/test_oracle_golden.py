@@ -327,3 +327,36 @@ def test_resample_structure(golden):
     cum = np.cumsum(w / w.sum())
     ref = np.array([np.searchsorted(cum, (i + 0.37) / 400, side="right") + 1 for i in range(400)])
     assert np.mean(ref == idx) > 0.99
+
+
+def test_as_determinacy_and_values_against_qz_gensys(golden):
+    """The oracle's closed-form decision rule against Sims' gensys by QZ on the full 8-state canonical form (the route the
+    reference takes through DSGE.jl), on draws that cover the indeterminacy region: the 'exactly one stable root'
+    test agrees with gensys' existence + uniqueness on every draw, and the likelihood values agree where a solution
+    exists.  Pins the -Inf path that no reference fixture exercises."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("as_gensys", os.path.join(os.path.dirname(__file__), "..", "tools", "as_gensys_check.py"))
+    gz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gz)
+    g = golden("as_clouds.npz")
+    data = g["data"][:, :60]
+    flat = np.ascontiguousarray(data.T).ravel()
+    rng = np.random.default_rng(12)
+    base = g["prior_draws"][:, :16]
+    n_det = n_indet = 0
+    for r in range(300):
+        th = base[r % base.shape[0]].copy()
+        th[2] = rng.uniform(0.2, 2.5)            # psi_1 across the Taylor-principle boundary
+        th[3] = rng.uniform(0.0, 0.8)            # psi_2
+        th[1] = rng.uniform(0.01, 1.0)           # kappa
+        th[7] = rng.uniform(0.0, 0.95)           # rho_R
+        ours = O.lib().orc_as_loglik(np.ascontiguousarray(th), flat, 60, 2)
+        ref = gz.loglik8(th, data)
+        assert np.isfinite(ours) == np.isfinite(ref), (r, th[:10], ours, ref)
+        if np.isfinite(ref):
+            n_det += 1
+            assert ours == pytest.approx(ref, rel=1e-8, abs=1e-7)
+        else:
+            n_indet += 1
+    assert n_det > 100 and n_indet > 30
