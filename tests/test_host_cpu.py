@@ -164,6 +164,16 @@ def test_oracle_initial_draw_distributions():
     assert abs(x2.mean() - 0.75 / 2.0) < 5 * np.sqrt((0.75 ** 2 / (4.0 * 1.0)) / N)
     chk(5, 2.0 / 7.0, 2.0 * 5.0 / (49.0 * 8.0))
     chk(6, 2.0 / 4.0, 4.0 / (16.0 * 3.0))
+    # full distributions (Kolmogorov-Smirnov against scipy's reference CDFs; 200 000 draws => D_crit(1e-3) ~ 0.0044)
+    from scipy import stats
+    ks = lambda x, dist: stats.kstest(x, dist.cdf).statistic
+    assert ks(P[:, 0], stats.norm(1.0, 2.0)) < 0.0044
+    assert ks(P[:, 1], stats.uniform(0.0, 3.0)) < 0.0044                      # Uniform(-1, 3) truncated to its valuebounds (0, 3)
+    assert ks(P[:, 2], stats.gamma(2.5, scale=0.4)) < 0.0044
+    assert ks(P[:, 3], stats.gamma(0.6, scale=2.0)) < 0.0044                  # shape < 1: boosted Marsaglia-Tsang
+    assert ks(P[:, 4] ** 2, stats.invgamma(3.0, scale=0.75)) < 0.0044         # RootInverseGamma(6, 0.5)
+    assert ks(P[:, 5], stats.beta(2.0, 5.0)) < 0.0044
+    assert ks(P[:, 6], stats.invgamma(5.0, scale=2.0)) < 0.0044
     # the row's loglh / logprior are the model's
     for r in (0, 17, N - 1):
         th = np.ascontiguousarray(P[r, :8])
@@ -228,3 +238,27 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "particle_mh_steps_per_sec_per_stage" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_log_prior_families_against_scipy():
+    """All six prior families' log-densities (ModelConstructors.prior) against scipy.stats: Normal / Uniform /
+    Gamma / RootInverseGamma are also pinned by the reference's fixtures; Beta and InverseGamma only here."""
+    from scipy import stats
+    fams = [(M.Normal(0.4, 0.2), lambda x: stats.norm(0.4, 0.2).logpdf(x), (-1.0, 2.0)),
+            (M.Uniform(0.0, 3.0), lambda x: stats.uniform(0.0, 3.0).logpdf(x), (0.1, 2.9)),
+            (M.Gamma(2.5, 0.4), lambda x: stats.gamma(2.5, scale=0.4).logpdf(x), (0.01, 5.0)),
+            (M.Beta(2.0, 5.0), lambda x: stats.beta(2.0, 5.0).logpdf(x), (0.01, 0.99)),
+            (M.InverseGamma(5.0, 2.0), lambda x: stats.invgamma(5.0, scale=2.0).logpdf(x), (0.05, 4.0)),
+            # RootInverseGamma(nu, tau): x^2 ~ InverseGamma(nu/2, nu tau^2/2)  =>  p(x) = 2 x p_IG(x^2)
+            (M.RootInverseGamma(4.0, 0.5), lambda x: np.log(2 * x) + stats.invgamma(2.0, scale=0.5).logpdf(x * x), (0.05, 3.0))]
+    rng = np.random.default_rng(1)
+    for prior, ref, (lo, hi) in fams:
+        ps = [M.parameter("p", 0.5, (-1e5, 1e5), (-1e5, 1e5), None, prior)]
+        mod = O.Model(M.make_spec(ps))
+        for x in rng.uniform(lo, hi, 200):
+            assert mod.logprior(np.array([x])) == pytest.approx(float(ref(x)), rel=1e-12, abs=1e-12), (prior, x)
+    # outside the support
+    for prior, x in ((M.Uniform(0.0, 3.0), 3.5), (M.Gamma(2.5, 0.4), -0.1), (M.Beta(2.0, 5.0), 1.2), (M.InverseGamma(5.0, 2.0), -1.0),
+                     (M.RootInverseGamma(4.0, 0.5), -0.3)):
+        mod = O.Model(M.make_spec([M.parameter("p", 0.5, (-1e5, 1e5), (-1e5, 1e5), None, prior)]))
+        assert mod.logprior(np.array([x])) == -np.inf
