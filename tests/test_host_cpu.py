@@ -262,3 +262,44 @@ def test_log_prior_families_against_scipy():
                      (M.RootInverseGamma(4.0, 0.5), -0.3)):
         mod = O.Model(M.make_spec([M.parameter("p", 0.5, (-1e5, 1e5), (-1e5, 1e5), None, prior)]))
         assert mod.logprior(np.array([x])) == -np.inf
+
+
+@pytest.mark.parametrize("alpha,n_blocks", [(1.0, 1), (0.5, 1), (0.7, 2)])
+def test_mutation_leaves_the_posterior_invariant(alpha, n_blocks):
+    """Metropolis-Hastings with the (mixture) proposal and its density correction q0 - q1 (mutation.jl:123,
+    helpers.jl:128-164) must leave the target invariant: particles drawn from the exact Gaussian posterior of a linear
+    model keep its mean and covariance after several mutation sweeps at phi = 1.  A wrong proposal-density ratio (the
+    mixture is NOT symmetric for alpha < 1) shows up here as a shifted / shrunk cloud."""
+    rng = np.random.default_rng(3)
+    d, T, N = 3, 40, 40000
+    X = rng.standard_normal((T, d)); X[:, 0] = 1.0
+    y = X @ np.array([0.5, -0.3, 0.8]) + rng.standard_normal(T)
+    prior_sd = 2.0
+    ps = [M.parameter("b%d" % k, 0.0, (-1e5, 1e5), (-1e5, 1e5), None, M.Normal(0.0, prior_sd)) for k in range(d)]
+    spec = M.make_spec(ps, M.LinearGaussianLogLik(y, X, 1.0))
+    prec = X.T @ X + np.eye(d) / prior_sd ** 2
+    cov_post = np.linalg.inv(prec)
+    mean_post = cov_post @ (X.T @ y)
+    P = np.zeros((N, d + 5), order="F")
+    P[:, :d] = rng.multivariate_normal(mean_post, cov_post, N)
+    P[:, d + 4] = 1.0
+    mod = O.Model(spec)
+    buf = O.cloud_f(P)
+    L = O.lib()
+    L.orc_evaluate(mod.h, buf, N)
+    perm = np.arange(d, dtype=np.int32)
+    sizes = np.array([d], np.int32) if n_blocks == 1 else np.array([2, 1], np.int32)
+    st = C.c_int()
+    # a deliberately mis-centred / mis-scaled proposal: the correction, not the proposal, must carry the target
+    mu_prop = mean_post + np.array([0.3, -0.2, 0.1])
+    cov_prop = np.ascontiguousarray(1.5 * cov_post)
+    pr = L.orc_proposal_create(d, d, np.ascontiguousarray(mu_prop), cov_prop, n_blocks, sizes, perm, perm, 0.8, C.byref(st))
+    assert pr and st.value == 0
+    for sweep in range(6):
+        L.orc_mutate(mod.h, pr, buf, N, 0, 1.0, 1.0, alpha, 2, d, 0, 100 + sweep, 2 + sweep, 0)
+    L.orc_proposal_free(pr)
+    Q = O.cloud_m(buf, N, d)
+    se = np.sqrt(np.diag(cov_post) / N)
+    assert np.all(np.abs(Q[:, :d].mean(axis=0) - mean_post) < 5 * se), (Q[:, :d].mean(axis=0), mean_post)
+    np.testing.assert_allclose(np.cov(Q[:, :d].T), cov_post, rtol=0.06, atol=0.06 * np.sqrt(np.outer(np.diag(cov_post), np.diag(cov_post))).max())
+    assert 0.05 < Q[:, d + 3].mean() / 2 < 0.9                     # accept column: sum over the 2 MH steps / n_free (per sweep)
