@@ -342,3 +342,32 @@ def test_log_marginal_likelihood_from_weight_history():
         log_mdd += np.log(np.mean(W_prev * inc))
         W_prev = nw                                     # reset to 1 by the stage when it resampled (smc_main.jl:445)
     assert log_mdd == pytest.approx(exact, abs=0.05), (log_mdd, exact)
+
+
+def test_incremental_weights_all_prior_weight_branches():
+    """The three incremental-weight formulas of src/smc_main.jl:401-410 (prior weight 0, 1 and in between) against a
+    direct numpy restatement, followed by update_weights! / normalize_weights! / ESS (particle.jl:250-259,362-369,
+    smc_main.jl:427)."""
+    rng = np.random.default_rng(8)
+    N, d = 3000, 2
+    for pw, lpod in ((0.0, 0.0), (1.0, 0.0), (0.35, -3.2)):
+        P = np.zeros((N, d + 5), order="F")
+        P[:, d] = rng.normal(-50, 3, N)            # loglh
+        P[:, d + 2] = rng.normal(-30, 2, N)        # old_loglh
+        P[:, d + 4] = rng.uniform(0.2, 1.8, N)     # weights
+        phi_n1, phi_n = 0.21, 0.34
+        ll, old, w0 = P[:, d].copy(), P[:, d + 2].copy(), P[:, d + 4].copy()
+        if pw == 0.0:
+            inc = np.exp((phi_n1 - phi_n) * old + (phi_n - phi_n1) * ll)
+        elif pw == 1.0:
+            inc = np.exp((phi_n - phi_n1) * ll)
+        else:
+            inc = np.exp((phi_n1 - phi_n) * np.log(np.exp(old - lpod + np.log(1 - pw)) + pw) + (phi_n - phi_n1) * ll)
+        wn = w0 * inc
+        wn = wn * N / wn.sum()
+        buf = O.cloud_f(P)
+        oinc, onw, out = np.zeros(N), np.zeros(N), np.zeros(3)
+        assert O.lib().orc_correct(buf, N, d, phi_n1, phi_n, pw, lpod, oinc.ctypes.data_as(C.c_void_p), onw.ctypes.data_as(C.c_void_p), out) == 0
+        np.testing.assert_allclose(oinc, inc, rtol=1e-12)
+        np.testing.assert_allclose(onw, wn, rtol=1e-12)
+        assert out[1] == pytest.approx(N * N / np.sum(wn ** 2), rel=1e-12) and out[2] == pytest.approx(N, rel=1e-12)
