@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define SMCB200_ABI_VERSION 1
+#define SMCB200_ABI_VERSION 2
 
 typedef struct smcb200_ctx smcb200_ctx;
 
@@ -147,8 +147,12 @@ int32_t smcb200_resample_weights(smcb200_ctx *ctx, const double *weights, int64_
  * search stops at cumulative[n_parts], src/resample.jl:54, which makes n_parts < n unusable there). */
 int32_t smcb200_resample_weights_n(smcb200_ctx *ctx, const double *weights, int64_t n, int64_t n_out, int32_t method,
                                    uint64_t seed, uint32_t stage, double u_override, int64_t *idx_out, double *cum_out);
-/* weighted_mean / weighted_cov (src/particle.jl:481-486,526-532): mean[n_para], cov[n_para^2]. */
+/* weighted_mean / weighted_cov (src/particle.jl:481-486,526-532): mean[n_para], cov[n_para^2].  Two passes over the
+ * cloud like StatsBase.cov (mean, then centred scatter). */
 int32_t smcb200_moments(smcb200_ctx *ctx, double *mean, double *cov);
+/* The same moments as the fused stage computes them for the proposal (src/smc_main.jl:457-465): ONE pass over the cloud
+ * with the parameter vector of particle 0 as shift; equal to smcb200_moments up to rounding (~1e-15 relative). */
+int32_t smcb200_moments_onepass(smcb200_ctx *ctx, double *mean, double *cov);
 /* mutation of every particle (src/mutation.jl:56-138 through the fan-out at smc_main.jl:471-484).
  * mean_fr / cov_fr: theta_bar and R restricted to the free parameters (:462-465).  Blocks as from
  * generate_free_blocks / generate_all_blocks (src/helpers.jl:215-260) but 0-based, concatenated, with
@@ -197,6 +201,20 @@ typedef struct {
 int32_t smcb200_stage(smcb200_ctx *ctx, const smcb200_stage_config *cfg, smcb200_stage_state *state,
                       const double *schedule, int32_t n_phi, double *inc_out, double *normw_out,
                       smcb200_stage_result *result);
+/* The recursion `while phi_n < 1` (src/smc_main.jl:377-508) for up to n_stages consecutive stages in ONE call, without
+ * the host in the loop.  cfg: as for smcb200_stage; its phi_n / stage fields are ignored, phi_n1 is read for an adaptive
+ * run (cloud.tempering_schedule[i_first - 1]).  i_first: the reference's loop index `i` of the first stage to run
+ * (>= 2; stage k uses phi_n1 = schedule[i-2], phi_n = schedule[i-1] on a fixed schedule and seeds its random streams
+ * with stage = i, exactly as n_stages calls of smcb200_stage would).  Fixed schedule: all stages are enqueued back to
+ * back -- step size, mean accept rate and the resample decision stay on the device -- and the host synchronises once;
+ * adaptive schedule: one synchronisation per stage, stops after the stage that reaches phi_n = 1.
+ * inc_hist / normw_hist (nullable): host matrices, column k (leading dimension ld_hist >= shard length) receives the
+ * w_matrix / W_matrix column of stage k (src/smc_main.jl:419-420,445); they stream out on a copy stream behind the
+ * computation (pinned memory keeps that asynchronous).  results[n_stages]; *n_done = stages completed.  The same status
+ * codes as smcb200_stage; after an error results[0 .. *n_done) are valid. */
+int32_t smcb200_run_stages(smcb200_ctx *ctx, const smcb200_stage_config *cfg, smcb200_stage_state *state,
+                           const double *schedule, int32_t n_phi, int32_t i_first, int32_t n_stages, double *inc_hist,
+                           double *normw_hist, int64_t ld_hist, smcb200_stage_result *results, int32_t *n_done);
 /* Same with the Cloud living in HOST memory: upload -> stage -> download (what a caller holding a
  * Julia `Cloud` pays per call). */
 int32_t smcb200_stage_host(smcb200_ctx *ctx, double *particles, int64_t ld, const smcb200_stage_config *cfg,
@@ -213,9 +231,13 @@ int32_t smcb200_last_kernel_ms(const smcb200_ctx *ctx, int32_t which, float *ms_
  * one, synchronises and returns the elapsed device time in milliseconds */
 int32_t smcb200_timer_start(smcb200_ctx *ctx);
 int32_t smcb200_timer_stop(smcb200_ctx *ctx, float *ms_out);
+/* measured FP64 FMA throughput of this GPU (TFLOP/s, best of 5 launches of `iters` x 64 dependent-chain DFMA per thread
+ * on every SM): the denominator of bench.py's FP64 roofline */
+int32_t smcb200_fp64_peak(smcb200_ctx *ctx, int32_t iters, double *tflops_out);
 /* device-side deterministic elementary functions, for parity tests: op 0 exp, 1 log, 2 sin(2 pi x),
  * 3 cos(2 pi x), 4/5 = z0/z1 of normal_pair(seed, particle = i, stage = 0, slot = x[i]) (binary64 Box-Muller,
- * prior draws), 6..9 = the four proposal normals of normal_quad (binary32 Box-Muller) of the same Philox block */
+ * prior draws), 6..9 = the four proposal normals of normal_quad (table-driven inverse CDF in binary32) of the same
+ * Philox block */
 int32_t smcb200_debug_math(smcb200_ctx *ctx, int32_t op, const double *x, int64_t n, uint64_t seed, double *out);
 
 #if defined(__GNUC__)

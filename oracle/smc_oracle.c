@@ -202,44 +202,31 @@ static inline void normal_pair(const uint32_t r[4], double *z0, double *z1)
     *z0 = rad * cs;
     *z1 = rad * sn;
 }
-/* Proposal normals: four N(0,1) variates from one Philox block, Box-Muller in binary32 (32-bit uniforms,
- * degree-7 division-free log, 3-term sin/cos kernels on [0, pi/4] after an exact octant split).  IEEE
- * binary32 +,*,fma,sqrt only => the device produces the same bits (DESIGN.md "Numerical contract"). */
-static inline void normal_pair_f32(uint32_t a, uint32_t b, double *z0, double *z1)
+/* Proposal normals: four N(0,1) variates from one Philox block, one 32-bit word each, through a table-driven
+ * inverse normal CDF in binary32 (table: oracle/normal_table.h, written by tools/make_normal_table.py together with the
+ * engine's copy; max |z - Phi^-1(p)| = 5e-7).  Word r: sign = bit 31; v = (r << 1) | 1, p = v / 2^33 in (0, 1/2);
+ * f = (float)v selects the row (exponent, top three mantissa bits), x = 1 + (low 20 mantissa bits) / 2^23, and
+ * z = ((b3 x + b2) x + b1) x + b0 with three binary32 fma.  Exact integer steps + IEEE binary32 conversion / fma only
+ * => the device produces the same bits (DESIGN.md "Numerical contract"). */
+#include "normal_table.h"
+static const float ORC_NORMAL_TAB[4 * SMC_NORMAL_TABLE_ROWS] = {SMC_NORMAL_TABLE_VALUES};
+static inline double normal_icdf(uint32_t r)
 {
-    float u = __builtin_fmaf((float)a, 0x1p-32f, 0x1p-33f);
-    uint32_t ix; memcpy(&ix, &u, 4);
-    ix += 0x3f800000u - 0x3f3504f3u;
-    int k = (int)(ix >> 23) - 127;
-    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
-    float m; memcpy(&m, &ix, 4);
-    float f = m - 1.0f;
-    static const float LQ[8] = {0.9999999403953552f, -0.500003457069397f, 0.3333560824394226f, -0.24971559643745422f,
-                                0.19884242117404938f, -0.1721244603395462f, 0.1633809357881546f, -0.10378583520650864f};
-    float q = LQ[7];
-    for (int i = 6; i >= 0; --i) q = __builtin_fmaf(q, f, LQ[i]);
-    float lnu = __builtin_fmaf((float)k, 0.6931471805599453f, f * q);
-    float t = -2.0f * lnu;
-    float rad = sqrtf(t > 0.0f ? t : 0.0f);
-    uint32_t o = b >> 29;
-    float g = (float)(b & 0x1fffffffu) * 0x1p-29f;
-    if (o & 1u) g = 1.0f - g;
-    float x = g * 0.7853981633974483f;
-    float z = x * x;
-    float s = __builtin_fmaf(x * z, __builtin_fmaf(z, __builtin_fmaf(z, -0.0001958801003638655f, 0.008332748897373676f), -0.166666641831398f), x);
-    float c = __builtin_fmaf(z * z, __builtin_fmaf(z, __builtin_fmaf(z, 2.4581931938882917e-05f, -0.0013888553949072957f), 0.0416666679084301f),
-                             __builtin_fmaf(-0.5f, z, 1.0f));
-    float sp = (o & 1u) ? c : s, cp = (o & 1u) ? s : c;
-    uint32_t qd = o >> 1;
-    float sn = (qd == 0u) ? sp : (qd == 1u) ? cp : (qd == 2u) ? -sp : -cp;
-    float cs = (qd == 0u) ? cp : (qd == 1u) ? -sp : (qd == 2u) ? -cp : sp;
-    *z0 = (double)(rad * cs);
-    *z1 = (double)(rad * sn);
+    uint32_t v = (r << 1) | 1u;
+    float f = (float)v;                     /* round to nearest even */
+    uint32_t fb; memcpy(&fb, &f, 4);
+    const float *c = ORC_NORMAL_TAB + 4 * ((fb >> 20) - (127u << 3));
+    uint32_t xb = (fb & 0x000fffffu) | 0x3f800000u;
+    float x; memcpy(&x, &xb, 4);
+    float z = __builtin_fmaf(__builtin_fmaf(__builtin_fmaf(c[3], x, c[2]), x, c[1]), x, c[0]);
+    uint32_t zb; memcpy(&zb, &z, 4);
+    zb ^= (r & 0x80000000u);
+    memcpy(&z, &zb, 4);
+    return (double)z;
 }
 static inline void normal_quad(const uint32_t r[4], double z[4])
 {
-    normal_pair_f32(r[0], r[1], &z[0], &z[1]);
-    normal_pair_f32(r[2], r[3], &z[2], &z[3]);
+    for (int k = 0; k < 4; ++k) z[k] = normal_icdf(r[k]);
 }
 ORC_API void orc_normal_quad(uint64_t seed, uint32_t particle, uint32_t stage, uint32_t slot, double *out)
 {
@@ -570,6 +557,7 @@ ORC_API double orc_update_c(double c, double accept, double target)
 #define M_LANES 32
 #define M_R 64
 #define M2_CH 512
+#define MAX_D_MOM 64
 struct wx_ctx { const double *w, *x, *y; double mx, my, sw; };
 ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double *cov)
 {
@@ -632,10 +620,62 @@ ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double
     free(tl);
 }
 
-/* canonical mean of a column (update_acceptance_rate!, particle.jl:466-468) */
+/* One-pass form of the same moments, as the engine's fused stage computes them: with a shift x0 (the parameter vector of
+ * particle 0 -- any point of the cloud's support keeps the sums well conditioned)
+ *   Sw = sum w,  m_k = sum w (x_k - x0_k),  C_ab = sum (w (x_a - x0_a)) (x_b - x0_b)
+ *   mean_k = x0_k + m_k / Sw,  cov_ab = C_ab / Sw - (m_a / Sw)(m_b / Sw)
+ * Equal to orc_moments (the reference's two-pass form, src/particle.jl:481-532) up to rounding (~1e-15 relative).
+ * Canonical order of every sum: chunks of M2_CH consecutive particles, lane l accumulates particles l, l + 32, ...
+ * sequentially, adjacent-pair tree over the 32 lanes, then over chunks (zero padded to a power of two). */
+ORC_API void orc_moments_shifted(const double *cloud, i64 N, int d, const double *shift, double *mean, double *cov)
+{
+    const double *w = COL(cloud, N, C_WEIGHT(d));
+    i64 nch = (N + M2_CH - 1) / M2_CH;
+    i64 Pc = next_pow2(nch < 1 ? 1 : nch);
+    double *tl = (double *)calloc((size_t)Pc, sizeof(double));
+    double lane[M_LANES];
+    int E = d * (d + 1) / 2, nq = 1 + d + E;
+    double *sums = (double *)malloc(sizeof(double) * (size_t)nq);
+    for (int q = 0; q < nq; ++q) {
+        int a = 0, b = 0;
+        if (q > d) { int e = q - 1 - d; while ((a + 1) * (a + 2) / 2 <= e) ++a; b = e - a * (a + 1) / 2; }
+        else if (q >= 1) a = q - 1;
+        const double *xa = COL(cloud, N, a), *xb = COL(cloud, N, b);
+        memset(tl, 0, sizeof(double) * (size_t)Pc);
+        for (i64 c = 0; c < nch; ++c) {
+            for (int l = 0; l < M_LANES; ++l) {
+                double acc = 0.0;
+                for (int r = 0; r < M2_CH / M_LANES; ++r) {
+                    i64 i = c * M2_CH + (i64)r * M_LANES + l;
+                    if (i < N) {
+                        if (q == 0) acc = acc + w[i];
+                        else if (q <= d) acc = FMA(w[i], xa[i] - shift[a], acc);
+                        else acc = FMA(w[i] * (xa[i] - shift[a]), xb[i] - shift[b], acc);
+                    }
+                }
+                lane[l] = acc;
+            }
+            tl[c] = tree_inplace(lane, M_LANES);
+        }
+        sums[q] = tree_inplace(tl, Pc);
+    }
+    double sw = sums[0];
+    double e[MAX_D_MOM];
+    for (int k = 0; k < d; ++k) { e[k] = sums[1 + k] / sw; mean[k] = shift[k] + e[k]; }
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double v = FMA(-e[a], e[b], sums[1 + d + a * (a + 1) / 2 + b] / sw);
+            cov[(size_t)a * d + b] = v;
+            cov[(size_t)b * d + a] = v;
+        }
+    free(tl); free(sums);
+}
+
+/* canonical mean of the accept column (update_acceptance_rate!, particle.jl:466-468): tiles of 128 consecutive particles
+ * (one per lane), adjacent-pair tree over the lanes, then over tiles -- the order the mutation kernel's epilogue produces */
 ORC_API double orc_mean_accept(const double *cloud, i64 N, int d)
 {
-    return orc_canon_sum(COL(cloud, N, C_ACCEPT(d)), N) / (double)N;
+    return orc_canon_sum_generic(COL(cloud, N, C_ACCEPT(d)), N, 128, 1) / (double)N;
 }
 
 /* Lower Cholesky, row by row; returns 0 or (1 + failing row) if not positive definite
@@ -1256,6 +1296,9 @@ ORC_API int orc_stage(const orc_model *m, double *cloud, double *scratch /* N*(d
     io->sum_w = out[0]; io->ess = out[1];
     if (st) { io->status = 1; return 1; }
     io->resampled = 0;
+    /* shift of the one-pass moments: the parameter vector of particle 0 BEFORE selection */
+    double shift[MAX_D];
+    for (int k = 0; k < d; ++k) shift[k] = COL(cloud, N, k)[0];
     if (io->ess < io->threshold_ratio * (double)N) {
         double *wn = (double *)malloc(sizeof(double) * (size_t)N);
         i64 *idx = (i64 *)malloc(sizeof(i64) * (size_t)N);
@@ -1271,7 +1314,7 @@ ORC_API int orc_stage(const orc_model *m, double *cloud, double *scratch /* N*(d
     io->c = orc_update_c(io->c, io->accept, io->target);
     double *mean = mean_out ? mean_out : (double *)malloc(sizeof(double) * (size_t)d);
     double *cov = cov_out ? cov_out : (double *)malloc(sizeof(double) * (size_t)d * d);
-    orc_moments(cloud, N, d, mean, cov);
+    orc_moments_shifted(cloud, N, d, shift, mean, cov);
     int n_free = 0; int freeidx[MAX_D];
     for (int k = 0; k < d; ++k) if (!m->fixed[k]) freeidx[n_free++] = k;
     double mean_fr[MAX_D];

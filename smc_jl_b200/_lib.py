@@ -83,6 +83,10 @@ def _load():
         "smcb200_resample_weights": (i32, [vp, vp, i64, i32, u64, u32, d, vp, vp]),
         "smcb200_resample_weights_n": (i32, [vp, vp, i64, i64, i32, u64, u32, d, vp, vp]),
         "smcb200_moments": (i32, [vp, vp, vp]),
+        "smcb200_moments_onepass": (i32, [vp, vp, vp]),
+        "smcb200_run_stages": (i32, [vp, C.POINTER(StageConfig), C.POINTER(StageState), vp, i32, i32, i32, vp, vp, i64,
+                                     C.POINTER(StageResult), C.POINTER(i32)]),
+        "smcb200_fp64_peak": (i32, [vp, i32, pd]),
         "smcb200_mutate": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, d, d, d, d, i32, i32, u64, u32, pd]),
         "smcb200_stage": (i32, [vp, C.POINTER(StageConfig), C.POINTER(StageState), vp, i32, vp, vp, C.POINTER(StageResult)]),
         "smcb200_stage_host": (i32, [vp, vp, i64, C.POINTER(StageConfig), C.POINTER(StageState), vp, i32,

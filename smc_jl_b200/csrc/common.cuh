@@ -22,10 +22,25 @@ constexpr int DMAX = 32;               // max n_para with a device mutation kern
 constexpr int NBMAX = 8;               // max n_blocks
 constexpr int PACKMAX = DMAX * (DMAX + 1) / 2;
 constexpr int EQMAX = 8;
-constexpr int MB_NQ = 640;             // doubles per rank and mailbox slot (>= PACKMAX + DMAX + 1)
+constexpr int HIST_RING = 4;         // device ring of weight-history column pairs in flight to the host
+constexpr int SUMMARY_RING = 512;
+constexpr int MB_NQ = 4096;             // doubles per rank and mailbox slot (>= PACKMAX + DMAX + 1)
 
-// device scalar slots (ctx->scal)
-enum { SC_S = 0, SC_Q = 1, SC_S2 = 2, SC_SRES = 3, SC_ACC = 4, SC_COUNT = 16 };
+// device scalar slots (ctx->scal): the stage's sums, decisions and the state carried from stage to stage.  Flags and
+// counters are stored as doubles so that ONE small copy brings the whole stage summary to the host.
+enum {
+    SC_S = 0, SC_Q = 1, SC_S2 = 2, SC_SRES = 3,   // sum w~, sum W^2, sum W, sum W / n_parts   (global)
+    SC_ACC = 4,                                    // sum of the accept column (global)
+    SC_ESS = 5, SC_RESAMPLE = 6,                   // ESS of this stage; 1.0 when ESS < threshold_ratio * n_parts
+    SC_PHI_N = 7, SC_PHI_N1 = 8,
+    SC_C = 9, SC_ACCEPT = 10,                      // step size in force; mean accept of the latest mutation
+    SC_ESS_PREV = 11, SC_PHI_PROP = 12, SC_J = 13, SC_RESAMPLED_LAST = 14,
+    SC_STATUS = 15,                                // 0 or an SMCB200_ERR_* code raised on the device (poisons the stage)
+    SC_EVALS = 16, SC_SWEEPS = 17,
+    SC_COUNT = 32
+};
+constexpr int CK = 3;                  // trial phi per sweep of the cooperative adaptive-phi solve: depth-2 bisection tree
+constexpr int ACC_TILE = 128;          // accept-column sum: one 128-particle tile per lane tree (R = 1), then the tile tree
 
 constexpr int ESS_K = 15;   // trial phi per pass of the adaptive-phi solve: the 15 nodes of a depth-4 bisection tree
 struct PhiState {           // adaptive-phi state machine, lives in device memory
@@ -74,16 +89,35 @@ struct ASConst {                // An-Schorfheide DSGE likelihood slot: 3 x T da
     const double* data;
     int32_t T, npre;
 };
+struct PeerCtx {                 // the NVLink mailboxes of this rank's communicator (world == 1: unused)
+    double* const* inbox;        // device table [world]: every rank's inbox
+    unsigned long long* epoch;   // device-resident exchange counter (identical on all ranks: same sequence of exchanges)
+    int* err;
+    int rank, world;
+};
 struct MutArgs {
     double phi_n, alpha;
     int n_mh_steps, n_blocks, n_free;
     uint64_t seed;
     uint32_t stage;
+    // fused stage: device-side inputs (all nullable)
+    const double* scal;        // SC_* scalars: phi_n = scal[SC_PHI_N], the kernel returns at once when scal[SC_STATUS] != 0,
+                               // rows are read from `alt_in` when scal[SC_RESAMPLE] != 0 (the stage resampled into it)
+    const double* alt_in;
+    // accept-column sum (update_acceptance_rate!, particle.jl:466-468) fused into the epilogue
+    double* acc_partials;      // [P_acc] tile sums (entries >= number of tiles stay zero)
+    int acc_P;
+    unsigned* acc_counter;
+    double* acc_out;           // shard-local root
+    double* acc_mean_out;      // nullable: global sum / n_global -> scal[SC_ACCEPT]
+    double n_global;
+    PeerCtx pc;                // cross-GPU exchange of the shard roots inside the kernel's last block
 };
 struct Ctx;
 struct KernelEntry {            // one likelihood functor's kernels + the constant-memory uploaders of its translation unit
     int kind, neq, k, stride, coef, sig, d;
     void (*mut[2][3][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][0 blocks / 1 single block / 2 single full block][mixture]
+    const void* mut_fn(int has_old, int blk, int mix) const { return (const void*)mut[has_old][blk][mix]; }
     void (*eval)(double*, int64_t, int);
     void (*draw)(double*, int64_t, int64_t, const double*, uint64_t, int, int*);   // initial_draw!
     int (*upload_model)(Ctx*);
@@ -99,23 +133,35 @@ struct Ctx {
     int64_t N_global = 0, N = 0, index0 = 0, per = 0;
     double* scal_loc = nullptr;    // [256] local roots before the cross-rank tree
     double* gath = nullptr;        // [world][256] gathered roots
-    double* rmax_g = nullptr;      // [world * per] running max of the global cumsum (world > 1)
-    double* bmax_g = nullptr;      // [world * nb_local]
+    double* bmax_g = nullptr;      // [world][nb_local] block maxima of the global cumsum's running max (world > 1)
+    double** rmax_tab = nullptr;   // device table [world]: every rank's running-max column (CUDA IPC)
+    const double* shift_base[2] = {nullptr, nullptr};   // rank 0's cloud buffers (moment shift = its particle 0)
+    int64_t n_rank0 = 0;
     // small-reduction mailboxes: every rank owns an inbox [2 parities][world][MB_NQ] doubles + [2][world] epoch flags that
     // its peers write directly over NVLink (CUDA IPC mappings); see k_peer_exchange
     double* mbox = nullptr;
     double** mbox_tab = nullptr;   // device table [world]: every rank's inbox
     void* mbox_open[16] = {};      // opened peer mappings (host)
-    unsigned long long mb_epoch = 0;
+    unsigned long long* mb_epoch_dev = nullptr;   // device-resident exchange counter (kernels exchange without the host)
     int* mb_err = nullptr;         // device flag: a peer never showed up (time-out)
     double** peer_tab = nullptr;   // device table [2][world] of peers' cloud buffers (CUDA IPC)
     int64_t* peer_cnt = nullptr;   // device [world] particles held by each rank
-    void* ipc_open[2][16] = {};    // opened peer mappings (host)
+    void* ipc_open[3][16] = {};    // opened peer mappings (host): cloud buffer 0 / 1, running-max column
     int d = 0;
     // device buffers
     double* cloud[2] = {nullptr, nullptr};
     int cur = 0;
     double* tmp = nullptr;         // N
+    double* hist_scr = nullptr;    // [HIST_RING][2][N] incremental / normalised weight columns of recent stages
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t hist_ready[8]{}, hist_copied[8]{};
+    double* acc_partials = nullptr; int acc_P = 0;   // accept-column tile sums
+    double* m1p_partials = nullptr; size_t m1p_len = 0; int m1p_P = 0;   // one-pass moments: [1 + d + E][P_chunks]
+    double* m1p_sums = nullptr;    // [1 + d + E] shard-local roots, then global
+    int coop_blocks_per_sm = 0;    // occupancy of k_correct_coop (queried once)
+    int sm_count = 0;
+    double* coop_partials = nullptr; size_t coop_partials_len = 0;
+    double* h_summary = nullptr;   // pinned ring of stage summaries [SUMMARY_RING][SC_COUNT]
     double* rmax = nullptr;        // N   running max of the cumsum
     int64_t* idx = nullptr;        // N
     double* partials = nullptr;    // tile partial sums, weight-type orders  [6][P_w]
@@ -183,7 +229,8 @@ constexpr int MUT_MINB20 = SMC_MUT_WARPS_PER_SM * 32 / MUT_THREADS;   // residen
 int mutate_upload_model(Ctx* ctx);                      // priors + likelihood slots -> __constant__
 int mutate_upload_proposal(Ctx* ctx, bool from_device); // MutConst -> __constant__
 bool mutate_supported(const Ctx* ctx, bool has_old);
-int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage);
+int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage, bool fused);
+PeerCtx peer_ctx(const Ctx* ctx);
 int evaluate_launch(Ctx* ctx, int mode);
 int initial_draw_launch(Ctx* ctx, const double* fixed_values_dev, uint64_t seed, int max_tries, int* n_failed_dev);
 

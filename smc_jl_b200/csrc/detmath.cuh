@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cmath>
 
+#include "normal_table.h"
+
 #if defined(__CUDACC__)
 #define SMC_HD __host__ __device__ __forceinline__
 #else
@@ -172,11 +174,8 @@ struct u32x4 { uint32_t x, y, z, w; };
 
 SMC_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
 {
-#if defined(__CUDA_ARCH__)
-    lo = a * b; hi = __umulhi(a, b);
-#else
-    const uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
-#endif
+    const uint64_t p = (uint64_t)a * b;      // one IMAD.WIDE.U32 on the device
+    lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
 }
 
 SMC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
@@ -220,13 +219,16 @@ SMC_HD void normal_pair(u32x4 r, double& z0, double& z1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Proposal normals: FOUR N(0,1) variates from ONE Philox block, Box-Muller evaluated in binary32.
-// The random-walk proposal only needs a symmetric, well-distributed increment (the Metropolis ratio is
-// computed in binary64 from the point actually proposed), so the normals carry float precision: 32-bit
-// uniforms (|z| <= 6.76), a degree-7 division-free log, 3-term sin/cos kernels.  This halves the Philox
-// work and takes the log / sqrt / sincos chains off the FP64 pipe (~48 instead of ~98 instructions per
-// normal on sm_100a).  Every operation is an IEEE binary32 +,*,fma,sqrt or an exact integer step, so the
-// oracle reproduces the same bits.  (Exactly antisymmetric in the angle: z -> -z is measure-preserving.)
+// Proposal normals: FOUR N(0,1) variates from ONE Philox block, one 32-bit word each, by a table-driven inverse
+// normal CDF evaluated in binary32 (tools/make_normal_table.py writes the table and reports its accuracy:
+// max |z - Phi^-1| = 5e-7, |z| <= 6.34).  The random-walk proposal only needs a symmetric, well-distributed
+// increment (the Metropolis ratio is computed in binary64 from the point actually proposed), so the normals carry
+// float precision.  Word r: sign = bit 31; v = (r << 1) | 1 is odd, p = v / 2^33 in (0, 1/2); the binary32 image
+// f = (float)v selects the segment (exponent, top three mantissa bits) and the remaining 20 mantissa bits give
+// x in [1, 1.125); z = ((b3 x + b2) x + b1) x + b0 with three fma; the sign bit is XORed in, so the map is exactly
+// antisymmetric (z -> -z is measure preserving).  ~11 instructions per normal on sm_100a (the binary32 Box-Muller
+// it replaces took ~55) and every step is an exact integer operation or an IEEE binary32 conversion / fma, so the
+// oracle reproduces the same bits.
 // ---------------------------------------------------------------------------------------------
 SMC_HD float bits_to_float(uint32_t u)
 {
@@ -244,45 +246,29 @@ SMC_HD uint32_t float_to_bits(float x)
     uint32_t u; std::memcpy(&u, &x, 4); return u;
 #endif
 }
-SMC_HD void normal_pair_f32(uint32_t a, uint32_t b, double& z0, double& z1)
+constexpr int NORMAL_TAB_ROWS = SMC_NORMAL_TABLE_ROWS;
+static constexpr float normal_tab_host[4 * NORMAL_TAB_ROWS] = {SMC_NORMAL_TABLE_VALUES};
+#if defined(__CUDACC__)
+static __device__ __align__(16) const float normal_tab_dev[4 * NORMAL_TAB_ROWS] = {SMC_NORMAL_TABLE_VALUES};
+#endif
+// tab: [NORMAL_TAB_ROWS] rows of (b0, b1, b2, b3); 16-byte aligned (shared memory inside the mutation kernel)
+SMC_HD double normal_icdf(uint32_t r, const float4* tab)
 {
-    // radius: u in (0, 1], u = 2^k m with m in [sqrt(1/2), sqrt(2)), ln u = k ln2 + f q(f), f = m - 1
-    const float u = fmaf((float)a, 0x1p-32f, 0x1p-33f);
-    uint32_t ix = float_to_bits(u) + (0x3f800000u - 0x3f3504f3u);
-    const int k = (int)(ix >> 23) - 127;
-    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
-    const float f = bits_to_float(ix) - 1.0f;
-    float q = -0.10378583520650864f;
-    q = fmaf(q, f, 0.1633809357881546f);
-    q = fmaf(q, f, -0.1721244603395462f);
-    q = fmaf(q, f, 0.19884242117404938f);
-    q = fmaf(q, f, -0.24971559643745422f);
-    q = fmaf(q, f, 0.3333560824394226f);
-    q = fmaf(q, f, -0.500003457069397f);
-    q = fmaf(q, f, 0.9999999403953552f);
-    const float lnu = fmaf((float)k, 0.6931471805599453f, f * q);
-    const float rad = sqrtf(fmaxf(-2.0f * lnu, 0.0f));
-    // angle 2 pi b / 2^32: 3 octant bits + 29 fraction bits, kernels on [0, pi/4]
-    const uint32_t o = b >> 29;
-    float g = (float)(b & 0x1fffffffu) * 0x1p-29f;
-    if (o & 1u) g = 1.0f - g;
-    const float x = g * 0.7853981633974483f;
-    const float z = x * x;
-    const float s = fmaf(x * z, fmaf(z, fmaf(z, -0.0001958801003638655f, 0.008332748897373676f), -0.166666641831398f), x);
-    const float c = fmaf(z * z, fmaf(z, fmaf(z, 2.4581931938882917e-05f, -0.0013888553949072957f), 0.0416666679084301f),
-                         fmaf(-0.5f, z, 1.0f));
-    const float sp = (o & 1u) ? c : s;
-    const float cp = (o & 1u) ? s : c;
-    const uint32_t qd = o >> 1;
-    const float sn = (qd == 0u) ? sp : (qd == 1u) ? cp : (qd == 2u) ? -sp : -cp;
-    const float cs = (qd == 0u) ? cp : (qd == 1u) ? -sp : (qd == 2u) ? -cp : sp;
-    z0 = (double)(rad * cs);
-    z1 = (double)(rad * sn);
+    const uint32_t v = (r << 1) | 1u;
+#if defined(__CUDA_ARCH__)
+    const float f = __uint2float_rn(v);
+#else
+    const float f = (float)v;
+#endif
+    const uint32_t fb = float_to_bits(f);
+    const float4 c = tab[(fb >> 20) - (127u << 3)];
+    const float x = bits_to_float((fb & 0x000fffffu) | 0x3f800000u);
+    const float z = fmaf(fmaf(fmaf(c.w, x, c.z), x, c.y), x, c.x);
+    return (double)bits_to_float(float_to_bits(z) ^ (r & 0x80000000u));
 }
-SMC_HD void normal_quad(u32x4 r, double& z0, double& z1, double& z2, double& z3)
+SMC_HD void normal_quad(u32x4 r, const float4* tab, double& z0, double& z1, double& z2, double& z3)
 {
-    normal_pair_f32(r.x, r.y, z0, z1);
-    normal_pair_f32(r.z, r.w, z2, z3);
+    z0 = normal_icdf(r.x, tab); z1 = normal_icdf(r.y, tab); z2 = normal_icdf(r.z, tab); z3 = normal_icdf(r.w, tab);
 }
 
 // Lower Cholesky, row by row, explicit fma order.  Returns 0 or 1 + failing row.

@@ -9,7 +9,7 @@
 #include <cstring>
 #include <new>
 
-#include "kernels.cuh"
+#include "stage_kernels.cuh"
 
 using namespace smc;
 
@@ -68,12 +68,12 @@ constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601,
 static_assert(SL_ESS + 2 * ESS_K <= SL_COUNT, "scal_loc too small");
 // where a kernel should write shard-local roots, and the cross-rank tree that follows
 inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
-// cross-rank tree of nq shard-local roots (combine) or their [world][nq] layout (gather into c->gath): one
-// k_peer_exchange launch over the NVLink mailboxes
-int peer_exchange(Ctx* c, double* dst, const double* local_src, int nq, int combine)
+// cross-rank tree of nq shard-local roots (combine) or their [world][nq] layout (gather into dst): one
+// k_peer_exchange launch over the NVLink mailboxes; `flag` (device, nullable) predicates the launch
+int peer_exchange(Ctx* c, double* dst, const double* local_src, int nq, int combine, const double* flag = nullptr)
 {
-    if (nq > MB_NQ) { c->err = "peer_exchange: too many quantities"; return SMCB200_ERR_BAD_ARGUMENT; }
-    k_peer_exchange<<<1, 256, 0, c->stream>>>(local_src, nq, c->rank, c->world, c->mbox_tab, ++c->mb_epoch, combine, dst, c->mb_err);
+    if (nq > MB_NQ) { c->err = "peer_exchange: too many quantities"; return SMCB200_ERR_UNSUPPORTED; }
+    k_peer_exchange<<<1, 256, 0, c->stream>>>(local_src, nq, peer_ctx(c), combine, dst, flag);
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
@@ -89,11 +89,13 @@ void free_cloud(Ctx* c)
     cudaFree(c->cloud[0]); cudaFree(c->cloud[1]); cudaFree(c->tmp); cudaFree(c->rmax); cudaFree(c->idx);
     cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->ess_partials); c->ess_partials = nullptr; cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
     cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
-    for (int b = 0; b < 2; ++b)
+    cudaFree(c->hist_scr); cudaFree(c->acc_partials); cudaFree(c->m1p_partials); cudaFree(c->m1p_sums); cudaFree(c->coop_partials);
+    c->hist_scr = c->acc_partials = c->m1p_partials = c->m1p_sums = c->coop_partials = nullptr;
+    for (int b = 0; b < 3; ++b)
         for (int r = 0; r < 16; ++r)
             if (c->ipc_open[b][r]) { cudaIpcCloseMemHandle(c->ipc_open[b][r]); c->ipc_open[b][r] = nullptr; }
-    cudaFree(c->rmax_g); cudaFree(c->bmax_g); cudaFree(c->peer_tab); cudaFree(c->peer_cnt);
-    c->rmax_g = c->bmax_g = nullptr; c->peer_tab = nullptr; c->peer_cnt = nullptr;
+    cudaFree(c->bmax_g); cudaFree(c->peer_tab); cudaFree(c->peer_cnt); cudaFree(c->rmax_tab);
+    c->bmax_g = nullptr; c->peer_tab = nullptr; c->peer_cnt = nullptr; c->rmax_tab = nullptr;
     c->cloud[0] = c->cloud[1] = c->tmp = c->rmax = nullptr; c->idx = nullptr; c->partials = c->mpartials = nullptr;
     c->scan_blocktot = c->scan_blockoff = c->scan_levels = c->scan_bmax = nullptr; c->msum = c->csum = nullptr;
     c->scan_nb_cap = 0;
@@ -104,44 +106,89 @@ void free_cloud(Ctx* c)
 struct Tiles { int ntiles, P; };
 Tiles weight_tiles(int64_t n) { int nt = (int)((n + W_TILE - 1) / W_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles moment_tiles(int64_t n) { int nt = (int)((n + M_TILE - 1) / M_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+Tiles accept_tiles(int64_t n) { int nt = (int)((n + ACC_TILE - 1) / ACC_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+
+// cooperative grid of k_correct_coop for this shard: block b owns tpb consecutive tiles (tpb a power of two)
+struct CoopGeom { int grid, tpb, Pb; };
+CoopGeom coop_geom(const Ctx* c, int64_t n)
+{
+    const Tiles t = weight_tiles(n);
+    const int cap = (c->coop_blocks_per_sm > 0 ? c->coop_blocks_per_sm : 1) * (c->sm_count > 0 ? c->sm_count : 1);
+    int tpb = 1;
+    while ((t.ntiles + tpb - 1) / tpb > cap) tpb *= 2;
+    CoopGeom g;
+    g.tpb = tpb;
+    g.grid = (t.ntiles + tpb - 1) / tpb;
+    g.Pb = (t.P >= tpb) ? t.P / tpb : 1;
+    return g;
+}
 
 int sync(Ctx* c)
 {
     SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->world > 1) {           // a peer that never reached an exchange trips the device-side time-out
+        int e = 0;
+        SMC_CUDA(c, cudaMemcpy(&e, c->mb_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) { c->err = "a peer rank never reached a cross-GPU reduction (time-out)"; return SMCB200_ERR_NCCL; }
+    }
     return SMCB200_OK;
 }
 
-// ---- correction ---------------------------------------------------------------------------------
-int launch_correct(Ctx* c, double phi_n1, double phi_n, double pw, double lpod, double* inc_dev, double* normw_dev)
+// ---- correction (+ adaptive phi) --------------------------------------------------------------------
+struct CorrectLaunch {
+    double phi_n1 = 0, phi_n = 0, pw = 0, lpod = 0, threshold_ratio = 0;
+    int adaptive = 0, solve_only = 0, use_carry = 0;
+    const double* sched_dev = nullptr; int n_phi = 0; double tempering_target = 0;
+    double c_in = 0, accept_in = 0, ess_prev_in = 0, phi_prop_in = 0; long long j_in = 0; int resampled_last_in = 0;
+    double* inc_dev = nullptr; double* normw_dev = nullptr;
+};
+int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
 {
     const int d = c->d;
     double* cl = c->cloud[c->cur];
-    CorrArgs a;
-    a.phi_n1 = phi_n1; a.phi_n = phi_n; a.pw = pw; a.lpod = lpod;
-    a.mode = (pw == 0.0) ? 0 : (pw == 1.0 ? 1 : 2);
-    a.log_1m_pw = (a.mode == 2) ? det_log(1.0 - pw) : 0.0;
-    const Tiles t = weight_tiles(c->N);
-    double* w = cl + col_off(c->N, d + 4);
-    double* lo = local_out(c);
-    k_weights_a<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), w, w, inc_dev, c->N, a,
-                                                 c->partials, t.ntiles, t.P, c->counters, lo);
-    int st = reduce_ranks(c, c->scal + SC_S, lo + SC_S, 1); if (st) return st;
-    k_weights_b<<<t.ntiles, 256, 0, c->stream>>>(w, normw_dev, c->N, (double)c->N_global, 1,
-                                                 c->partials, t.ntiles, t.P, c->counters, c->scal, lo);
-    st = reduce_ranks(c, c->scal + SC_Q, lo + SC_Q, 2); if (st) return st;
-    c->launches += 2;
-    SMC_CUDA(c, cudaGetLastError());
+    const CoopGeom g = coop_geom(c, c->N);
+    CoopArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.ll = cl + col_off(c->N, d); a.old = cl + col_off(c->N, d + 2); a.w = cl + col_off(c->N, d + 4);
+    a.inc_out = L.inc_dev; a.normw_out = L.normw_dev;
+    a.N = c->N; a.n_global = (double)c->N_global;
+    a.ntiles = weight_tiles(c->N).ntiles; a.tpb = g.tpb; a.Pb = g.Pb;
+    a.corr.phi_n1 = L.phi_n1; a.corr.phi_n = L.phi_n; a.corr.pw = L.pw; a.corr.lpod = L.lpod;
+    a.corr.mode = (L.pw == 0.0) ? 0 : (L.pw == 1.0 ? 1 : 2);
+    a.corr.log_1m_pw = (a.corr.mode == 2) ? det_log(1.0 - L.pw) : 0.0;
+    a.threshold_ratio = L.threshold_ratio;
+    a.adaptive = L.adaptive; a.solve_only = L.solve_only; a.use_carry = L.use_carry;
+    a.sched = L.sched_dev; a.n_phi = L.n_phi; a.tempering_target = L.tempering_target;
+    a.c_in = L.c_in; a.accept_in = L.accept_in; a.ess_prev_in = L.ess_prev_in; a.phi_prop_in = L.phi_prop_in; a.j_in = L.j_in;
+    a.resampled_last_in = L.resampled_last_in;
+    a.partials = c->coop_partials; a.scal = c->scal; a.st = c->phi_state; a.pc = peer_ctx(c);
+    void* args[] = {&a};
+    SMC_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_correct_coop, dim3(g.grid), dim3(256), args, 0, c->stream));
+    c->launches += 1;
+    return SMCB200_OK;
+}
+
+int upload_schedule(Ctx* c, const double* sched, int n_phi)
+{
+    if (c->sched_cap < n_phi) {
+        cudaFree(c->sched_dev);
+        c->sched_dev = nullptr; c->sched_cap = 0;
+        SMC_CUDA(c, cudaMalloc(&c->sched_dev, sizeof(double) * n_phi));
+        c->sched_cap = n_phi;
+    }
+    SMC_CUDA(c, cudaMemcpyAsync(c->sched_dev, sched, sizeof(double) * n_phi, cudaMemcpyHostToDevice, c->stream));
     return SMCB200_OK;
 }
 
 // one multi-trial pass of compute_ESS: S_k, Q_k for the ESS_K trial phi in `trials` (device) -> c->ess_sq
-int launch_ess_multi(Ctx* c, double phi_n1, const double* trials_dev, const int* done_dev)
+int launch_ess_multi(Ctx* c, double phi_n1, const double* trials_dev)
 {
     const int d = c->d;
     double* cl = c->cloud[c->cur];
     const Tiles t = weight_tiles(c->N);
     k_ess_multi<<<t.ntiles, 256, 0, c->stream>>>(cl + col_off(c->N, d), cl + col_off(c->N, d + 2), cl + col_off(c->N, d + 4), c->N,
-                                                 phi_n1, trials_dev, done_dev, c->ess_partials, t.P);
+                                                 phi_n1, trials_dev, nullptr, c->ess_partials, t.P);
     k_tree_finalize<<<2 * ESS_K, 256, 0, c->stream>>>(c->ess_partials, t.ntiles, t.P, c->world > 1 ? c->scal_loc + SL_ESS : c->ess_sq);
     c->launches += 2;
     SMC_CUDA(c, cudaGetLastError());
@@ -164,6 +211,7 @@ int ensure_scan_buffers(Ctx* c, int nb)
 {
     if (nb <= c->scan_nb_cap) return SMCB200_OK;
     cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels); cudaFree(c->scan_bmax);
+    c->scan_blocktot = c->scan_blockoff = c->scan_levels = c->scan_bmax = nullptr; c->scan_nb_cap = 0;
     SMC_CUDA(c, cudaMalloc(&c->scan_blocktot, sizeof(double) * nb));
     SMC_CUDA(c, cudaMalloc(&c->scan_blockoff, sizeof(double) * nb));
     SMC_CUDA(c, cudaMalloc(&c->scan_levels, sizeof(double) * 2 * nb));
@@ -172,12 +220,20 @@ int ensure_scan_buffers(Ctx* c, int nb)
     return SMCB200_OK;
 }
 
+double systematic_offset(uint64_t seed, uint32_t stage, double u_override)
+{
+    if (u_override >= 0.0) return u_override;
+    const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
+    return u01(r.x, r.y);
+}
+
 // src: n weights on the device (div_n: use src/n_parts, the `normalized_weights/n_parts` of smc_main.jl:438);
-// rmax/craw/idx: device outputs.  `sres` = device slot receiving sum(weights) ("weights ./ sum(weights)").
-// Single-shard version (also serves the exported resample(weights) on host vectors).
+// rmax/craw/idx: device outputs.  `sres` = device slot holding sum(weights) ("weights ./ sum(weights)"); it is computed
+// here unless have_sres.  Single-shard version (also serves the exported resample(weights) on host vectors).
+// flag (device, nullable): every kernel returns at once when *flag == 0 (device-side resample decision).
 int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int method, uint64_t seed, uint32_t stage,
                             double u_override, double* rmax, double* craw, int64_t* idx, double* partials,
-                            unsigned* counter, double* sres, int64_t n_out = -1)
+                            unsigned* counter, double* sres, bool have_sres, const double* flag, int64_t n_out = -1)
 {
     if (n_out < 0) n_out = n;
     if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
@@ -188,95 +244,99 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
     if (st) return st;
     const Tiles t = weight_tiles(n);
     const double nd = (double)n;
-    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, n, nd, div_n, partials, t.ntiles, t.P, counter, sres);
-    k_scan<false><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, c->scan_blocktot, nullptr,
-                                                              nullptr, nullptr, nullptr);
-    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT);
-    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, g.nb, nullptr, 1, 0, c->scan_blockoff);
-    k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
-                                                             craw, c->scan_bmax);
-    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, g.nb);
-    double u = u_override;
-    if (!(u >= 0.0)) {
-        const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
-        u = u01(r.x, r.y);
+    if (!have_sres) {
+        k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, n, nd, div_n, partials, t.ntiles, t.P, counter, sres, flag);
+        c->launches += 1;
     }
-    k_search<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(rmax, c->scan_bmax, g.nb, g.B, n, n_out, 0, method, seed, stage,
-                                                                     u, (double)n_out, idx);
-    c->launches += 7;
+    k_scan<false><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, c->scan_blocktot, nullptr,
+                                                              nullptr, nullptr, nullptr, flag);
+    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT, flag);
+    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, g.nb, nullptr, 1, 0, c->scan_blockoff, flag);
+    k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
+                                                             craw, c->scan_bmax, flag);
+    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, g.nb, flag);
+    const double u = systematic_offset(seed, stage, u_override);
+    k_search<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(rmax, nullptr, 0, c->scan_bmax, g.nb, g.B, n, n_out, 0, method, seed,
+                                                                     stage, u, (double)n_out, idx, flag);
+    c->launches += 6;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
 }
 
-// Selection on the sharded cloud: canonical global cumsum (shard totals exchanged), ancestors of this
-// shard's outputs searched in the all-gathered running max, rows pulled from the owners over NVLink.
-int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override)
+// Selection on the sharded cloud: canonical global cumsum (shard roots exchanged), this shard's running maxima stay in
+// place; the per-block maxima of all shards are gathered through the mailboxes (a few hundred doubles), every rank
+// searches its own outputs' ancestors in them and then in the OWNER's running-max block over NVLink, and the rows are
+// pulled from the owners the same way (k_gather_peer).  No collective library call, so the whole chain can be
+// predicated on the device-side resample flag.
+int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override, bool fused, double* nw_hist)
 {
     if (method != SMCB200_RESAMPLE_SYSTEMATIC && method != SMCB200_RESAMPLE_MULTINOMIAL)
         return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
-    NcclApi* nc = nccl_api();
     const int d = c->d;
     double* cl = c->cloud[c->cur];
     const double* src = cl + col_off(c->N, d + 4);
+    const double* flag = fused ? c->scal + SC_RESAMPLE : nullptr;
     const int B = SCAN_TILE;
     const int nb = (int)(c->per / B);                 // blocks of this shard's full subtree
+    if (nb > MB_NQ) return fail(c, SMCB200_ERR_UNSUPPORTED, "multi-GPU selection supports up to 2^24 particles per GPU");
     int st = ensure_scan_buffers(c, nb); if (st) return st;
     const Tiles t = weight_tiles(c->N);
     const double nd = (double)c->N_global;
-    // sum(weights) over all shards
-    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, c->N, nd, 1, c->partials + (size_t)3 * t.P, t.ntiles, t.P, c->counters + 2,
-                                              c->scal_loc + SC_SRES);
-    st = reduce_ranks(c, c->scal + SC_SRES, c->scal_loc + SC_SRES, 1); if (st) return st;
-    k_scan<false><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, c->scan_blocktot, nullptr,
-                                                            nullptr, nullptr, nullptr);
-    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT);
-    st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_ROOT, 1, 0); if (st) return st;
-    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, nb, c->gath, c->world, c->rank, c->scan_blockoff);
-    double* rloc = c->rmax_g + (size_t)c->rank * c->per;
-    double* bloc = c->bmax_g + (size_t)c->rank * nb;
-    k_scan<true><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, nullptr, c->scan_blockoff,
-                                                           rloc, nullptr, bloc);
-    k_prefix_max<<<1, 256, 0, c->stream>>>(bloc, nb);
-    // shard maxima -> carry of the lower ranks, then every rank gets the global running max + block maxima
-    SMC_CUDA(c, cudaMemcpyAsync(c->scal_loc + SL_SCAN_MAX, bloc + nb - 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_MAX, 1, 0); if (st) return st;
-    k_apply_rank_carry<<<1, 256, 0, c->stream>>>(bloc, nb, c->gath, c->rank);
-    SMC_NCCL(c, nc->AllGather(bloc, c->bmax_g, (size_t)nb, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
-    SMC_NCCL(c, nc->AllGather(rloc, c->rmax_g, (size_t)c->per, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
-    double u = u_override;
-    if (!(u >= 0.0)) {
-        const u32x4 r = rng4(seed, 0u, stage, 0u, PURP_RESAMPLE);
-        u = u01(r.x, r.y);
+    if (!fused) {      // sum(weights) over all shards (the fused stage has it from the correction kernel)
+        k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, c->N, nd, 1, c->partials + (size_t)3 * t.P, t.ntiles, t.P, c->counters + 2,
+                                                  c->scal_loc + SC_SRES);
+        c->launches += 1;
+        st = reduce_ranks(c, c->scal + SC_SRES, c->scal_loc + SC_SRES, 1); if (st) return st;
     }
-    k_search<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->rmax_g, c->bmax_g, nb * c->world, B, c->N_global, c->N,
-                                                                    c->index0, method, seed, stage, u, nd, c->idx);
-    k_gather_peer<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->peer_tab + (size_t)c->cur * c->world, c->peer_cnt, c->per,
-                                                                         c->cloud[c->cur ^ 1], c->idx, c->N, d + 4, d + 4);
-    c->launches += 9;
+    k_scan<false><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, c->scan_blocktot, nullptr,
+                                                            nullptr, nullptr, nullptr, flag);
+    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT, flag);
+    st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_ROOT, 1, 0, flag); if (st) return st;
+    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, nb, c->gath, c->world, c->rank, c->scan_blockoff, flag);
+    k_scan<true><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, nullptr, c->scan_blockoff,
+                                                           c->rmax, nullptr, c->scan_bmax, flag);
+    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, nb, flag);
+    // block maxima of every shard -> [world][nb]; the maxima of the lower ranks are folded in afterwards
+    st = peer_exchange(c, c->bmax_g, c->scan_bmax, nb, 0, flag); if (st) return st;
+    k_fix_rank_carry<<<1, 256, 0, c->stream>>>(c->bmax_g, nb, c->world, flag);
+    const double u = systematic_offset(seed, stage, u_override);
+    k_search<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(nullptr, c->rmax_tab, nb, c->bmax_g, nb * c->world, B, c->N_global, c->N,
+                                                                    c->index0, method, seed, stage, u, nd, c->idx, flag);
+    double* dst = c->cloud[c->cur ^ 1];
+    k_gather_peer<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->peer_tab + (size_t)c->cur * c->world, c->peer_cnt, c->per, dst,
+                                                                         c->idx, c->N, d + 4,
+                                                                         fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4),
+                                                                         nw_hist, flag);
+    c->launches += 8;
     SMC_CUDA(c, cudaGetLastError());
-    c->cur ^= 1;
+    if (!fused) c->cur ^= 1;
     return SMCB200_OK;
 }
 
-int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override)
+// fused: the kernels are predicated on scal[SC_RESAMPLE], sum(weights) comes from the correction kernel, the rows are
+// gathered into the other buffer and the weights are reset in the current one (the buffers do not flip: the moments and
+// mutation kernels pick the gathered rows up from there and mutation writes the current buffer again).
+int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, double u_override, bool fused, double* nw_hist)
 {
-    if (c->world > 1) return launch_resample_cloud_sharded(c, method, seed, stage, u_override);
+    if (c->world > 1) return launch_resample_cloud_sharded(c, method, seed, stage, u_override, fused, nw_hist);
     const int d = c->d;
     double* cl = c->cloud[c->cur];
+    double* dst = c->cloud[c->cur ^ 1];
     const Tiles t = weight_tiles(c->N);
+    const double* flag = fused ? c->scal + SC_RESAMPLE : nullptr;
     int st = launch_resample_indices(c, cl + col_off(c->N, d + 4), 1, c->N, method, seed, stage, u_override, c->rmax, nullptr,
-                                     c->idx, c->partials + (size_t)3 * t.P, c->counters + 2, c->scal + SC_SRES);
+                                     c->idx, c->partials + (size_t)3 * t.P, c->counters + 2, c->scal + SC_SRES, fused, flag);
     if (st) return st;
-    k_gather<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(cl, c->cloud[c->cur ^ 1], c->idx, c->N, d + 4, d + 4);
+    k_gather<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(cl, dst, c->idx, c->N, d + 4,
+                                                                    fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4),
+                                                                    nw_hist, flag);
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
-    c->cur ^= 1;
+    if (!fused) c->cur ^= 1;
     return SMCB200_OK;
 }
 
-// ---- moments ------------------------------------------------------------------------------------------
-Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
-
+// ---- moments (two-pass form of the reference: the exported weighted_mean / weighted_cov) -----------------------
 template <int D>
 int launch_m2(Ctx* c, const double* cl, double* partials, const Tiles& t)
 {
@@ -306,17 +366,9 @@ int launch_moments(Ctx* c)
     switch (d) {
     case 2: st = launch_m2<2>(c, cl, part, tc); break;
     case 3: st = launch_m2<3>(c, cl, part, tc); break;
-    case 4: st = launch_m2<4>(c, cl, part, tc); break;
-    case 5: st = launch_m2<5>(c, cl, part, tc); break;
-    case 6: st = launch_m2<6>(c, cl, part, tc); break;
-    case 8: st = launch_m2<8>(c, cl, part, tc); break;
     case 9: st = launch_m2<9>(c, cl, part, tc); break;
-    case 10: st = launch_m2<10>(c, cl, part, tc); break;
-    case 12: st = launch_m2<12>(c, cl, part, tc); break;
     case 16: st = launch_m2<16>(c, cl, part, tc); break;
     case 20: st = launch_m2<20>(c, cl, part, tc); break;
-    case 24: st = launch_m2<24>(c, cl, part, tc); break;
-    case 32: st = launch_m2<32>(c, cl, part, tc); break;
     default: k_moments2_generic<<<tc.ntiles, 128, 0, c->stream>>>(cl, c->N, d, c->msum, part, tc.P); break;
     }
     if (st) return st;
@@ -325,6 +377,61 @@ int launch_moments(Ctx* c)
     if (tc.ntiles < tc.P || t.ntiles < t.P)
         SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * c->partials_len_m, c->stream));
     c->launches += 4;
+    SMC_CUDA(c, cudaGetLastError());
+    return SMCB200_OK;
+}
+
+// ---- one-pass moments + step size + proposal factor (the fused stage) ---------------------------------------------
+template <int D>
+int launch_m1p(Ctx* c, const double* x0, const double* x1, const double* wcol, const double* shift, int64_t stride, const Tiles& t)
+{
+    constexpr size_t stage = (size_t)(D + 1) * M2_CH, red = (size_t)(1 + D + D * (D + 1) / 2) * 33;
+    constexpr size_t smem = sizeof(double) * (stage > red ? stage : red);
+    static bool configured = false;
+    if (!configured) {
+        if (smem > 48 * 1024)
+            SMC_CUDA(c, cudaFuncSetAttribute(k_moments1p<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMC_CUDA(c, cudaFuncSetAttribute(k_moments1p<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    k_moments1p<D><<<t.ntiles, 32 * M1P_G, smem, c->stream>>>(x0, x1, wcol, c->N, c->scal, shift, stride, c->m1p_partials, t.P);
+    return SMCB200_OK;
+}
+
+int launch_moments_prepare(Ctx* c, const BlockSpec& bs, double target)
+{
+    const int d = c->d;
+    const double* x0 = c->cloud[c->cur];
+    const double* x1 = c->cloud[c->cur ^ 1];
+    const double* wcol = x0 + col_off(c->N, d + 4);
+    // shift = parameter vector of global particle 0 in the (pre-selection) current buffer of rank 0
+    const double* shift = (c->world > 1) ? c->shift_base[c->cur] : x0;
+    const int64_t stride = (c->world > 1) ? c->n_rank0 : c->N;
+    const Tiles t = chunk_tiles(c->N);
+    const int E = d * (d + 1) / 2, nq = 1 + d + E;
+    int st = SMCB200_OK;
+    switch (d) {
+    case 2: st = launch_m1p<2>(c, x0, x1, wcol, shift, stride, t); break;
+    case 3: st = launch_m1p<3>(c, x0, x1, wcol, shift, stride, t); break;
+    case 4: st = launch_m1p<4>(c, x0, x1, wcol, shift, stride, t); break;
+    case 5: st = launch_m1p<5>(c, x0, x1, wcol, shift, stride, t); break;
+    case 6: st = launch_m1p<6>(c, x0, x1, wcol, shift, stride, t); break;
+    case 8: st = launch_m1p<8>(c, x0, x1, wcol, shift, stride, t); break;
+    case 9: st = launch_m1p<9>(c, x0, x1, wcol, shift, stride, t); break;
+    case 10: st = launch_m1p<10>(c, x0, x1, wcol, shift, stride, t); break;
+    case 12: st = launch_m1p<12>(c, x0, x1, wcol, shift, stride, t); break;
+    case 16: st = launch_m1p<16>(c, x0, x1, wcol, shift, stride, t); break;
+    case 20: st = launch_m1p<20>(c, x0, x1, wcol, shift, stride, t); break;
+    case 24: st = launch_m1p<24>(c, x0, x1, wcol, shift, stride, t); break;
+    case 32: st = launch_m1p<32>(c, x0, x1, wcol, shift, stride, t); break;
+    default:
+        k_moments1p_generic<<<t.ntiles, 128, 0, c->stream>>>(x0, x1, wcol, c->N, d, c->scal, shift, stride, c->m1p_partials, t.P);
+        break;
+    }
+    if (st) return st;
+    k_moments_finish<<<nq, 256, 0, c->stream>>>(c->m1p_partials, t.P, nq, c->m1p_sums, c->m1p_sums + (1 + DMAX + PACKMAX), c->counters + 6,
+                                                peer_ctx(c), shift, stride, bs, target, c->scal, c->mutc_dev);
+    c->launches += 2;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
 }
@@ -383,14 +490,99 @@ int check_ready(Ctx* c, bool need_lik)
     return SMCB200_OK;
 }
 
-int mean_accept(Ctx* c)
+// device temporaries of one call, released on every exit path
+struct DevTemps {
+    std::vector<void*> p;
+    ~DevTemps() { for (void* q : p) cudaFree(q); }
+    template <class T> cudaError_t alloc(T** out, size_t n) { cudaError_t e = cudaMalloc(out, sizeof(T) * (n ? n : 1)); if (e == cudaSuccess) p.push_back(*out); return e; }
+};
+
+// ---- one stage, enqueued without any host synchronisation ---------------------------------------------------------------
+struct StageLaunch {
+    const smcb200_stage_config* cfg;
+    double phi_n1, phi_n;
+    uint32_t stage;
+    double c, accept, ess_prev, phi_prop; long long j; int resampled_last;
+    bool use_carry;
+    int n_phi;                 // adaptive: schedule already on the device (c->sched_dev)
+    int hist_slot;             // -1: no weight-history columns
+    bool time_phases;
+};
+
+int stage_enqueue(Ctx* c, const StageLaunch& L)
 {
-    const Tiles t = weight_tiles(c->N);
-    k_colsum<<<t.ntiles, 256, 0, c->stream>>>(c->cloud[c->cur] + col_off(c->N, c->d + 3), c->N, 1.0, 0,
-                                              c->partials + (size_t)4 * t.P, t.ntiles, t.P, c->counters + 3, local_out(c) + SC_ACC);
-    c->launches += 1;
-    SMC_CUDA(c, cudaGetLastError());
-    return reduce_ranks(c, c->scal + SC_ACC, c->scal_loc + SC_ACC, 1);
+    const smcb200_stage_config* cfg = L.cfg;
+    const int d = c->d;
+    double* inc_dev = nullptr; double* nw_dev = nullptr;
+    if (L.hist_slot >= 0) {
+        inc_dev = c->hist_scr + (size_t)L.hist_slot * 2 * c->N;
+        nw_dev = inc_dev + c->N;
+    }
+    // ---- adaptive phi + correction + ESS + resample decision: one cooperative kernel --------------------------
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    CorrectLaunch cl;
+    cl.phi_n1 = L.phi_n1; cl.phi_n = L.phi_n; cl.pw = cfg->prior_weight; cl.lpod = cfg->log_prob_old_data;
+    cl.threshold_ratio = cfg->threshold_ratio; cl.adaptive = cfg->adaptive; cl.use_carry = L.use_carry ? 1 : 0;
+    cl.sched_dev = c->sched_dev; cl.n_phi = L.n_phi; cl.tempering_target = cfg->tempering_target;
+    cl.c_in = L.c; cl.accept_in = L.accept; cl.ess_prev_in = L.ess_prev; cl.phi_prop_in = L.phi_prop; cl.j_in = L.j;
+    cl.resampled_last_in = L.resampled_last;
+    cl.inc_dev = inc_dev; cl.normw_dev = nw_dev;
+    int st = launch_correct_coop(c, cl); if (st) return st;
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    // ---- selection, predicated on the device-side decision ------------------------------------------------------
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    st = launch_resample_cloud(c, cfg->resample_method, cfg->seed, L.stage, -1.0, true, nw_dev); if (st) return st;
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    if (L.hist_slot >= 0) SMC_CUDA(c, cudaEventRecord(c->hist_ready[L.hist_slot], c->stream));
+    // ---- moments, step size, proposal factor ---------------------------------------------------------------------
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    int perm[DMAX], sizes[NBMAX], ball[DMAX];
+    generate_blocks(c->n_free, cfg->n_blocks, cfg->seed, L.stage, perm, sizes);
+    for (int a = 0; a < c->n_free; ++a) ball[a] = c->free_idx[perm[a]];
+    BlockSpec bs;
+    st = make_blockspec(c, cfg->n_blocks, sizes, ball, &bs); if (st) return st;
+    st = launch_moments_prepare(c, bs, cfg->target); if (st) return st;
+    c->mutc_host->n_blocks = cfg->n_blocks;
+    st = mutate_upload_proposal(c, true); if (st) return st;
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    // ---- mutation (+ mean accept) -------------------------------------------------------------------------------
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    st = mutate_launch(c, 0.0, cfg->alpha, cfg->n_mh_steps, cfg->has_old_data != 0, cfg->seed, L.stage, true); if (st) return st;
+    if (L.time_phases) SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+    (void)d;
+    return SMCB200_OK;
+}
+
+int check_stage_cfg(Ctx* c, const smcb200_stage_config* cfg)
+{
+    if (!(cfg->alpha >= 0.0 && cfg->alpha <= 1.0)) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "alpha must be within [0, 1]");
+    if (!(cfg->prior_weight >= 0.0 && cfg->prior_weight <= 1.0))
+        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
+    if (cfg->n_blocks < 1 || cfg->n_blocks > NBMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_blocks must be in 1..8");
+    if (cfg->n_mh_steps < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "n_mh_steps must be >= 1");
+    if (cfg->resample_method != SMCB200_RESAMPLE_SYSTEMATIC && cfg->resample_method != SMCB200_RESAMPLE_MULTINOMIAL)
+        return fail(c, SMCB200_ERR_BAD_RESAMPLER, "Invalid resampler in SMC. Options are :systematic or :multinomial");
+    if (!mutate_supported(c, cfg->has_old_data != 0)) return fail(c, SMCB200_ERR_UNSUPPORTED, "no device mutation kernel for this likelihood / n_para");
+    return SMCB200_OK;
+}
+
+// stage summary (pinned host copy of the device scalars) -> result / state
+int summary_to_result(Ctx* c, const double* h, const smcb200_stage_config* cfg, smcb200_stage_state* state, smcb200_stage_result* res)
+{
+    std::memset(res, 0, sizeof(*res));
+    res->phi_n = h[SC_PHI_N]; res->ess = h[SC_ESS]; res->sum_weights = h[SC_S];
+    res->status = (int)h[SC_STATUS];
+    if (res->status == SMCB200_ERR_NAN_ESS) return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight.");
+    res->resampled = h[SC_RESAMPLE] != 0.0 ? 1 : 0;
+    res->c = h[SC_C]; res->accept = h[SC_ACCEPT];
+    if (cfg->adaptive) {
+        state->j = (int64_t)h[SC_J]; state->phi_prop = h[SC_PHI_PROP];
+        state->resampled_last_period = 0;
+    }
+    if (res->resampled) state->resampled_last_period = 1;
+    if (res->status) return fail(c, res->status, "proposal covariance is not positive definite");
+    state->c = res->c; state->accept = res->accept; state->ess_prev = res->ess;
+    return SMCB200_OK;
 }
 
 }  // namespace
@@ -449,6 +641,23 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     ok = ok && cudaMallocHost(&c->h_moments, sizeof(double) * (1 + DMAX + PACKMAX)) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&c->tev[i]) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < HIST_RING && ok; ++i) {
+        ok = cudaEventCreateWithFlags(&c->hist_ready[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->hist_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->mb_epoch_dev, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(c->mb_epoch_dev, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->mb_err, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->mb_err, 0, sizeof(int)) == cudaSuccess;
+    if (ok) {
+        int coop = 0;
+        ok = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop != 0;
+        ok = ok && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm, k_correct_coop, 256, 0) == cudaSuccess;
+        ok = ok && c->coop_blocks_per_sm >= 1;
+    }
     ok = ok && cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     if (!ok) { smcb200_destroy(c); return SMCB200_ERR_CUDA; }
@@ -470,7 +679,13 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
-    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev);
+    cudaFreeHost(c->h_summary);
+    for (int i = 0; i < HIST_RING; ++i) {
+        if (c->hist_ready[i]) cudaEventDestroy(c->hist_ready[i]);
+        if (c->hist_copied[i]) cudaEventDestroy(c->hist_copied[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -550,57 +765,74 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMalloc(&c->msum, sizeof(double) * (1 + DMAX)));
     SMC_CUDA(c, cudaMalloc(&c->csum, sizeof(double) * PACKMAX));
     SMC_CUDA(c, cudaMemset(c->cloud[0], 0, sizeof(double) * cols * c->N));
+    // fused-stage buffers: weight-history ring, accept-column tile sums, one-pass moment partials, cooperative-grid partials
+    SMC_CUDA(c, cudaMalloc(&c->hist_scr, sizeof(double) * (size_t)HIST_RING * 2 * c->N));
+    const Tiles ta = accept_tiles(c->N);
+    c->acc_P = ta.P;
+    SMC_CUDA(c, cudaMalloc(&c->acc_partials, sizeof(double) * ta.P));
+    SMC_CUDA(c, cudaMemset(c->acc_partials, 0, sizeof(double) * ta.P));
+    const size_t nq1 = (size_t)1 + n_para + E;
+    c->m1p_P = tch.P; c->m1p_len = nq1 * tch.P;
+    SMC_CUDA(c, cudaMalloc(&c->m1p_partials, sizeof(double) * c->m1p_len));
+    SMC_CUDA(c, cudaMemset(c->m1p_partials, 0, sizeof(double) * c->m1p_len));
+    SMC_CUDA(c, cudaMalloc(&c->m1p_sums, sizeof(double) * 2 * (1 + DMAX + PACKMAX)));
+    const CoopGeom cgm = coop_geom(c, c->N);
+    c->coop_partials_len = (size_t)((2 * CK > 3) ? 2 * CK : 3) * cgm.Pb;
+    SMC_CUDA(c, cudaMalloc(&c->coop_partials, sizeof(double) * c->coop_partials_len));
+    SMC_CUDA(c, cudaMemset(c->coop_partials, 0, sizeof(double) * c->coop_partials_len));
     c->cur = 0;
     if (c->world > 1) {
-        // peers' cloud buffers: exchange CUDA-IPC handles + shard sizes through the communicator
+        // peers' cloud buffers and running-max columns: exchange CUDA-IPC handles + shard sizes through the communicator
         NcclApi* nc = nccl_api();
         const int W = c->world;
-        struct Info { cudaIpcMemHandle_t h[2]; int64_t count; int64_t pad; };
-        Info mine, *all_dev = nullptr, *mine_dev = nullptr;
+        struct Info { cudaIpcMemHandle_t h[3]; int64_t count; int64_t pad; };
+        Info mine;
         std::vector<Info> all(W);
+        DevTemps tmp;
+        Info *all_dev = nullptr, *mine_dev = nullptr;
         SMC_CUDA(c, cudaIpcGetMemHandle(&mine.h[0], c->cloud[0]));
         SMC_CUDA(c, cudaIpcGetMemHandle(&mine.h[1], c->cloud[1]));
+        SMC_CUDA(c, cudaIpcGetMemHandle(&mine.h[2], c->rmax));
         mine.count = c->N; mine.pad = 0;
-        SMC_CUDA(c, cudaMalloc(&all_dev, sizeof(Info) * W));
-        SMC_CUDA(c, cudaMalloc(&mine_dev, sizeof(Info)));
+        SMC_CUDA(c, tmp.alloc(&all_dev, (size_t)W));
+        SMC_CUDA(c, tmp.alloc(&mine_dev, 1));
         SMC_CUDA(c, cudaMemcpyAsync(mine_dev, &mine, sizeof(Info), cudaMemcpyHostToDevice, c->stream));
         SMC_NCCL(c, nc->AllGather(mine_dev, all_dev, sizeof(Info), ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
         SMC_CUDA(c, cudaMemcpyAsync(all.data(), all_dev, sizeof(Info) * W, cudaMemcpyDeviceToHost, c->stream));
         SMC_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(all_dev); cudaFree(mine_dev);
-        std::vector<double*> tab(2 * W);
+        std::vector<double*> tab(3 * W);
         std::vector<int64_t> cnt(W);
         for (int r = 0; r < W; ++r) {
             cnt[r] = all[r].count;
-            for (int b = 0; b < 2; ++b) {
-                if (r == c->rank) { tab[b * W + r] = c->cloud[b]; continue; }
+            for (int b = 0; b < 3; ++b) {
+                if (r == c->rank) { tab[b * W + r] = (b < 2) ? c->cloud[b] : c->rmax; continue; }
                 void* p = nullptr;
                 SMC_CUDA(c, cudaIpcOpenMemHandle(&p, all[r].h[b], cudaIpcMemLazyEnablePeerAccess));
                 c->ipc_open[b][r] = p;
                 tab[b * W + r] = (double*)p;
             }
         }
+        c->shift_base[0] = tab[0]; c->shift_base[1] = tab[W]; c->n_rank0 = cnt[0];
         SMC_CUDA(c, cudaMalloc(&c->peer_tab, sizeof(double*) * 2 * W));
+        SMC_CUDA(c, cudaMalloc(&c->rmax_tab, sizeof(double*) * W));
         SMC_CUDA(c, cudaMalloc(&c->peer_cnt, sizeof(int64_t) * W));
         SMC_CUDA(c, cudaMemcpy(c->peer_tab, tab.data(), sizeof(double*) * 2 * W, cudaMemcpyHostToDevice));
+        SMC_CUDA(c, cudaMemcpy(c->rmax_tab, tab.data() + 2 * W, sizeof(double*) * W, cudaMemcpyHostToDevice));
         SMC_CUDA(c, cudaMemcpy(c->peer_cnt, cnt.data(), sizeof(int64_t) * W, cudaMemcpyHostToDevice));
         // reduction mailboxes (allocated once per context, zeroed: epoch 0 = nothing published)
         if (!c->mbox) {
             const size_t bytes = sizeof(double) * 2 * W * MB_NQ + sizeof(unsigned long long) * 2 * W;
             SMC_CUDA(c, cudaMalloc(&c->mbox, bytes));
             SMC_CUDA(c, cudaMemset(c->mbox, 0, bytes));
-            SMC_CUDA(c, cudaMalloc(&c->mb_err, sizeof(int)));
-            SMC_CUDA(c, cudaMemset(c->mb_err, 0, sizeof(int)));
             cudaIpcMemHandle_t mh, *mh_all_dev = nullptr, *mh_dev = nullptr;
             std::vector<cudaIpcMemHandle_t> mh_all(W);
             SMC_CUDA(c, cudaIpcGetMemHandle(&mh, c->mbox));
-            SMC_CUDA(c, cudaMalloc(&mh_all_dev, sizeof(mh) * W));
-            SMC_CUDA(c, cudaMalloc(&mh_dev, sizeof(mh)));
+            SMC_CUDA(c, tmp.alloc(&mh_all_dev, (size_t)W));
+            SMC_CUDA(c, tmp.alloc(&mh_dev, 1));
             SMC_CUDA(c, cudaMemcpyAsync(mh_dev, &mh, sizeof(mh), cudaMemcpyHostToDevice, c->stream));
             SMC_NCCL(c, nc->AllGather(mh_dev, mh_all_dev, sizeof(mh), ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
             SMC_CUDA(c, cudaMemcpyAsync(mh_all.data(), mh_all_dev, sizeof(mh) * W, cudaMemcpyDeviceToHost, c->stream));
             SMC_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(mh_all_dev); cudaFree(mh_dev);
             std::vector<double*> mt(W);
             for (int r = 0; r < W; ++r) {
                 if (r == c->rank) { mt[r] = c->mbox; continue; }
@@ -612,7 +844,6 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
             SMC_CUDA(c, cudaMalloc(&c->mbox_tab, sizeof(double*) * W));
             SMC_CUDA(c, cudaMemcpy(c->mbox_tab, mt.data(), sizeof(double*) * W, cudaMemcpyHostToDevice));
         }
-        SMC_CUDA(c, cudaMalloc(&c->rmax_g, sizeof(double) * (size_t)per * W));
         SMC_CUDA(c, cudaMalloc(&c->bmax_g, sizeof(double) * (size_t)(per / SCAN_TILE) * W));
     }
     return SMCB200_OK;
@@ -796,20 +1027,20 @@ int32_t smcb200_correct(smcb200_ctx* c, double phi_n1, double phi_n, double pw, 
     if (!(pw >= 0.0 && pw <= 1.0))
         return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
     cudaSetDevice(c->device);
-    double* inc_dev = inc_out ? c->tmp : nullptr;
-    double* nw_dev = normw_out ? c->rmax : nullptr;
+    CorrectLaunch L;
+    L.phi_n1 = phi_n1; L.phi_n = phi_n; L.pw = pw; L.lpod = lpod; L.threshold_ratio = 0.0;
+    L.inc_dev = inc_out ? c->hist_scr : nullptr;
+    L.normw_dev = normw_out ? c->hist_scr + c->N : nullptr;
     SMC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    st = launch_correct(c, phi_n1, phi_n, pw, lpod, inc_dev, nw_dev); if (st) return st;
+    st = launch_correct_coop(c, L); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
-    if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, inc_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
-    if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, nw_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, L.inc_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, L.normw_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
     st = sync(c); if (st) return st;
     cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
-    const double n = (double)c->N_global;
-    const double ess = (n * n) / c->h_scal[SC_Q];
-    if (out) { out[0] = c->h_scal[SC_S]; out[1] = ess; out[2] = c->h_scal[SC_S2]; }
-    if (ess != ess) return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight.");
+    if (out) { out[0] = c->h_scal[SC_S]; out[1] = c->h_scal[SC_ESS]; out[2] = c->h_scal[SC_S2]; }
+    if (c->h_scal[SC_ESS] != c->h_scal[SC_ESS]) return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight.");
     return SMCB200_OK;
 }
 
@@ -823,7 +1054,7 @@ int32_t smcb200_ess_at(smcb200_ctx* c, const double* phi, int32_t K, double phi_
         for (int k = 0; k < ESS_K; ++k) tr[k] = phi[(k0 + k < K) ? k0 + k : K - 1];
         // the trial vector travels through the state block's trial[] array
         SMC_CUDA(c, cudaMemcpyAsync(c->phi_state->trial, tr, sizeof(tr), cudaMemcpyHostToDevice, c->stream));
-        st = launch_ess_multi(c, phi_n1, c->phi_state->trial, nullptr); if (st) return st;
+        st = launch_ess_multi(c, phi_n1, c->phi_state->trial); if (st) return st;
         double sq[2 * ESS_K];
         SMC_CUDA(c, cudaMemcpyAsync(sq, c->ess_sq, sizeof(sq), cudaMemcpyDeviceToHost, c->stream));
         st = sync(c); if (st) return st;
@@ -838,39 +1069,18 @@ int32_t smcb200_solve_adaptive_phi(smcb200_ctx* c, const double* sched, int32_t 
     int st = check_ready(c, false); if (st) return st;
     if (!sched || n_phi < 1 || !j_io || !phi_prop_io || !phi_n_out) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
     cudaSetDevice(c->device);
-    if (c->sched_cap < n_phi) {
-        cudaFree(c->sched_dev);
-        SMC_CUDA(c, cudaMalloc(&c->sched_dev, sizeof(double) * n_phi));
-        c->sched_cap = n_phi;
-    }
-    SMC_CUDA(c, cudaMemcpyAsync(c->sched_dev, sched, sizeof(double) * n_phi, cudaMemcpyHostToDevice, c->stream));
-    PhiState* h = c->h_phi_state;
-    std::memset(h, 0, sizeof(*h));
-    const double n = (double)c->N_global;
-    h->ess_bar = resampled_last ? tempering_target * n : tempering_target * ess_prev;   // helpers.jl:14-20
-    h->phi_prop = *phi_prop_io; h->phi_cur = *phi_prop_io; h->phi_n1 = phi_n1; h->j = *j_io; h->n_phi = n_phi;
-    h->trial[0] = h->phi_prop;                               // phase 0 trials: phi_prop, then the next schedule points
-    for (int k = 1; k < ESS_K; ++k) {
-        long long idx = h->j - 1 + (k - 1);
-        if (idx > n_phi - 1) idx = n_phi - 1;
-        h->trial[k] = sched[idx];
-    }
-    SMC_CUDA(c, cudaMemcpyAsync(c->phi_state, h, sizeof(PhiState), cudaMemcpyHostToDevice, c->stream));
-    // every pass evaluates g() at ESS_K trial phi (one sweep over three columns) and advances the schedule walk /
-    // four bisection levels on the device; the host only polls the `done` flag between batches of passes
-    for (int round = 0; round < 64; ++round) {
-        for (int e = 0; e < (round == 0 ? 15 : 4); ++e) {     // 1 schedule-walk pass + ceil(53 / 4) bisection passes is the usual total
-            st = launch_ess_multi(c, phi_n1, c->phi_state->trial, &c->phi_state->done); if (st) return st;
-            k_phi_step_multi<<<1, 32, 0, c->stream>>>(c->phi_state, c->sched_dev, c->ess_sq);
-            c->launches += 1;
-        }
-        SMC_CUDA(c, cudaGetLastError());
-        SMC_CUDA(c, cudaMemcpyAsync(h, c->phi_state, sizeof(PhiState), cudaMemcpyDeviceToHost, c->stream));
-        st = sync(c); if (st) return st;
-        if (h->done) break;
-    }
-    if (!h->done) return fail(c, SMCB200_ERR_NAN_ESS, "solve_adaptive_phi did not converge (NaN ESS?)");
-    *j_io = h->j; *phi_prop_io = h->phi_prop; *phi_n_out = h->phi_n;
+    st = upload_schedule(c, sched, n_phi); if (st) return st;
+    // one cooperative launch: schedule walk + bisection on the device, no host polling
+    CorrectLaunch L;
+    L.phi_n1 = phi_n1; L.adaptive = 1; L.solve_only = 1; L.use_carry = 1;      // (carry: leaves c / accept / status alone)
+    L.sched_dev = c->sched_dev; L.n_phi = n_phi; L.tempering_target = tempering_target;
+    L.ess_prev_in = ess_prev; L.phi_prop_in = *phi_prop_io; L.j_in = *j_io; L.resampled_last_in = resampled_last;
+    st = launch_correct_coop(c, L); if (st) return st;
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    st = sync(c); if (st) return st;
+    const double phi_n = c->h_scal[SC_PHI_N];
+    if (!(phi_n == phi_n)) return fail(c, SMCB200_ERR_NAN_ESS, "solve_adaptive_phi did not converge (NaN ESS?)");
+    *j_io = (int64_t)c->h_scal[SC_J]; *phi_prop_io = c->h_scal[SC_PHI_PROP]; *phi_n_out = phi_n;
     return SMCB200_OK;
 }
 
@@ -879,7 +1089,7 @@ int32_t smcb200_resample(smcb200_ctx* c, int32_t method, uint64_t seed, uint32_t
     int st = check_ready(c, false); if (st) return st;
     cudaSetDevice(c->device);
     SMC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    st = launch_resample_cloud(c, method, seed, stage, u_override); if (st) return st;
+    st = launch_resample_cloud(c, method, seed, stage, u_override, false, nullptr); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     if (idx_out) SMC_CUDA(c, cudaMemcpyAsync(idx_out, c->idx, sizeof(int64_t) * c->N, cudaMemcpyDeviceToHost, c->stream));
     st = sync(c); if (st) return st;
@@ -898,24 +1108,24 @@ int32_t smcb200_resample_weights_n(smcb200_ctx* c, const double* weights, int64_
 {
     if (!c || !weights || n < 1 || n_out < 1 || !idx_out) return c ? fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument") : SMCB200_ERR_BAD_ARGUMENT;
     cudaSetDevice(c->device);
+    DevTemps tmp;                       // released on every return path
     double *w = nullptr, *r = nullptr, *cr = nullptr, *part = nullptr;
     int64_t* idx = nullptr;
     const Tiles t = weight_tiles(n);
-    SMC_CUDA(c, cudaMalloc(&w, sizeof(double) * n));
-    SMC_CUDA(c, cudaMalloc(&r, sizeof(double) * n));
-    SMC_CUDA(c, cudaMalloc(&cr, sizeof(double) * n));
-    SMC_CUDA(c, cudaMalloc(&idx, sizeof(int64_t) * n_out));
-    SMC_CUDA(c, cudaMalloc(&part, sizeof(double) * t.P));
+    SMC_CUDA(c, tmp.alloc(&w, (size_t)n));
+    SMC_CUDA(c, tmp.alloc(&r, (size_t)n));
+    SMC_CUDA(c, tmp.alloc(&cr, (size_t)n));
+    SMC_CUDA(c, tmp.alloc(&idx, (size_t)n_out));
+    SMC_CUDA(c, tmp.alloc(&part, (size_t)t.P));
     SMC_CUDA(c, cudaMemsetAsync(part, 0, sizeof(double) * t.P, c->stream));
     SMC_CUDA(c, cudaMemcpyAsync(w, weights, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    int st = launch_resample_indices(c, w, 0, n, method, seed, stage, u_override, r, cr, idx, part, c->counters + 4, c->scal + SC_SRES, n_out);
-    if (st == SMCB200_OK) {
-        cudaMemcpyAsync(idx_out, idx, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, c->stream);
-        if (cum_out) cudaMemcpyAsync(cum_out, cr, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
-        st = sync(c);
-    }
-    cudaFree(w); cudaFree(r); cudaFree(cr); cudaFree(idx); cudaFree(part);
-    return st;
+    int st = launch_resample_indices(c, w, 0, n, method, seed, stage, u_override, r, cr, idx, part, c->counters + 4, c->scal_loc + SC_SRES,
+                                     false, nullptr, n_out);
+    if (st) { cudaStreamSynchronize(c->stream); return st; }
+    SMC_CUDA(c, cudaMemcpyAsync(idx_out, idx, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, c->stream));
+    if (cum_out) SMC_CUDA(c, cudaMemcpyAsync(cum_out, cr, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SMCB200_OK;
 }
 
 int32_t smcb200_moments(smcb200_ctx* c, double* mean, double* cov)
@@ -936,6 +1146,47 @@ int32_t smcb200_moments(smcb200_ctx* c, double* mean, double* cov)
         for (int a = 0; a < d; ++a)
             for (int b = 0; b <= a; ++b) {
                 const double v = c->h_moments[1 + DMAX + a * (a + 1) / 2 + b] / sw;
+                cov[a * d + b] = v; cov[b * d + a] = v;
+            }
+    return SMCB200_OK;
+}
+
+int32_t smcb200_moments_onepass(smcb200_ctx* c, double* mean, double* cov)
+{
+    int st = check_ready(c, false); if (st) return st;
+    if (!c->have_params) return fail(c, SMCB200_ERR_NOT_READY, "no parameters: call smcb200_set_parameters first");
+    cudaSetDevice(c->device);
+    const int d = c->d, E = d * (d + 1) / 2, nq = 1 + d + E;
+    // the stage's moment pass on the current cloud (no selection pending, step size untouched): a one-block spec that
+    // holds every free parameter keeps k_moments_finish's proposal preparation well defined
+    int sizes[1] = {c->n_free}, ball[DMAX];
+    for (int a = 0; a < c->n_free; ++a) ball[a] = c->free_idx[a];
+    BlockSpec bs;
+    st = make_blockspec(c, 1, sizes, ball, &bs); if (st) return st;
+    double keep[SC_COUNT];
+    SMC_CUDA(c, cudaMemcpyAsync(keep, c->scal, sizeof(keep), cudaMemcpyDeviceToHost, c->stream));
+    SMC_CUDA(c, cudaStreamSynchronize(c->stream));
+    double z[SC_COUNT]; std::memcpy(z, keep, sizeof(z));
+    z[SC_RESAMPLE] = 0.0; z[SC_STATUS] = 0.0; z[SC_C] = 1.0; z[SC_ACCEPT] = 0.25;
+    SMC_CUDA(c, cudaMemcpyAsync(c->scal, z, sizeof(z), cudaMemcpyHostToDevice, c->stream));
+    SMC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    st = launch_moments_prepare(c, bs, 0.25); if (st) return st;
+    SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    double sums[1 + DMAX + PACKMAX], shift[DMAX];
+    SMC_CUDA(c, cudaMemcpyAsync(sums, c->m1p_sums + (1 + DMAX + PACKMAX), sizeof(double) * nq, cudaMemcpyDeviceToHost, c->stream));
+    const double* sb = (c->world > 1) ? c->shift_base[c->cur] : c->cloud[c->cur];
+    const int64_t stride = (c->world > 1) ? c->n_rank0 : c->N;
+    SMC_CUDA(c, cudaMemcpy2DAsync(shift, sizeof(double), sb, sizeof(double) * stride, sizeof(double), d, cudaMemcpyDeviceToHost, c->stream));
+    SMC_CUDA(c, cudaMemcpyAsync(c->scal, keep, sizeof(keep), cudaMemcpyHostToDevice, c->stream));
+    st = sync(c); if (st) return st;
+    cudaEventElapsedTime(&c->last_ms[2], c->ev[4], c->ev[5]);
+    const double sw = sums[0];
+    double e[DMAX];
+    for (int k = 0; k < d; ++k) { e[k] = sums[1 + k] / sw; if (mean) mean[k] = shift[k] + e[k]; }
+    if (cov)
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b <= a; ++b) {
+                const double v = fma(-e[a], e[b], sums[1 + d + a * (a + 1) / 2 + b] / sw);
                 cov[a * d + b] = v; cov[b * d + a] = v;
             }
     return SMCB200_OK;
@@ -966,13 +1217,12 @@ int32_t smcb200_mutate(smcb200_ctx* c, const double* mean_fr, const double* cov_
     if (st) return fail(c, SMCB200_ERR_NOT_POSDEF, "proposal covariance is not positive definite");
     st = mutate_upload_proposal(c, false); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    st = mutate_launch(c, phi_n, alpha, n_mh_steps, has_old != 0, seed, stage); if (st) return st;
+    st = mutate_launch(c, phi_n, alpha, n_mh_steps, has_old != 0, seed, stage, false); if (st) return st;
     SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-    st = mean_accept(c); if (st) return st;
     SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
     st = sync(c); if (st) return st;
     cudaEventElapsedTime(&c->last_ms[3], c->ev[6], c->ev[7]);
-    if (mean_accept_out) *mean_accept_out = c->h_scal[SC_ACC] / (double)c->N_global;
+    if (mean_accept_out) *mean_accept_out = c->h_scal[SC_ACCEPT];
     return SMCB200_OK;
 }
 
@@ -981,80 +1231,98 @@ int32_t smcb200_stage(smcb200_ctx* c, const smcb200_stage_config* cfg, smcb200_s
 {
     int st = check_ready(c, true); if (st) return st;
     if (!cfg || !state || !res) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "null argument");
-    if (!(cfg->alpha >= 0.0 && cfg->alpha <= 1.0)) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "alpha must be within [0, 1]");
-    if (!(cfg->prior_weight >= 0.0 && cfg->prior_weight <= 1.0))
-        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "The keyword tempered_update_prior_weight must be within the interval [0, 1]");
     cudaSetDevice(c->device);
     std::memset(res, 0, sizeof(*res));
-    double phi_n = cfg->phi_n;
+    st = check_stage_cfg(c, cfg); if (st) return st;
     if (cfg->adaptive) {
-        st = smcb200_solve_adaptive_phi(c, sched, n_phi, &state->j, &state->phi_prop, cfg->phi_n1, cfg->tempering_target,
-                                        state->ess_prev, state->resampled_last_period, &phi_n);
-        if (st) return st;
-        state->resampled_last_period = 0;
+        if (!sched || n_phi < 1) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "adaptive tempering needs the proposed fixed schedule");
+        st = upload_schedule(c, sched, n_phi); if (st) return st;
     }
-    res->phi_n = phi_n;
-    const double n = (double)c->N_global;
-    // ---- correction -------------------------------------------------------------------------------------
-    double* inc_dev = inc_out ? c->tmp : nullptr;
-    double* nw_dev = normw_out ? c->rmax : nullptr;
-    SMC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    st = launch_correct(c, cfg->phi_n1, phi_n, cfg->prior_weight, cfg->log_prob_old_data, inc_dev, nw_dev); if (st) return st;
-    SMC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
-    if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, inc_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
-    if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, nw_dev, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    StageLaunch L;
+    L.cfg = cfg; L.phi_n1 = cfg->phi_n1; L.phi_n = cfg->phi_n; L.stage = cfg->stage;
+    L.c = state->c; L.accept = state->accept; L.ess_prev = state->ess_prev; L.phi_prop = state->phi_prop; L.j = state->j;
+    L.resampled_last = state->resampled_last_period; L.use_carry = false; L.n_phi = n_phi;
+    L.hist_slot = (inc_out || normw_out) ? 0 : -1; L.time_phases = true;
+    st = stage_enqueue(c, L); if (st) return st;
+    SMC_CUDA(c, cudaMemcpyAsync(c->h_summary, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    if (L.hist_slot >= 0) {
+        // the w_matrix / W_matrix columns leave on the copy stream while moments and mutation run
+        SMC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->hist_ready[0], 0));
+        if (inc_out) SMC_CUDA(c, cudaMemcpyAsync(inc_out, c->hist_scr, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (normw_out) SMC_CUDA(c, cudaMemcpyAsync(normw_out, c->hist_scr + c->N, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->copy_stream));
+        SMC_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    }
     st = sync(c); if (st) return st;
-    res->sum_weights = c->h_scal[SC_S];
-    res->ess = (n * n) / c->h_scal[SC_Q];
-    if (res->ess != res->ess) { res->status = SMCB200_ERR_NAN_ESS; return fail(c, SMCB200_ERR_NAN_ESS, "No particles have non-zero weight."); }
-    // ---- selection ----------------------------------------------------------------------------------------
-    SMC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    if (res->ess < cfg->threshold_ratio * n) {
-        st = launch_resample_cloud(c, cfg->resample_method, cfg->seed, cfg->stage, -1.0); if (st) return st;
-        res->resampled = 1;
-        state->resampled_last_period = 1;
-        if (normw_out) for (int64_t i = 0; i < c->N; ++i) normw_out[i] = 1.0;   // W_matrix[:, i] .= 1
-    }
-    SMC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-    // ---- mutation -----------------------------------------------------------------------------------------
-    state->c = update_step_size(state->c, state->accept, cfg->target);
-    res->c = state->c;
-    SMC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-    st = launch_moments(c); if (st) return st;
-    int perm[DMAX], sizes[NBMAX], ball[DMAX];
-    if (cfg->n_blocks < 1 || cfg->n_blocks > NBMAX) return fail(c, SMCB200_ERR_UNSUPPORTED, "n_blocks must be in 1..8");
-    generate_blocks(c->n_free, cfg->n_blocks, cfg->seed, cfg->stage, perm, sizes);
-    for (int a = 0; a < c->n_free; ++a) ball[a] = c->free_idx[perm[a]];
-    BlockSpec bs;
-    st = make_blockspec(c, cfg->n_blocks, sizes, ball, &bs); if (st) return st;
-    k_prepare_proposal<<<1, 32, 0, c->stream>>>(c->msum, c->csum, bs, state->c, c->mutc_dev, c->status_dev);
-    c->launches += 1;
-    c->mutc_host->n_blocks = cfg->n_blocks;
-    st = mutate_upload_proposal(c, true); if (st) return st;
-    SMC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-    SMC_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    st = mutate_launch(c, phi_n, cfg->alpha, cfg->n_mh_steps, cfg->has_old_data != 0, cfg->seed, cfg->stage); if (st) return st;
-    SMC_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-    st = mean_accept(c); if (st) return st;
-    SMC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
-    SMC_CUDA(c, cudaMemcpyAsync(c->h_status, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (c->world > 1) SMC_CUDA(c, cudaMemcpyAsync(c->h_status + 1, c->mb_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    st = sync(c); if (st) return st;
-    if (c->world > 1 && c->h_status[1]) return fail(c, SMCB200_ERR_NCCL, "a peer rank never reached a cross-GPU reduction (time-out)");
-    if (*c->h_status) {
-        cudaMemsetAsync(c->status_dev, 0, sizeof(int), c->stream);
-        res->status = *c->h_status;
-        return fail(c, *c->h_status, "proposal covariance is not positive definite");
-    }
-    state->accept = c->h_scal[SC_ACC] / n;
-    state->ess_prev = res->ess;
-    res->accept = state->accept;
+    st = summary_to_result(c, c->h_summary, cfg, state, res); if (st) return st;
     cudaEventElapsedTime(&res->ms_correct, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&res->ms_resample, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&res->ms_moments, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&res->ms_mutate, c->ev[6], c->ev[7]);
     c->last_ms[0] = res->ms_correct; c->last_ms[1] = res->ms_resample; c->last_ms[2] = res->ms_moments; c->last_ms[3] = res->ms_mutate;
+    return SMCB200_OK;
+}
+
+// The recursion `while phi_n < 1` (src/smc_main.jl:377-508) for up to n_stages stages in ONE call.  Fixed schedule: every
+// stage is enqueued back to back (the step size, the mean accept rate and the resample decision are carried on the
+// device), the stage summaries and the w/W history columns stream to the host behind the computation, and the host
+// synchronises once.  Adaptive schedule: one synchronisation per stage (the host has to see phi_n to stop at 1).
+int32_t smcb200_run_stages(smcb200_ctx* c, const smcb200_stage_config* cfg0, smcb200_stage_state* state, const double* sched,
+                           int32_t n_phi, int32_t i_first, int32_t n_stages, double* inc_hist, double* normw_hist, int64_t ld_hist,
+                           smcb200_stage_result* results, int32_t* n_done)
+{
+    int st = check_ready(c, true); if (st) return st;
+    if (!cfg0 || !state || !sched || !results || !n_done || n_phi < 2 || i_first < 2 || n_stages < 1)
+        return fail(c, SMCB200_ERR_BAD_ARGUMENT, "bad argument");
+    if ((inc_hist || normw_hist) && ld_hist < c->N) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "history matrices are too small");
+    cudaSetDevice(c->device);
+    *n_done = 0;
+    st = check_stage_cfg(c, cfg0); if (st) return st;
+    const bool adaptive = cfg0->adaptive != 0;
+    if (!adaptive && i_first - 1 + n_stages > n_phi) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "the fixed schedule has fewer stages");
+    st = upload_schedule(c, sched, n_phi); if (st) return st;
+    const bool hist = inc_hist || normw_hist;
+    smcb200_stage_config cfg = *cfg0;
+    double phi_n1 = cfg0->phi_n1;
+    int done = 0;
+    while (done < n_stages) {
+        const int batch = adaptive ? 1 : ((n_stages - done < SUMMARY_RING) ? n_stages - done : SUMMARY_RING);
+        for (int k = 0; k < batch; ++k) {
+            const int s = done + k, i = i_first + s;
+            StageLaunch L;
+            L.cfg = &cfg;
+            L.stage = (uint32_t)i;
+            if (adaptive) { L.phi_n1 = phi_n1; L.phi_n = 0.0; }
+            else { L.phi_n1 = sched[i - 2]; L.phi_n = sched[i - 1]; }
+            L.c = state->c; L.accept = state->accept; L.ess_prev = state->ess_prev; L.phi_prop = state->phi_prop; L.j = state->j;
+            L.resampled_last = state->resampled_last_period;
+            L.use_carry = (s > 0) && !adaptive;        // later stages of a fixed-schedule batch: c / accept live on the device
+            L.n_phi = n_phi;
+            L.hist_slot = hist ? (s % HIST_RING) : -1;
+            L.time_phases = false;
+            if (hist && s >= HIST_RING) SMC_CUDA(c, cudaStreamWaitEvent(c->stream, c->hist_copied[L.hist_slot], 0));
+            st = stage_enqueue(c, L); if (st) return st;
+            SMC_CUDA(c, cudaMemcpyAsync(c->h_summary + (size_t)k * SC_COUNT, c->scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+            if (hist) {
+                const double* src = c->hist_scr + (size_t)L.hist_slot * 2 * c->N;
+                SMC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->hist_ready[L.hist_slot], 0));
+                if (inc_hist) SMC_CUDA(c, cudaMemcpyAsync(inc_hist + (size_t)s * ld_hist, src, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->copy_stream));
+                if (normw_hist) SMC_CUDA(c, cudaMemcpyAsync(normw_hist + (size_t)s * ld_hist, src + c->N, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->copy_stream));
+                SMC_CUDA(c, cudaEventRecord(c->hist_copied[L.hist_slot], c->copy_stream));
+            }
+        }
+        st = sync(c); if (st) return st;
+        for (int k = 0; k < batch; ++k) {
+            st = summary_to_result(c, c->h_summary + (size_t)k * SC_COUNT, &cfg, state, &results[done + k]);
+            if (st) { if (hist) cudaStreamSynchronize(c->copy_stream); *n_done = done + k; return st; }
+        }
+        done += batch;
+        if (adaptive) {
+            phi_n1 = results[done - 1].phi_n;
+            if (phi_n1 >= 1.0) break;
+        }
+    }
+    if (hist) SMC_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    *n_done = done;
     return SMCB200_OK;
 }
 
@@ -1064,6 +1332,32 @@ int32_t smcb200_stage_host(smcb200_ctx* c, double* particles, int64_t ld, const 
     int st = smcb200_cloud_upload(c, particles, ld, 0); if (st) return st;
     st = smcb200_stage(c, cfg, state, sched, n_phi, nullptr, nullptr, res); if (st) return st;
     return smcb200_cloud_download(c, particles, ld, 0);
+}
+
+int32_t smcb200_fp64_peak(smcb200_ctx* c, int32_t iters, double* tflops_out)
+{
+    if (!c || iters < 1 || !tflops_out) return SMCB200_ERR_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    const int blocks = c->sm_count * 8, threads = 256;
+    DevTemps tmp;
+    double* out = nullptr;
+    SMC_CUDA(c, tmp.alloc(&out, (size_t)blocks * threads));
+    k_fp64_peak<<<blocks, threads, 0, c->stream>>>(out, 16, 0.999999, 1e-9);          // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        SMC_CUDA(c, cudaEventRecord(c->tev[0], c->stream));
+        k_fp64_peak<<<blocks, threads, 0, c->stream>>>(out, iters, 0.999999, 1e-9);
+        SMC_CUDA(c, cudaEventRecord(c->tev[1], c->stream));
+        SMC_CUDA(c, cudaEventSynchronize(c->tev[1]));
+        float ms = 0.f;
+        SMC_CUDA(c, cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));
+        if (ms < best) best = ms;
+    }
+    c->launches += 6;
+    SMC_CUDA(c, cudaGetLastError());
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;    // 64 DFMA per thread and iteration
+    *tflops_out = flops / ((double)best * 1e-3) / 1e12;
+    return SMCB200_OK;
 }
 
 int64_t smcb200_kernel_launches(const smcb200_ctx* c) { return c ? c->launches : 0; }

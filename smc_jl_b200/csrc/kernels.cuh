@@ -4,79 +4,9 @@
 // (HBM-bound); every reduction follows the canonical orders of DESIGN.md "Numerical contract".
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace smc {
-
-// =================================================================================================
-// canonical 256-lane block tree + last-block tile tree
-// =================================================================================================
-__device__ __forceinline__ double warp_tree(double v)
-{
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, s);
-    return v;
-}
-
-// adjacent-pair tree over the 256 threads of the block; result valid in thread 0. sm: 8 doubles.
-__device__ __forceinline__ double block_tree_256(double v, double* sm)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = warp_tree(v);
-    __syncthreads();               // protect sm reuse across calls
-    if (lane == 0) sm[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        double x = (lane < 8) ? sm[lane] : 0.0;
-        x = x + __shfl_xor_sync(0xffffffffu, x, 1);
-        x = x + __shfl_xor_sync(0xffffffffu, x, 2);
-        x = x + __shfl_xor_sync(0xffffffffu, x, 4);
-        v = x;
-    }
-    return v;
-}
-
-// adjacent-pair tree over `ntiles` tile partials (zero padded to the power of two P) by one block
-// of 256 threads; result valid in thread 0.  part[] entries >= ntiles must be zero (they are never
-// written after the initial memset).
-__device__ __forceinline__ double tiles_tree_256(double* part, int ntiles, int P, double* sm)
-{
-    double x;
-    if (P <= 256) {
-        x = ((int)threadIdx.x < ntiles) ? __ldcg(part + threadIdx.x) : 0.0;
-    } else {
-        const int m = P / 256;
-        double* p = part + (size_t)threadIdx.x * m;
-        for (int s = 1; s < m; s <<= 1)
-            for (int i = 0; i < m; i += 2 * s) __stcg(p + i, __ldcg(p + i) + __ldcg(p + i + s));
-        x = __ldcg(p);
-    }
-    return block_tree_256(x, sm);
-}
-
-// The block that finishes last reduces the tile partials of NQ quantities into out[q].
-// v[q] must be valid in thread 0.  Returns true (block-uniform) in the finishing block.
-template <int NQ>
-__device__ __forceinline__ bool finish_tiles(const double (&v)[NQ], double* partials, int ntiles, int P,
-                                             unsigned* counter, double* out, double* sm)
-{
-    __shared__ bool is_last;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) __stcg(partials + (size_t)q * P + blockIdx.x, v[q]);
-        __threadfence();
-        const unsigned t = atomicInc(counter, gridDim.x - 1);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return false;
-    __threadfence();
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        const double r = tiles_tree_256(partials + (size_t)q * P, ntiles, P, sm);
-        if (threadIdx.x == 0) out[q] = r;
-    }
-    return true;
-}
 
 // =================================================================================================
 // Small cross-GPU reductions without a collective library: ONE launch per reduction.  Every rank pushes its nq
@@ -88,40 +18,10 @@ __device__ __forceinline__ bool finish_tiles(const double (&v)[NQ], double* part
 // A peer that never arrives (a crashed rank) trips a clock-based time-out instead of hanging the GPU.
 // =================================================================================================
 __global__ void __launch_bounds__(256)
-k_peer_exchange(const double* __restrict__ local_src, int nq, int rank, int world, double* const* __restrict__ inbox,
-                unsigned long long epoch, int combine, double* __restrict__ dst, int* __restrict__ err)
+k_peer_exchange(const double* __restrict__ local_src, int nq, PeerCtx pc, int combine, double* __restrict__ dst, const double* flag)
 {
-    const int par = (int)(epoch & 1ull);
-    const size_t flag_off = (size_t)2 * world * MB_NQ;               // flags follow the value slots (as doubles' worth of u64)
-    for (int r = 0; r < world; ++r) {
-        double* slot = inbox[r] + ((size_t)par * world + rank) * MB_NQ;
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) slot[q] = local_src[q];
-    }
-    __syncthreads();                     // the block's remote stores happen-before the (cumulative) fences below
-    if ((int)threadIdx.x < world) {
-        __threadfence_system();
-        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(inbox[threadIdx.x] + flag_off) + (size_t)par * world + rank;
-        *f = epoch;
-        volatile unsigned long long* g = reinterpret_cast<volatile unsigned long long*>(inbox[rank] + flag_off) + (size_t)par * world + threadIdx.x;
-        const long long t0 = clock64();
-        while (*g < epoch) {
-            if (clock64() - t0 > 20000000000ll) { *err = 1; break; }    // ~10 s at 2 GHz
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-    const double* mine = inbox[rank] + (size_t)par * world * MB_NQ;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        if (combine) {
-            double v[16];
-            for (int r = 0; r < world; ++r) v[r] = __ldcg(mine + (size_t)r * MB_NQ + q);
-            for (int s = 1; s < world; s <<= 1)
-                for (int i = 0; i + s < world; i += 2 * s) v[i] = v[i] + v[i + s];
-            dst[q] = v[0];
-        } else {
-            for (int r = 0; r < world; ++r) dst[(size_t)r * nq + q] = __ldcg(mine + (size_t)r * MB_NQ + q);
-        }
-    }
+    if (flag && *flag == 0.0) return;
+    peer_exchange_block(pc, local_src, nq, combine, dst);
 }
 
 // =================================================================================================
@@ -138,62 +38,6 @@ __device__ __forceinline__ double inc_weight(double ll, double old, const CorrAr
     if (a.mode == 1) return det_exp((phi_n - a.phi_n1) * ll);
     const double inner = det_log(det_exp((old - a.lpod) + a.log_1m_pw) + a.pw);
     return det_exp((a.phi_n1 - phi_n) * inner + (phi_n - a.phi_n1) * ll);
-}
-
-// pass A: w~ = w * inc; S = canonical sum of w~ (in place on the weight column).
-__global__ void __launch_bounds__(256)
-k_weights_a(const double* __restrict__ ll, const double* __restrict__ old, const double* w,
-            double* wout, double* __restrict__ inc_out, int64_t N, CorrArgs a,
-            double* partials, int ntiles, int P, unsigned* counter, double* out)
-{
-    __shared__ double sm[8];
-    const double phi_n = a.phi_n;
-    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
-    double x[W_R];
-#pragma unroll
-    for (int r = 0; r < W_R; ++r) {
-        const int64_t i = base + (int64_t)r * W_LANES;
-        x[r] = 0.0;
-        if (i < N) {
-            const double inc = inc_weight(ll[i], old[i], a, phi_n);
-            x[r] = w[i] * inc;
-            wout[i] = x[r];
-            if (inc_out) inc_out[i] = inc;
-        }
-    }
-    double acc = 0.0;
-#pragma unroll
-    for (int r = 0; r < W_R; ++r) acc = acc + x[r];
-    double v[1] = {block_tree_256(acc, sm)};
-    finish_tiles<1>(v, partials, ntiles, P, counter, out + SC_S, sm);
-}
-
-// pass B: W = (w~ * N) / S; Q = sum W^2, S2 = sum W.  store != 0 writes W back (normalize_weights!).
-__global__ void __launch_bounds__(256)
-k_weights_b(double* w, double* __restrict__ normw_out, int64_t N, double n_parts, int store,
-            double* partials, int ntiles, int P, unsigned* counter, double* scal, double* out)
-{
-    __shared__ double sm[8];
-    const double S = scal[SC_S];
-    const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
-    double x[W_R];
-#pragma unroll
-    for (int r = 0; r < W_R; ++r) {
-        const int64_t i = base + (int64_t)r * W_LANES;
-        x[r] = 0.0;
-        if (i < N) {
-            x[r] = (w[i] * n_parts) / S;
-            if (store) w[i] = x[r];
-            if (normw_out) normw_out[i] = x[r];
-        }
-    }
-    double q = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int r = 0; r < W_R; ++r) { q = q + x[r] * x[r]; s2 = s2 + x[r]; }
-    double v[2];
-    v[0] = block_tree_256(q, sm);
-    v[1] = block_tree_256(s2, sm);
-    finish_tiles<2>(v, partials + (size_t)P, ntiles, P, counter + 1, out + SC_Q, sm);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -246,79 +90,13 @@ k_ess_multi(const double* __restrict__ ll, const double* __restrict__ old, const
     }
 }
 
-__device__ inline void phi_build_tree(PhiState* st)
-{
-    double a[ESS_K], b[ESS_K];
-    a[0] = st->lo; b[0] = st->hi;
-    for (int n = 0; n < ESS_K; ++n) {
-        const double mid = 0.5 * (a[n] + b[n]);
-        st->trial[n] = mid;
-        if (2 * n + 2 < ESS_K) { a[2 * n + 1] = a[n]; b[2 * n + 1] = mid; a[2 * n + 2] = mid; b[2 * n + 2] = b[n]; }
-    }
-}
-__device__ inline void phi_fill_walk(PhiState* st, const double* sched)
-{
-    st->trial[0] = st->phi_prop;
-    for (int k = 1; k < ESS_K; ++k) {
-        long long idx = st->j - 1 + (k - 1);
-        if (idx > st->n_phi - 1) idx = st->n_phi - 1;
-        st->trial[k] = sched[idx];
-    }
-}
-// Transition of solve_adaptive_phi (src/helpers.jl:26-54) over one multi-trial pass: consumes as many of the ESS_K
-// evaluations as the sequential algorithm would have made (the schedule walk, then up to 4 bisection levels), i.e. the
-// result is the one of the one-evaluation-at-a-time loop, bit for bit.  One thread.
-__global__ void k_phi_step_multi(PhiState* st, const double* __restrict__ sched, const double* __restrict__ sq)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
-    bool finish = false;
-    if (st->phase == 0) {
-        int k = 0;
-        double g;
-        for (;;) {
-            g = (sq[k] * sq[k]) / sq[ESS_K + k] - st->ess_bar;
-            st->evals += 1; st->g_last = g;
-            if (g >= 0.0 && st->j <= st->n_phi) {
-                st->phi_prop = sched[st->j - 1];
-                st->j += 1;
-                st->phi_cur = st->phi_prop;
-                if (++k == ESS_K) { phi_fill_walk(st, sched); return; }     // more schedule points next pass
-                continue;
-            }
-            break;
-        }
-        if (st->phi_prop != 1.0 || g < 0.0) {
-            st->lo = st->phi_n1; st->hi = st->phi_prop; st->phase = 1;
-        } else {
-            st->phi_n = 1.0; st->done = 1;
-            return;
-        }
-    } else {
-        int node = 0;
-        for (int level = 0; level < 4 && !finish; ++level) {
-            const double mid = 0.5 * (st->lo + st->hi);
-            if (!(mid > st->lo && mid < st->hi)) { finish = true; break; }
-            const double g = (sq[node] * sq[node]) / sq[ESS_K + node] - st->ess_bar;
-            st->evals += 1; st->g_last = g;
-            if (g == 0.0) { st->lo = mid; finish = true; }
-            else if (g > 0.0) { st->lo = mid; node = 2 * node + 2; }      // continue in (mid, hi): right child
-            else { st->hi = mid; node = 2 * node + 1; }                   // continue in (lo, mid): left child
-        }
-    }
-    if (!finish) {
-        const double mid = 0.5 * (st->lo + st->hi);
-        if (mid > st->lo && mid < st->hi) { st->phi_cur = mid; phi_build_tree(st); return; }
-    }
-    st->phi_n = (st->lo == st->phi_n1) ? st->hi : st->lo;
-    st->done = 1;
-}
-
 // canonical sum of one column (optionally divided by a constant first): out = sum_i x_i / div
 __global__ void __launch_bounds__(256)
 k_colsum(const double* __restrict__ x, int64_t N, double div, int use_div, double* partials, int ntiles, int P,
-         unsigned* counter, double* out)
+         unsigned* counter, double* out, const double* flag = nullptr)
 {
     __shared__ double sm[8];
+    if (flag && *flag == 0.0) return;
     const int64_t base = (int64_t)blockIdx.x * W_TILE + threadIdx.x;
     double acc = 0.0;
 #pragma unroll
@@ -344,9 +122,10 @@ template <bool FINAL>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* __restrict__ S_ptr, int64_t n, int B,
        double* __restrict__ blocktot, const double* __restrict__ blockoff, double* __restrict__ rmax,
-       double* __restrict__ craw, double* __restrict__ bmax)
+       double* __restrict__ craw, double* __restrict__ bmax, const double* flag = nullptr)
 {
     extern __shared__ double sm_dyn[];
+    if (flag && *flag == 0.0) return;
     double* tile = sm_dyn;                               // [nleaf][LEAF + 1]
     double* lv = sm_dyn + SCAN_THREADS * (LEAF + 1);     // [2*nleaf] tree levels
     double* lmax = lv + 2 * SCAN_THREADS;        // [nleaf]
@@ -433,8 +212,10 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
 // down: block offsets, top-down, starting from the shard's own offset in the cross-rank tree
 //       (rank_roots = gathered shard roots; nullptr on one GPU).
 __global__ void __launch_bounds__(256)
-k_scan_upper_up(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ root_out)
+k_scan_upper_up(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ root_out,
+                const double* flag = nullptr)
 {
+    if (flag && *flag == 0.0) return;
     int nlev = 0;
     while ((1 << nlev) < nb) ++nlev;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) lv[i] = blocktot[i];
@@ -449,9 +230,10 @@ k_scan_upper_up(const double* __restrict__ blocktot, int nb, double* __restrict_
 
 __global__ void __launch_bounds__(256)
 k_scan_upper_down(const double* __restrict__ lv, int nb, const double* __restrict__ rank_roots, int world, int rank,
-                  double* __restrict__ blockoff)
+                  double* __restrict__ blockoff, const double* flag = nullptr)
 {
     __shared__ double off0;
+    if (flag && *flag == 0.0) return;
     if (threadIdx.x == 0) {
         double off = 0.0;
         if (rank_roots && world > 1) {
@@ -482,19 +264,27 @@ k_scan_upper_down(const double* __restrict__ lv, int nb, const double* __restric
     }
 }
 
-// multi-GPU: fold the maxima of the lower ranks into this shard's inclusive prefix max
-__global__ void k_apply_rank_carry(double* __restrict__ bmax, int nb, const double* __restrict__ rank_max, int rank)
+// multi-GPU: bmax [world][nb] holds every shard's inclusive prefix max of its own block maxima; fold the maxima of the
+// lower ranks in, which makes it the inclusive prefix max over the global block sequence.  One block.
+__global__ void __launch_bounds__(256) k_fix_rank_carry(double* __restrict__ bmax, int nb, int world, const double* flag = nullptr)
 {
-    double carry = -dinf();
-    for (int r = 0; r < rank; ++r) carry = fmax(carry, rank_max[r]);
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) bmax[b] = fmax(bmax[b], carry);
+    __shared__ double carry[16];
+    if (flag && *flag == 0.0) return;
+    if ((int)threadIdx.x < world) {
+        double cmax = -dinf();
+        for (int r = 0; r < (int)threadIdx.x; ++r) cmax = fmax(cmax, bmax[(size_t)r * nb + nb - 1]);
+        carry[threadIdx.x] = cmax;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * world; e += blockDim.x) bmax[e] = fmax(bmax[e], carry[e / nb]);
 }
 
 // inclusive prefix max of the block maxima (one block of 256 threads; max is exact in any order)
-__global__ void __launch_bounds__(256) k_prefix_max(double* bmax, int nb)
+__global__ void __launch_bounds__(256) k_prefix_max(double* bmax, int nb, const double* flag = nullptr)
 {
     __shared__ double sm[256];
     __shared__ double carry;
+    if (flag && *flag == 0.0) return;
     const int tid = threadIdx.x;
     if (tid == 0) carry = -dinf();
     __syncthreads();
@@ -525,12 +315,14 @@ __global__ void __launch_bounds__(256) k_prefix_max(double* bmax, int nb)
 // returns 0) is clamped to n.
 // =================================================================================================
 __global__ void __launch_bounds__(256)
-k_search(const double* __restrict__ rmax, const double* __restrict__ bmax_incl, int nb, int B, int64_t n,
+k_search(const double* __restrict__ rmax_single, const double* const* __restrict__ rmax_tab, int nb_rank,
+         const double* __restrict__ bmax_incl, int nb, int B, int64_t n,
          int64_t n_out, int64_t out0, int method, uint64_t seed, uint32_t stage, double u, double n_parts,
-         int64_t* __restrict__ idx)
+         int64_t* __restrict__ idx, const double* flag = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_out) return;
+    if (flag && *flag == 0.0) return;
     const int64_t gi = out0 + i;
     double t;
     if (method == SMCB200_RESAMPLE_SYSTEMATIC) {
@@ -546,11 +338,20 @@ k_search(const double* __restrict__ rmax, const double* __restrict__ bmax_incl, 
     }
     int64_t res = n;
     if (lo < nb) {
+        // running max of block `lo`: this GPU's buffer, or the owning rank's over NVLink (CUDA-IPC mapping); rm[g - base]
+        // is the value at global index g
+        const double* rm = rmax_single;
+        int64_t base = 0;
+        if (!rmax_single) {
+            const int owner = lo / nb_rank;
+            rm = rmax_tab[owner];
+            base = (int64_t)owner * nb_rank * B;
+        }
         int64_t jlo = (int64_t)lo * B, jhi = jlo + B;
         if (jhi > n) jhi = n;
         while (jlo < jhi) {
             const int64_t mid = (jlo + jhi) >> 1;
-            if (rmax[mid] > t) jhi = mid; else jlo = mid + 1;
+            if (rm[mid - base] > t) jhi = mid; else jlo = mid + 1;
         }
         res = jlo + 1;
         if (res > n) res = n;
@@ -563,10 +364,11 @@ k_search(const double* __restrict__ rmax, const double* __restrict__ bmax_incl, 
 // =================================================================================================
 __global__ void __launch_bounds__(256)
 k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t* __restrict__ idx, int64_t N,
-         int ncopy, int wcol)
+         int ncopy, double* __restrict__ wreset, double* __restrict__ nw_hist, const double* flag = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
+    if (flag && *flag == 0.0) return;
     const int64_t a = idx[i] - 1;
     int c = 0;
     for (; c + 4 <= ncopy; c += 4) {
@@ -576,7 +378,8 @@ k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t
         dst[col_off(N, c + 2) + i] = v2; dst[col_off(N, c + 3) + i] = v3;
     }
     for (; c < ncopy; ++c) dst[col_off(N, c) + i] = src[col_off(N, c) + a];
-    dst[col_off(N, wcol) + i] = 1.0;
+    wreset[i] = 1.0;                       // reset_weights!, particle.jl:378-383
+    if (nw_hist) nw_hist[i] = 1.0;         // W_matrix[:, i] .= 1, smc_main.jl:445
 }
 
 // multi-GPU gather: ancestors are GLOBAL indices; rows are read straight from the owning rank's cloud
@@ -584,10 +387,12 @@ k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t
 // column are near-contiguous on one or two peers) -- the "all-to-all(v)" of the stage, done by the kernel.
 __global__ void __launch_bounds__(256)
 k_gather_peer(double* const* __restrict__ peers, const int64_t* __restrict__ peer_cnt, int64_t per, double* __restrict__ dst,
-              const int64_t* __restrict__ idx, int64_t N, int ncopy, int wcol)
+              const int64_t* __restrict__ idx, int64_t N, int ncopy, double* __restrict__ wreset, double* __restrict__ nw_hist,
+              const double* flag = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
+    if (flag && *flag == 0.0) return;
     const int64_t a = idx[i] - 1;
     const int r = (int)(a / per);
     const int64_t row = a - (int64_t)r * per;
@@ -601,7 +406,8 @@ k_gather_peer(double* const* __restrict__ peers, const int64_t* __restrict__ pee
         dst[col_off(N, c + 2) + i] = v2; dst[col_off(N, c + 3) + i] = v3;
     }
     for (; c < ncopy; ++c) dst[col_off(N, c) + i] = src[col_off(nr, c) + row];
-    dst[col_off(N, wcol) + i] = 1.0;
+    wreset[i] = 1.0;
+    if (nw_hist) nw_hist[i] = 1.0;
 }
 
 // =================================================================================================
@@ -852,83 +658,6 @@ SMC_HD int build_mutconst(const double* mean, const double* cov, int d, const Bl
     return 0;
 }
 
-// One warp.  Same per-element arithmetic as build_mutconst()/cholesky_lower() (each L_ij is the same
-// fma chain over k ascending), evaluated column by column with one lane per row.
-__global__ void __launch_bounds__(32)
-k_prepare_proposal(const double* __restrict__ msum, const double* __restrict__ csum, BlockSpec bs, double c,
-                   MutConst* out, int* status)
-{
-    __shared__ double cov[DMAX][DMAX + 1];
-    __shared__ double S[DMAX][DMAX + 1];
-    __shared__ double L[DMAX][DMAX + 1];
-    const int lane = threadIdx.x;
-    const int d = bs.d;
-    const double sw = msum[0];
-    if (lane == 0) { out->n_blocks = bs.n_blocks; out->status = 0; }
-    out->mu[lane] = (lane < d) ? msum[1 + lane] / sw : 0.0;
-    for (int e = lane; e < d * (d + 1) / 2; e += 32) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        const int b = e - a * (a + 1) / 2;
-        const double v = csum[e] / sw;
-        cov[a][b] = v;
-        cov[b][a] = v;
-    }
-    __syncwarp();
-    for (int b = 0; b < bs.n_blocks; ++b) {
-        const int n = bs.bsize[b];
-        for (int e = lane; e < PACKMAX; e += 32) out->L[b][e] = 0.0;
-        out->csd[b][lane] = 0.0;
-        out->isd[b][lane] = 0.0; out->isdn[b][lane] = 0.0; out->rl[b][lane] = 0.0;
-        uint32_t mask = 0;
-        for (int i = 0; i < n; ++i) mask |= 1u << bs.member[b][i];
-        if (lane == 0) { out->mask[b] = mask; out->bsize[b] = n; }
-        const int ai = (lane < n) ? bs.member[b][lane] : 0;
-        if (lane < n)
-            for (int j = 0; j < n; ++j) {
-                const int aj = bs.member[b][j];
-                S[lane][j] = (cov[ai][aj] + cov[aj][ai]) / 2.0;      // R_fr = (R + R') / 2, smc_main.jl:462
-            }
-        __syncwarp();
-        bool bad = false;
-        for (int j = 0; j < n; ++j) {
-            double sv = 0.0;
-            if (lane >= j && lane < n) {
-                sv = S[lane][j];
-                for (int k = 0; k < j; ++k) sv = fma(-L[lane][k], L[j][k], sv);
-            }
-            const double sj = __shfl_sync(0xffffffffu, sv, j);
-            if (!(sj > 0.0)) { bad = true; break; }
-            const double dj = sqrt(sj);
-            if (lane == j) L[j][j] = dj;
-            else if (lane > j && lane < n) L[lane][j] = sv / dj;
-            __syncwarp();
-        }
-        if (bad) {
-            if (lane == 0) { out->status = SMCB200_ERR_NOT_POSDEF; *status = SMCB200_ERR_NOT_POSDEF; }
-            return;
-        }
-        __syncwarp();
-        if (lane < n) {
-            for (int j = 0; j <= lane; ++j) {
-                const int aj = bs.member[b][j];
-                out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * L[lane][j];
-            }
-            out->csd[b][ai] = c * sqrt(S[lane][lane]);
-            const double isd = 1.0 / sqrt(S[lane][lane]);
-            out->isd[b][ai] = isd;
-            out->isdn[b][ai] = isd * 0x1.9884533d43651p-2;
-            out->rl[b][ai] = 1.0 / (c * L[lane][lane]);
-        }
-        if (lane == 0) {
-            double ld = 0.0;
-            for (int i = 0; i < n; ++i) ld = ld + det_log(c * L[i][i]);
-            out->lognorm[b] = (double)n * (2.0 * 0.91893853320467274178) + 2.0 * ld;
-        }
-        __syncwarp();
-    }
-}
-
 // debug: elementwise deterministic math on the device
 __global__ void k_debug_math(int op, const double* __restrict__ x, int64_t n, uint64_t seed, double* __restrict__ out)
 {
@@ -948,7 +677,7 @@ __global__ void k_debug_math(int op, const double* __restrict__ x, int64_t n, ui
     }
     default: {   // 6..9: the four proposal normals of normal_quad
         double z[4];
-        normal_quad(rng4(seed, (uint32_t)i, 0u, (uint32_t)x[i], PURP_NORMAL), z[0], z[1], z[2], z[3]);
+        normal_quad(rng4(seed, (uint32_t)i, 0u, (uint32_t)x[i], PURP_NORMAL), reinterpret_cast<const float4*>(normal_tab_dev), z[0], z[1], z[2], z[3]);
         out[i] = z[(op - 6) & 3];
     }
     }

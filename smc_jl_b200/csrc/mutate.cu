@@ -78,7 +78,15 @@ int mutate_upload_proposal(Ctx* ctx, bool from_device)
     return e->upload_proposal(ctx, from_device);
 }
 
-int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage)
+PeerCtx peer_ctx(const Ctx* ctx)
+{
+    PeerCtx pc;
+    pc.inbox = ctx->mbox_tab; pc.epoch = ctx->mb_epoch_dev; pc.err = ctx->mb_err; pc.rank = ctx->rank; pc.world = ctx->world;
+    return pc;
+}
+
+// fused != 0: phi_n, the resample flag (which buffer holds the rows) and the poison status come from the device scalars
+int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has_old, uint64_t seed, uint32_t stage, bool fused)
 {
     const KernelEntry* e = find_entry(ctx);
     if (!e || !mutate_supported(ctx, has_old)) {
@@ -88,14 +96,27 @@ int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has
     MutArgs a;
     a.phi_n = phi_n; a.alpha = alpha; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
     a.seed = seed; a.stage = stage;
+    a.scal = fused ? ctx->scal : nullptr;
+    a.alt_in = ctx->cloud[ctx->cur ^ 1];
+    a.acc_partials = ctx->acc_partials; a.acc_P = ctx->acc_P; a.acc_counter = ctx->counters + 5;
+    a.acc_out = ctx->scal + SC_ACC; a.acc_mean_out = ctx->scal + SC_ACCEPT; a.n_global = (double)ctx->N_global;
+    a.pc = peer_ctx(ctx);
     const bool single = (a.n_blocks == 1);
     const unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
     const size_t smem = sizeof(double) * 2 * (size_t)e->d * MUT_THREADS;
     // one block that holds every parameter (none fixed): compile-time membership mask
     const bool full = single && ctx->n_free == e->d;      // (a single block always holds all free parameters)
     auto kern = e->mut[has_old ? 1 : 0][single ? (full ? 2 : 1) : 0][alpha < 1.0 ? 1 : 0];
-    if (smem > 48 * 1024)
-        SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::vector<const void*> configured;           // per-kernel attributes are set once
+    bool seen = false;
+    for (const void* k : configured) seen = seen || (k == (const void*)kern);
+    if (!seen) {
+        if (smem > 48 * 1024)
+            SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the chain state lives in shared memory: ask for the largest carve-out so that LIK::MINB blocks stay resident
+        SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured.push_back((const void*)kern);
+    }
     kern<<<grid, MUT_THREADS, smem, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);
     ctx->launches++;
     SMC_CUDA(ctx, cudaGetLastError());

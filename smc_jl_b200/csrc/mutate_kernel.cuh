@@ -19,6 +19,7 @@
 // functions of the unit that owns the selected kernel.
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 #include "aslik.cuh"
 
 namespace smc {
@@ -182,135 +183,174 @@ __device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
 // the proposal densities of compute_proposal_densities (helpers.jl:128-164).
 template <class LIK, bool HAS_OLD, int BLK, bool MIX>
 __global__ void __launch_bounds__(MUT_THREADS, LIK::MINB)
-k_mutate(double* __restrict__ cloud, int64_t N, int64_t index0, MutArgs a)
+k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
 {
     constexpr int D = LIK::D;
+    static_assert(MUT_THREADS == ACC_TILE, "the accept-column sum is defined on 128-particle tiles");
     extern __shared__ double sm_state[];
+    __shared__ float4 sm_tab[NORMAL_TAB_ROWS];     // inverse-normal-CDF table (4.2 KB; random per-lane rows)
+    __shared__ double sm_red[MUT_THREADS / 32];
+    __shared__ bool sm_last;
+    if (a.scal && a.scal[SC_STATUS] != 0.0) return;   // the stage was poisoned (NaN ESS / non-PD covariance): leave the cloud alone
+    if (c_mut.status != 0) return;
+    for (int k = threadIdx.x; k < NORMAL_TAB_ROWS; k += MUT_THREADS) sm_tab[k] = reinterpret_cast<const float4*>(normal_tab_dev)[k];
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * MUT_THREADS + threadIdx.x;
-    if (i >= N) return;
-    double* buf0 = sm_state + threadIdx.x;
-    double* buf1 = sm_state + D * MUT_THREADS + threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < D; ++k) buf0[k * MUT_THREADS] = cloud[col_off(N, k) + i];
-    double like = cloud[col_off(N, D) + i];
-    double lpri = cloud[col_off(N, D + 1) + i];
-    double lprev = cloud[col_off(N, D + 2) + i];
+    const bool live = i < N;
     double accept = 0.0;
-    bool flipped = false;
-    const uint32_t gp = (uint32_t)(index0 + i);
-    const double phi = a.phi_n, omphi = 1.0 - a.phi_n;
-    constexpr bool SINGLE = BLK != 0;
-    constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
-    const int nb = SINGLE ? 1 : a.n_blocks;
+    if (live) {
+        const double* src = (a.scal && a.scal[SC_RESAMPLE] != 0.0) ? a.alt_in : cloud;
+        double* buf0 = sm_state + threadIdx.x;
+        double* buf1 = sm_state + D * MUT_THREADS + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < D; ++k) buf0[k * MUT_THREADS] = src[col_off(N, k) + i];
+        double like = src[col_off(N, D) + i];
+        double lpri = src[col_off(N, D + 1) + i];
+        double lprev = src[col_off(N, D + 2) + i];
+        bool flipped = false;
+        const uint32_t gp = (uint32_t)(index0 + i);
+        const double phi = a.scal ? a.scal[SC_PHI_N] : a.phi_n;
+        const double omphi = 1.0 - phi;
+        constexpr bool SINGLE = BLK != 0;
+        constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
+        const int nb = SINGLE ? 1 : a.n_blocks;
 
-    for (int step = 0; step < a.n_mh_steps; ++step) {
-        for (int bb = 0; bb < nb; ++bb) {
-            const int b = SINGLE ? 0 : bb;
-            const uint32_t sb = (uint32_t)(step * nb + b);
-            const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
-            const double* cur = flipped ? buf1 : buf0;
-            double* cand = flipped ? buf0 : buf1;
-            // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
-            const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
-            const double step_prob = u01(r4.x, r4.y);
-            int comp = 1;
-            if (MIX) {
-                const double u_mix = u01(r4.z, r4.w);
-                comp = (u_mix < a.alpha) ? 1 : ((u_mix < a.alpha + (1.0 - a.alpha) / 2.0) ? 2 : 3);
-            }
-            // (1) normals of this block's members -> candidate buffer (used as scratch): one Philox block gives
-            // the four normals of parameters 4q .. 4q+3 (normal_quad, binary32 Box-Muller).  Rolled loop: small
-            // code (instruction cache); the two pairs of a quad are independent chains.
-            constexpr int NQUAD = (D + 3) / 4;
-#pragma unroll 1
-            for (int q = 0; q < NQUAD; ++q) {
-                if ((mask >> (4 * q)) & 15u) {
-                    double z0, z1, z2, z3;
-                    normal_quad(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), z0, z1, z2, z3);
-                    cand[(4 * q) * MUT_THREADS] = z0;
-                    if (4 * q + 1 < D) cand[(4 * q + 1) * MUT_THREADS] = z1;
-                    if (4 * q + 2 < D) cand[(4 * q + 2) * MUT_THREADS] = z2;
-                    if (4 * q + 3 < D) cand[(4 * q + 3) * MUT_THREADS] = z3;
-                }
-            }
-            // (2) proposal increment s = (c L) z, column by column (each s[r] sums over ascending columns)
-            double s[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) s[k] = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                if ((mask >> j) & 1u) {
-                    const double zj = cand[j * MUT_THREADS];
-#pragma unroll
-                    for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], zj, s[r]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const double t = cur[k * MUT_THREADS];
+        for (int step = 0; step < a.n_mh_steps; ++step) {
+            for (int bb = 0; bb < nb; ++bb) {
+                const int b = SINGLE ? 0 : bb;
+                const uint32_t sb = (uint32_t)(step * nb + b);
+                const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
+                const double* cur = flipped ? buf1 : buf0;
+                double* cand = flipped ? buf0 : buf1;
+                // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
+                const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
+                const double step_prob = u01(r4.x, r4.y);
+                int comp = 1;
                 if (MIX) {
-                    // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
-                    const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
-                    const double base = (comp == 3) ? c_mut.mu[k] : t;
-                    s[k] = ((mask >> k) & 1u) ? base + inc : t;
-                } else {
-                    s[k] = ((mask >> k) & 1u) ? t + s[k] : t;          // s is now theta'
+                    const double u_mix = u01(r4.z, r4.w);
+                    comp = (u_mix < a.alpha) ? 1 : ((u_mix < a.alpha + (1.0 - a.alpha) / 2.0) ? 2 : 3);
                 }
-                cand[k * MUT_THREADS] = s[k];
-            }
-            const bool ok = in_bounds<D>(s);
-            double pn = logprior<D>(s);
-            double ln = LIK::template ll<0>(s);
-            if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
-            double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
-            if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
-            // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
-            double qdiff = 0.0;
-            if (MIX) {
-                // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
-                // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
-                // fma chains, so one evaluation serves both.
-                const double lognorm = c_mut.lognorm[b];
+                // (1) + (2): one Philox block gives the four normals of parameters 4q .. 4q+3 (table-driven inverse
+                // CDF, normal_icdf); each normal is consumed at once by its column of the proposal increment
+                // s = (c L) z (every s[r] sums over ascending columns j, the oracle's order), so the normals never
+                // leave registers.  The mixture path also parks them in the candidate buffer (component 2 needs z_k).
+                constexpr int NQUAD = (D + 3) / 4;
+                double s[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k)
-                    s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
-                double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
+                for (int k = 0; k < D; ++k) s[k] = 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k)
-                    if ((mask >> k) & 1u) {
-                        const double zs = s[k] * c_mut.isd[b][k];
-                        ind = (ind * c_mut.isdn[b][k]) * det_exp(-0.5 * (zs * zs));
+                for (int q = 0; q < NQUAD; ++q) {
+                    if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
+                        double z[4];
+                        normal_quad(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), sm_tab, z[0], z[1], z[2], z[3]);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * q + jj;
+                            if (j < D) {
+                                if (MIX) cand[j * MUT_THREADS] = z[jj];
+                                if (BLK == 2 || ((mask >> j) & 1u)) {
+#pragma unroll
+                                    for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], z[jj], s[r]);
+                                }
+                            }
+                        }
                     }
-                const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+                }
 #pragma unroll
-                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
-                const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+                for (int k = 0; k < D; ++k) {
+                    const double t = cur[k * MUT_THREADS];
+                    if (MIX) {
+                        // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
+                        const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
+                        const double base = (comp == 3) ? c_mut.mu[k] : t;
+                        s[k] = ((mask >> k) & 1u) ? base + inc : t;
+                    } else {
+                        s[k] = (BLK == 2 || ((mask >> k) & 1u)) ? t + s[k] : t;          // s is now theta'
+                    }
+                    cand[k * MUT_THREADS] = s[k];
+                }
+                const bool ok = in_bounds<D>(s);
+                double pn = logprior<D>(s);
+                double ln = LIK::template ll<0>(s);
+                if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
+                double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
+                if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
+                // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
+                double qdiff = 0.0;
+                if (MIX) {
+                    // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
+                    // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
+                    // fma chains, so one evaluation serves both.
+                    const double lognorm = c_mut.lognorm[b];
 #pragma unroll
-                for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
-                const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
-                const double w2 = (1.0 - a.alpha) / 2.0;
-                double q0 = a.alpha * e_sym, q1 = a.alpha * e_sym;
-                q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
-                q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
-                q0 = det_log(q0); q1 = det_log(q1);
-                if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
-                qdiff = q0 - q1;
-            }
-            const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + qdiff);
-            if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
-                flipped = !flipped;
-                like = ln; lpri = pn; lprev = lo;
-                accept += (double)c_mut.bsize[b];
+                    for (int k = 0; k < D; ++k)
+                        s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
+                    double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
+#pragma unroll
+                    for (int k = 0; k < D; ++k)
+                        if ((mask >> k) & 1u) {
+                            const double zs = s[k] * c_mut.isd[b][k];
+                            ind = (ind * c_mut.isdn[b][k]) * det_exp(-0.5 * (zs * zs));
+                        }
+                    const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                    const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+                    const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+                    const double w2 = (1.0 - a.alpha) / 2.0;
+                    double q0 = a.alpha * e_sym, q1 = a.alpha * e_sym;
+                    q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
+                    q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
+                    q0 = det_log(q0); q1 = det_log(q1);
+                    if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
+                    qdiff = q0 - q1;
+                }
+                const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + qdiff);
+                if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
+                    flipped = !flipped;
+                    like = ln; lpri = pn; lprev = lo;
+                    accept += (double)c_mut.bsize[b];
+                }
             }
         }
-    }
-    const double* cur = flipped ? buf1 : buf0;
+        const double* cur = flipped ? buf1 : buf0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = cur[k * MUT_THREADS];
-    cloud[col_off(N, D) + i] = like;
-    cloud[col_off(N, D + 1) + i] = lpri;
-    cloud[col_off(N, D + 2) + i] = lprev;
-    cloud[col_off(N, D + 3) + i] = accept / (double)a.n_free;      // particle.jl:410-418
+        for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = cur[k * MUT_THREADS];
+        cloud[col_off(N, D) + i] = like;
+        cloud[col_off(N, D + 1) + i] = lpri;
+        cloud[col_off(N, D + 2) + i] = lprev;
+        accept = accept / (double)a.n_free;                            // particle.jl:410-418
+        cloud[col_off(N, D + 3) + i] = accept;
+    }
+    // sum of the accept column (update_acceptance_rate!, particle.jl:466-468): this block is one 128-particle tile of
+    // the canonical order (adjacent-pair tree over the lanes, then over the tiles); the last block to finish reduces
+    // the tile sums
+    if (!a.acc_partials) return;
+    double v = warp_tree(accept);
+    if ((threadIdx.x & 31) == 0) sm_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        v = (sm_red[0] + sm_red[1]) + (sm_red[2] + sm_red[3]);
+        __stcg(a.acc_partials + blockIdx.x, v);
+        __threadfence();
+        const unsigned t = atomicInc(a.acc_counter, gridDim.x - 1);
+        sm_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!sm_last) return;
+    __threadfence();
+    const double root = tiles_tree_block<MUT_THREADS>(a.acc_partials, a.acc_P, sm_red);
+    __shared__ double sm_x[2];
+    if (threadIdx.x == 0) { sm_x[0] = root; sm_x[1] = root; }
+    __syncthreads();
+    if (a.pc.world > 1) peer_exchange_block(a.pc, sm_x, 1, 1, sm_x + 1);     // fixed rank-order tree over the shard roots
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.acc_out = sm_x[1];
+        if (a.acc_mean_out) *a.acc_mean_out = sm_x[1] / a.n_global;
+    }
 }
 
 // stage-0 evaluators: mode 0 = draw_likelihood (initialization.jl:129-139); mode 1 =

@@ -1,0 +1,672 @@
+// stage_kernels.cuh -- the fused per-stage kernels (src/smc_main.jl:377-465 without the host in the loop):
+//   k_correct_coop    ONE cooperative launch for solve_adaptive_phi (src/helpers.jl:9-56) + correction + ESS +
+//                     the resample decision (src/smc_main.jl:386-435); every decision is left in device scalars
+//   k_moments1p<D>    weighted mean / covariance in ONE pass over the cloud (src/particle.jl:481-532): a chunk's
+//                     columns arrive by bulk asynchronous copies (cp.async.bulk + mbarrier), eight warps share the
+//                     lower triangle
+//   k_moments_finish  tile trees of the one-pass sums; its last block exchanges them across GPUs, updates the step
+//                     size (src/smc_main.jl:453-455) and factors the proposal covariance (src/mutation.jl:81) with
+//                     the whole block -> MutConst
+#pragma once
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace smc {
+namespace cg = cooperative_groups;
+
+// =================================================================================================
+// Transition of solve_adaptive_phi (src/helpers.jl:26-54) over one sweep of K trial phi: consumes as many of the
+// K evaluations as the sequential algorithm would have made (the schedule walk, then up to log2(K+1) bisection levels),
+// i.e. the result is the one of the one-evaluation-at-a-time loop, bit for bit.  One thread.  sq: S_k then Q_k.
+// =================================================================================================
+template <int K>
+__device__ inline void phi_build_tree_k(PhiState* st)
+{
+    double a[K], b[K];
+    a[0] = st->lo; b[0] = st->hi;
+    for (int n = 0; n < K; ++n) {
+        const double mid = 0.5 * (a[n] + b[n]);
+        st->trial[n] = mid;
+        if (2 * n + 2 < K) { a[2 * n + 1] = a[n]; b[2 * n + 1] = mid; a[2 * n + 2] = mid; b[2 * n + 2] = b[n]; }
+    }
+}
+template <int K>
+__device__ inline void phi_fill_walk_k(PhiState* st, const double* sched)
+{
+    st->trial[0] = st->phi_prop;
+    for (int k = 1; k < K; ++k) {
+        long long idx = st->j - 1 + (k - 1);
+        if (idx > st->n_phi - 1) idx = st->n_phi - 1;
+        st->trial[k] = sched[idx];
+    }
+}
+template <int K>
+__device__ inline void phi_transition(PhiState* st, const double* __restrict__ sched, const double* sq)
+{
+    constexpr int LEVELS = (K == 1) ? 1 : (K == 3) ? 2 : (K == 7) ? 3 : 4;
+    static_assert(K == 1 || K == 3 || K == 7 || K == 15, "K must be 2^L - 1");
+    if (st->done) return;
+    bool finish = false;
+    if (st->phase == 0) {
+        int k = 0;
+        double g;
+        for (;;) {
+            g = (sq[k] * sq[k]) / sq[K + k] - st->ess_bar;
+            st->evals += 1; st->g_last = g;
+            if (g >= 0.0 && st->j <= st->n_phi) {
+                st->phi_prop = sched[st->j - 1];
+                st->j += 1;
+                st->phi_cur = st->phi_prop;
+                if (++k == K) { phi_fill_walk_k<K>(st, sched); return; }     // more schedule points next sweep
+                continue;
+            }
+            break;
+        }
+        if (st->phi_prop != 1.0 || g < 0.0) {
+            st->lo = st->phi_n1; st->hi = st->phi_prop; st->phase = 1;
+        } else {
+            st->phi_n = 1.0; st->done = 1;
+            return;
+        }
+    } else {
+        int node = 0;
+        for (int level = 0; level < LEVELS && !finish; ++level) {
+            const double mid = 0.5 * (st->lo + st->hi);
+            if (!(mid > st->lo && mid < st->hi)) { finish = true; break; }
+            const double g = (sq[node] * sq[node]) / sq[K + node] - st->ess_bar;
+            st->evals += 1; st->g_last = g;
+            if (g == 0.0) { st->lo = mid; finish = true; }
+            else if (g > 0.0) { st->lo = mid; node = 2 * node + 2; }      // continue in (mid, hi): right child
+            else { st->hi = mid; node = 2 * node + 1; }                   // continue in (lo, mid): left child
+        }
+    }
+    if (!finish) {
+        const double mid = 0.5 * (st->lo + st->hi);
+        if (mid > st->lo && mid < st->hi) { st->phi_cur = mid; phi_build_tree_k<K>(st); return; }
+    }
+    st->phi_n = (st->lo == st->phi_n1) ? st->hi : st->lo;
+    st->done = 1;
+}
+
+// =================================================================================================
+// k_correct_coop: one cooperative launch per stage for everything up to the resample decision.
+// Block b owns the `tpb` (power of two) consecutive 1024-element tiles [b tpb, (b+1) tpb) of this shard, so its partial
+// is a subtree of the canonical tile tree; block 0 finishes the tree (one warp per quantity), exchanges the shard
+// roots with the other GPUs in place (NVLink mailboxes) and publishes the result between two grid barriers.
+//   adaptive: sweeps of CK trial phi (compute_ESS, helpers.jl:173-181) drive the bisection state machine until the
+//             bracket is exhausted -- the three columns stay in L1/L2, there is no host poll and no extra launch;
+//   pass A:   w~ = w * inc, S = sum w~                      (smc_main.jl:401-413, particle.jl:250-259)
+//   pass B:   W = (w~ N) / S, Q = sum W^2, sum W, sum W/N   (particle.jl:362-369, smc_main.jl:427)
+//   decision: ESS = N^2 / Q, resample iff ESS < threshold_ratio N (smc_main.jl:435); NaN ESS poisons the stage.
+// =================================================================================================
+struct CoopArgs {
+    const double* ll; const double* old; double* w;   // loglh, old_loglh, weight columns of this shard
+    double* inc_out; double* normw_out;               // nullable: w_matrix / W_matrix columns of this stage
+    int64_t N; double n_global;
+    int ntiles, tpb, Pb;
+    CorrArgs corr;
+    double threshold_ratio;
+    int adaptive, solve_only, use_carry;
+    const double* sched; int n_phi; double tempering_target;
+    double c_in, accept_in, ess_prev_in, phi_prop_in; long long j_in; int resampled_last_in;
+    double* partials;                                 // [max(2 CK, 3)][Pb], entries >= gridDim.x stay zero
+    double* scal;
+    PhiState* st;
+    PeerCtx pc;
+};
+
+// sums of NQ per-thread quantities over this block's tiles in the canonical order: `lane_sums(t, v)` gives the thread's
+// lane sums of tile t; returns (thread q < NQ) the block's subtree sum of quantity q
+template <int NQ, class F>
+__device__ __forceinline__ double coop_block_sums(const CoopArgs& a, double (*sm)[8], F lane_sums)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double stack[12];
+    int sp = 0;
+    for (int tt = 0; tt < a.tpb; ++tt) {
+        const int64_t tile = (int64_t)blockIdx.x * a.tpb + tt;
+        double v[NQ];
+        lane_sums(tile, v);
+        __syncthreads();                 // protects sm against the previous round's readers
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double s = warp_tree(v[q]);
+            if (lane == 0) sm[q][warp] = s;
+        }
+        __syncthreads();
+        if (tid < NQ) {
+            const double* r = sm[tid];
+            double x = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            int k = tt;
+            while (k & 1) { x = stack[--sp] + x; k >>= 1; }
+            stack[sp++] = x;
+        }
+    }
+    return (tid < NQ) ? stack[0] : 0.0;
+}
+
+// block 0: finish the tile tree of NQ quantities (one warp per quantity), cross the GPUs, leave the results in res[]
+// (shared memory, valid for every thread of block 0 after the call)
+template <int NQ>
+__device__ __forceinline__ void coop_root(const CoopArgs& a, double* res /* smem [NQ] */, double* tmp /* smem [NQ] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < NQ; q += 8) {
+        const double r = tiles_tree_warp(a.partials + (size_t)q * a.Pb, a.Pb);
+        if (lane == 0) tmp[q] = r;
+    }
+    __syncthreads();
+    if (a.pc.world > 1) peer_exchange_block(a.pc, tmp, NQ, 1, res);
+    else if ((int)threadIdx.x < NQ) res[threadIdx.x] = tmp[threadIdx.x];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_correct_coop(CoopArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    constexpr int NQMAX = (2 * CK > 3) ? 2 * CK : 3;
+    __shared__ double sm[NQMAX][8];
+    __shared__ double res[NQMAX], tmpq[NQMAX];
+    const int tid = threadIdx.x;
+    const bool lead = (blockIdx.x == 0 && tid == 0);
+    double* scal = a.scal;
+    PhiState* st = a.st;
+    double phi_n = a.corr.phi_n;
+    const double phi_n1 = a.corr.phi_n1;
+
+    if (lead) {
+        if (!a.use_carry) { scal[SC_C] = a.c_in; scal[SC_ACCEPT] = a.accept_in; scal[SC_STATUS] = 0.0; }
+        scal[SC_EVALS] = 0.0; scal[SC_SWEEPS] = 0.0;
+    }
+    // ---- solve_adaptive_phi -------------------------------------------------------------------------
+    if (a.adaptive) {
+        if (lead) {
+            st->ess_bar = a.resampled_last_in ? a.tempering_target * a.n_global : a.tempering_target * a.ess_prev_in;   // helpers.jl:14-20
+            st->phi_prop = a.phi_prop_in; st->phi_cur = a.phi_prop_in; st->phi_n1 = phi_n1; st->phi_n = 0.0;
+            st->j = a.j_in; st->n_phi = a.n_phi; st->phase = 0; st->done = 0; st->evals = 0; st->g_last = 0.0;
+            st->lo = 0.0; st->hi = 0.0;
+            phi_fill_walk_k<CK>(st, a.sched);
+            __threadfence();
+        }
+        grid.sync();
+        int sweeps = 0;
+        for (;;) {
+            if (*reinterpret_cast<volatile int*>(&st->done)) break;         // grid-uniform: written before the last barrier
+            double phi[CK];
+#pragma unroll
+            for (int k = 0; k < CK; ++k) phi[k] = __ldcg(&st->trial[k]);
+            const double part = coop_block_sums<2 * CK>(a, sm, [&](int64_t tile, double (&v)[2 * CK]) {
+#pragma unroll
+                for (int q = 0; q < 2 * CK; ++q) v[q] = 0.0;
+                const int64_t base = tile * W_TILE + tid;
+#pragma unroll
+                for (int r = 0; r < W_R; ++r) {
+                    const int64_t i = base + (int64_t)r * W_LANES;
+                    if (i < a.N) {
+                        const double l = __ldg(a.ll + i), o = __ldg(a.old + i), wi = a.w[i];
+#pragma unroll
+                        for (int k = 0; k < CK; ++k) {
+                            const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
+                            v[k] = v[k] + x;
+                            v[CK + k] = v[CK + k] + x * x;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CK; ++k) { v[k] = v[k] + 0.0; v[CK + k] = v[CK + k] + 0.0 * 0.0; }
+                    }
+                }
+            });
+            if (tid < 2 * CK) __stcg(a.partials + (size_t)tid * a.Pb + blockIdx.x, part);
+            __threadfence();
+            grid.sync();
+            if (blockIdx.x == 0) {
+                coop_root<2 * CK>(a, res, tmpq);
+                if (tid == 0) {
+                    phi_transition<CK>(st, a.sched, res);
+                    __threadfence();
+                }
+            }
+            ++sweeps;
+            grid.sync();
+        }
+        phi_n = __ldcg(&st->phi_n);
+        if (lead) {
+            scal[SC_J] = (double)st->j; scal[SC_PHI_PROP] = st->phi_prop; scal[SC_EVALS] = (double)st->evals;
+            scal[SC_SWEEPS] = (double)sweeps;
+        }
+    }
+    if (lead) { scal[SC_PHI_N] = phi_n; scal[SC_PHI_N1] = phi_n1; }
+    if (a.solve_only) return;
+
+    // ---- pass A: incremental weights, unnormalised weights, S ------------------------------------------
+    {
+        const double part = coop_block_sums<1>(a, sm, [&](int64_t tile, double (&v)[1]) {
+            const int64_t base = tile * W_TILE + tid;
+            double x[W_R];
+#pragma unroll
+            for (int r = 0; r < W_R; ++r) {
+                const int64_t i = base + (int64_t)r * W_LANES;
+                x[r] = 0.0;
+                if (i < a.N) {
+                    const double inc = inc_weight(__ldg(a.ll + i), __ldg(a.old + i), a.corr, phi_n);
+                    x[r] = a.w[i] * inc;
+                    a.w[i] = x[r];
+                    if (a.inc_out) a.inc_out[i] = inc;
+                }
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < W_R; ++r) acc = acc + x[r];
+            v[0] = acc;
+        });
+        if (tid == 0) __stcg(a.partials + blockIdx.x, part);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) {
+            coop_root<1>(a, res, tmpq);
+            if (tid == 0) { scal[SC_S] = res[0]; __threadfence(); }
+        }
+        grid.sync();
+    }
+    // ---- pass B: normalised weights, Q = sum W^2, sum W, sum W / n_parts ----------------------------------
+    {
+        const double S = __ldcg(scal + SC_S);
+        const double part = coop_block_sums<3>(a, sm, [&](int64_t tile, double (&v)[3]) {
+            const int64_t base = tile * W_TILE + tid;
+            double x[W_R], y[W_R];
+#pragma unroll
+            for (int r = 0; r < W_R; ++r) {
+                const int64_t i = base + (int64_t)r * W_LANES;
+                x[r] = 0.0; y[r] = 0.0;
+                if (i < a.N) {
+                    x[r] = (a.w[i] * a.n_global) / S;
+                    y[r] = x[r] / a.n_global;                 // normalized_weights / n_parts, smc_main.jl:438
+                    a.w[i] = x[r];
+                    if (a.normw_out) a.normw_out[i] = x[r];
+                }
+            }
+            double q = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < W_R; ++r) { q = q + x[r] * x[r]; s2 = s2 + x[r]; s3 = s3 + y[r]; }
+            v[0] = q; v[1] = s2; v[2] = s3;
+        });
+        if (tid < 3) __stcg(a.partials + (size_t)tid * a.Pb + blockIdx.x, part);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) {
+            coop_root<3>(a, res, tmpq);
+            if (tid == 0) {
+                const double n = a.n_global;
+                const double ess = (n * n) / res[0];                            // smc_main.jl:427
+                scal[SC_Q] = res[0]; scal[SC_S2] = res[1]; scal[SC_SRES] = res[2];
+                scal[SC_ESS] = ess;
+                const bool nan = (ess != ess);                                  // check_nan_ess, helpers.jl:270-305
+                if (nan) scal[SC_STATUS] = (double)SMCB200_ERR_NAN_ESS;
+                scal[SC_RESAMPLE] = (!nan && scal[SC_STATUS] == 0.0 && ess < a.threshold_ratio * n) ? 1.0 : 0.0;   // smc_main.jl:435
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// One-pass moments.  With x0 = the parameter vector of global particle 0 (any point of the cloud's support) as shift,
+//   Sw = sum w,  m_k = sum w (x_k - x0_k),  C_ab = sum (w (x_a - x0_a)) (x_b - x0_b)
+//   mean_k = x0_k + m_k / Sw,   cov_ab = C_ab / Sw - (m_a / Sw)(m_b / Sw)
+// which is weighted_mean / weighted_cov (src/particle.jl:481-532; StatsBase.cov(..., corrected = false)) in one sweep
+// instead of two (the reference's two-pass result differs from it by rounding only: ~1e-15 relative).
+// Canonical order per quantity: inside a chunk of M2_CH = 512 consecutive particles lane l accumulates particles
+// l, l + 32, ... sequentially, then the adjacent-pair tree over the 32 lanes, then over chunks.
+// Mapping: one block of 8 warps per chunk.  The chunk's d + 1 columns (86 KB at d = 20) arrive in two halves by bulk
+// asynchronous copies (cp.async.bulk, 2 KB each, completion on one mbarrier per half), so the first half is reduced
+// while the second is still in flight and two resident blocks per SM keep ~170 KB outstanding; lane = particle and
+// warp g owns the rows [rowb(g), rowb(g+1)) of the lower triangle (~26 register accumulators at d = 20).
+// Partials layout: [1 + d + d(d+1)/2][P] with quantity 0 = Sw, 1 + k = m_k, 1 + d + a(a+1)/2 + b = C_ab.
+// =================================================================================================
+constexpr int M1P_G = 4;
+template <int D>
+__host__ __device__ constexpr int m1p_rowb(int g)
+{
+    int a = 0;
+    while (a < D && (a * (a + 1)) / 2 * M1P_G < g * (D * (D + 1) / 2)) ++a;
+    return g >= M1P_G ? D : a;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+// One row group of the lower triangle over one chunk.  The two halves of the chunk are consumed as they arrive; each
+// half is centred in place (x <- x - x0, all threads) before the accumulation, so every warp reads ready differences.
+// Every thread of the block must call this (block barriers inside).
+template <int D, int GRP>
+__device__ __forceinline__ void m1p_group(double* __restrict__ xs /* smem [D+1][M2_CH] */, int64_t N, int64_t c0, int lane,
+                                          const double* __restrict__ shift, uint64_t* bars, bool bulk, double* __restrict__ red)
+{
+    constexpr int A0 = m1p_rowb<D>(GRP), A1 = m1p_rowb<D>(GRP + 1);
+    constexpr int NR = (A1 > A0) ? (A1 - A0) : 1;
+    constexpr int NC = (A1 > 0) ? A1 : 1;
+    constexpr int NT = 32 * M1P_G, HALF = M2_CH / 2;
+    double acc[NR][NC], m1[NR];
+#pragma unroll
+    for (int a = 0; a < NR; ++a) {
+        m1[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < NC; ++b) acc[a][b] = 0.0;
+    }
+    double sw = 0.0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        if (bulk) mbar_wait(bars + half, 0u);
+        for (int idx = threadIdx.x; idx < D * HALF; idx += NT) {
+            const int k = idx / HALF, p = idx % HALF;
+            xs[k * M2_CH + half * HALF + p] = xs[k * M2_CH + half * HALF + p] - shift[k];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int r = half * (HALF / 32); r < (half + 1) * (HALF / 32); ++r) {
+            const int64_t i = c0 + (int64_t)r * 32 + lane;
+            if (i < N) {
+                const double wi = xs[D * M2_CH + r * 32 + lane];
+                if (GRP == 0) sw = sw + wi;
+                if (A1 > A0) {
+                    double dx[NC];
+#pragma unroll
+                    for (int k = 0; k < A1; ++k) dx[k] = xs[k * M2_CH + r * 32 + lane];
+#pragma unroll
+                    for (int a = A0; a < A1; ++a) {
+                        m1[a - A0] = fma(wi, dx[a], m1[a - A0]);
+                        const double wa = wi * dx[a];
+#pragma unroll
+                        for (int b = 0; b <= a; ++b) acc[a - A0][b] = fma(wa, dx[b], acc[a - A0][b]);
+                    }
+                }
+            }
+        }
+    }
+    // per-lane sums -> shared memory rows [quantity][lane] (row stride 33: conflict-free for the row-wise tree that
+    // follows); the rows alias the staged columns, so every warp of the block must have finished reading them
+    __syncthreads();
+    if (GRP == 0) red[lane] = sw;
+    if (A1 > A0) {
+#pragma unroll
+        for (int a = A0; a < A1; ++a) {
+            red[(1 + a) * 33 + lane] = m1[a - A0];
+#pragma unroll
+            for (int b = 0; b <= a; ++b) red[(1 + D + a * (a + 1) / 2 + b) * 33 + lane] = acc[a - A0][b];
+        }
+    }
+}
+
+// wcol: the weight column (current buffer); x0 / x1: the parameter columns (x1 = the gather target, used when
+// scal[SC_RESAMPLE] != 0); shift_base[k * shift_stride] = parameter k of global particle 0
+template <int D>
+__global__ void __launch_bounds__(32 * M1P_G, 2)
+k_moments1p(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ wcol, int64_t N,
+            const double* __restrict__ scal, const double* __restrict__ shift_base, int64_t shift_stride,
+            double* __restrict__ partials, int P)
+{
+    extern __shared__ __align__(16) double sm_m1[];      // [D + 1][M2_CH]: parameter columns, then the weight column
+    __shared__ double shift[D];
+    __shared__ __align__(8) uint64_t bars[2];
+    if (scal && scal[SC_STATUS] != 0.0) return;
+    const double* __restrict__ X = (scal && scal[SC_RESAMPLE] != 0.0) ? x1 : x0;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x;
+    const int64_t c0 = chunk * M2_CH;
+    constexpr int NT = 32 * M1P_G;
+    const bool bulk = (c0 + M2_CH <= N) && ((N & 1) == 0);     // 16-byte aligned column segments
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bars, 1); mbar_init(bars + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            constexpr unsigned HB = (M2_CH / 2) * sizeof(double);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                mbar_expect_tx(bars + half, (unsigned)(D + 1) * HB);
+#pragma unroll 1
+                for (int k = 0; k <= D; ++k) {
+                    const double* col = (k < D) ? X + col_off(N, k) : wcol;
+                    bulk_g2s(sm_m1 + k * M2_CH + half * (M2_CH / 2), col + c0 + half * (M2_CH / 2), HB, bars + half);
+                }
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < (D + 1) * M2_CH; idx += NT) {
+            const int k = idx / M2_CH, p = idx % M2_CH;
+            const int64_t i = c0 + p;
+            sm_m1[idx] = (i < N) ? ((k < D) ? X[col_off(N, k) + i] : wcol[i]) : 0.0;
+        }
+    }
+    if (threadIdx.x < D) shift[threadIdx.x] = shift_base[(size_t)threadIdx.x * shift_stride];
+    __syncthreads();
+    double* red = sm_m1;                       // [NQ][33] per-lane sums, aliasing the staged columns once every warp is done
+    switch (g) {     // warp-uniform: each group is compiled with static row bounds (register-resident accumulators)
+    case 0: m1p_group<D, 0>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
+    case 1: m1p_group<D, 1>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
+    case 2: m1p_group<D, 2>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
+    default: m1p_group<D, 3>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
+    }
+    __syncthreads();
+    // adjacent-pair tree over the 32 lanes of every quantity, one thread per quantity (registers)
+    constexpr int NQ = 1 + D + D * (D + 1) / 2;
+    for (int q = threadIdx.x; q < NQ; q += NT) {
+        double v[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) v[l] = red[q * 33 + l];
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1)
+#pragma unroll
+            for (int l = 0; l < 32; l += 2 * sft) v[l] = v[l] + v[l + sft];
+        partials[(size_t)q * P + chunk] = v[0];
+    }
+}
+
+// any d <= DMAX (no shared-memory staging; warps over quantities); same order
+__global__ void __launch_bounds__(128)
+k_moments1p_generic(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ wcol, int64_t N, int d,
+                    const double* __restrict__ scal, const double* __restrict__ shift_base, int64_t shift_stride,
+                    double* __restrict__ partials, int P)
+{
+    if (scal && scal[SC_STATUS] != 0.0) return;
+    const double* __restrict__ X = (scal && scal[SC_RESAMPLE] != 0.0) ? x1 : x0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x;
+    const int64_t c0 = chunk * M2_CH;
+    const int E = d * (d + 1) / 2, nq = 1 + d + E;
+    for (int q = warp; q < nq; q += 4) {
+        int a = 0, b = 0;
+        if (q > d) {
+            const int e = q - 1 - d;
+            while ((a + 1) * (a + 2) / 2 <= e) ++a;
+            b = e - a * (a + 1) / 2;
+        } else if (q >= 1) {
+            a = q - 1;
+        }
+        const double sa = shift_base[(size_t)a * shift_stride], sb = shift_base[(size_t)b * shift_stride];
+        const double* xa = X + col_off(N, a);
+        const double* xb = X + col_off(N, b);
+        double acc = 0.0;
+        for (int r = 0; r < M2_CH / 32; ++r) {
+            const int64_t i = c0 + (int64_t)r * 32 + lane;
+            if (i < N) {
+                if (q == 0) acc = acc + wcol[i];
+                else if (q <= d) acc = fma(wcol[i], xa[i] - sa, acc);
+                else acc = fma(wcol[i] * (xa[i] - sa), xb[i] - sb, acc);
+            }
+        }
+        acc = warp_tree(acc);
+        if (lane == 0) partials[(size_t)q * P + chunk] = acc;
+    }
+}
+
+// Proposal preparation with the whole block: mean, covariance, step size, per-block Cholesky -> MutConst.
+// Same per-element arithmetic as build_mutconst() / cholesky_lower() (each L_ij is the same fma chain over k ascending).
+struct PrepSmem {
+    double cov[DMAX][DMAX + 1], S[DMAX][DMAX + 1], L[DMAX][DMAX + 1];
+    double mean[DMAX], e[DMAX], logs[DMAX];
+    int bad;
+};
+__device__ __forceinline__ void prepare_proposal_block(PrepSmem& sm, const BlockSpec& bs, double c, MutConst* out, double* scal)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+    const int d = bs.d;
+    if (tid == 0) { out->n_blocks = bs.n_blocks; out->status = 0; sm.bad = 0; }
+    if (tid < DMAX) out->mu[tid] = (tid < d) ? sm.mean[tid] : 0.0;
+    __syncthreads();
+    for (int b = 0; b < bs.n_blocks; ++b) {
+        const int n = bs.bsize[b];
+        for (int e = tid; e < PACKMAX; e += nt) out->L[b][e] = 0.0;
+        if (tid < DMAX) { out->csd[b][tid] = 0.0; out->isd[b][tid] = 0.0; out->isdn[b][tid] = 0.0; out->rl[b][tid] = 0.0; }
+        if (tid == 0) {
+            uint32_t mask = 0;
+            for (int i = 0; i < n; ++i) mask |= 1u << bs.member[b][i];
+            out->mask[b] = mask; out->bsize[b] = n;
+        }
+        for (int e = tid; e < n * n; e += nt) {
+            const int i = e / n, j = e % n;
+            const int ai = bs.member[b][i], aj = bs.member[b][j];
+            sm.S[i][j] = (sm.cov[ai][aj] + sm.cov[aj][ai]) / 2.0;          // R_fr = (R + R') / 2, smc_main.jl:462
+        }
+        __syncthreads();
+        if (warp == 0) {
+            bool bad = false;
+            for (int j = 0; j < n; ++j) {
+                double sv = 0.0;
+                if (lane >= j && lane < n) {
+                    sv = sm.S[lane][j];
+                    for (int k = 0; k < j; ++k) sv = fma(-sm.L[lane][k], sm.L[j][k], sv);
+                }
+                const double sj = __shfl_sync(0xffffffffu, sv, j);
+                if (!(sj > 0.0)) { bad = true; break; }
+                const double dj = sqrt(sj);
+                if (lane == j) sm.L[j][j] = dj;
+                else if (lane > j && lane < n) sm.L[lane][j] = sv / dj;
+                __syncwarp();
+            }
+            if (bad && lane == 0) sm.bad = 1;
+        }
+        __syncthreads();
+        if (sm.bad) {
+            if (tid == 0) { out->status = SMCB200_ERR_NOT_POSDEF; if (scal) scal[SC_STATUS] = (double)SMCB200_ERR_NOT_POSDEF; }
+            return;
+        }
+        for (int e = tid; e < n * n; e += nt) {
+            const int i = e / n, j = e % n;
+            if (j <= i) {
+                const int ai = bs.member[b][i], aj = bs.member[b][j];
+                out->L[b][aj * d - (aj * (aj - 1)) / 2 + (ai - aj)] = c * sm.L[i][j];
+            }
+        }
+        if (tid < n) {
+            const int ai = bs.member[b][tid];
+            out->csd[b][ai] = c * sqrt(sm.S[tid][tid]);
+            const double isd = 1.0 / sqrt(sm.S[tid][tid]);
+            out->isd[b][ai] = isd;
+            out->isdn[b][ai] = isd * 0x1.9884533d43651p-2;
+            out->rl[b][ai] = 1.0 / (c * sm.L[tid][tid]);
+            sm.logs[tid] = det_log(c * sm.L[tid][tid]);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double ld = 0.0;
+            for (int i = 0; i < n; ++i) ld = ld + sm.logs[i];
+            out->lognorm[b] = (double)n * (2.0 * 0.91893853320467274178) + 2.0 * ld;
+        }
+        __syncthreads();
+    }
+}
+
+// One block per quantity reduces its chunk partials; the last block to finish crosses the GPUs, forms mean / cov, updates
+// the step size c <- c f(accept) (smc_main.jl:453-455; both live in scal[]) and prepares the proposal.
+__global__ void __launch_bounds__(256)
+k_moments_finish(const double* __restrict__ partials, int P, int nq, double* __restrict__ sums_loc, double* __restrict__ sums,
+                 unsigned* counter, PeerCtx pc, const double* __restrict__ shift_base, int64_t shift_stride, BlockSpec bs,
+                 double target, double* scal, MutConst* out)
+{
+    __shared__ double smr[8];
+    __shared__ bool is_last;
+    __shared__ PrepSmem ps;
+    if (scal[SC_STATUS] != 0.0) return;
+    const double r = tiles_tree_block<256>(partials + (size_t)blockIdx.x * P, P, smr);
+    if (threadIdx.x == 0) {
+        __stcg(sums_loc + blockIdx.x, r);
+        __threadfence();
+        const unsigned t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (pc.world > 1) peer_exchange_block(pc, sums_loc, nq, 1, sums);
+    else for (int q = threadIdx.x; q < nq; q += blockDim.x) sums[q] = __ldcg(sums_loc + q);
+    __syncthreads();
+    const int d = bs.d;
+    const double sw = sums[0];
+    if ((int)threadIdx.x < d) {
+        const double e = sums[1 + threadIdx.x] / sw;
+        ps.e[threadIdx.x] = e;
+        ps.mean[threadIdx.x] = shift_base[(size_t)threadIdx.x * shift_stride] + e;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < d * (d + 1) / 2; q += blockDim.x) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= q) ++a;
+        const int b = q - a * (a + 1) / 2;
+        const double v = fma(-ps.e[a], ps.e[b], sums[1 + d + q] / sw);
+        ps.cov[a][b] = v;
+        ps.cov[b][a] = v;
+    }
+    __shared__ double c_new;
+    if (threadIdx.x == 0) {
+        c_new = update_step_size(scal[SC_C], scal[SC_ACCEPT], target);
+        scal[SC_C] = c_new;
+    }
+    __syncthreads();
+    prepare_proposal_block(ps, bs, c_new, out, scal);
+}
+
+// ---- FP64 peak probe (bench.py's roofline_fp64 denominator): 8 independent DFMA chains per thread ------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace smc

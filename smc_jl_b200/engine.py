@@ -196,6 +196,13 @@ class Engine:
         self._ck(lib.smcb200_moments(self.h, ptr(mean), ptr(cov)))
         return mean, cov
 
+    def moments_onepass(self):
+        """The stage's own one-pass moments (shift = particle 0); equals moments() up to rounding."""
+        mean = np.zeros(self.n_para)
+        cov = np.zeros((self.n_para, self.n_para))
+        self._ck(lib.smcb200_moments_onepass(self.h, ptr(mean), ptr(cov)))
+        return mean, cov
+
     def mutate(self, mean_fr, cov_fr, blocks_free, blocks_all, phi_n, phi_n1, c=1.0, alpha=1.0, n_mh_steps=1,
                has_old_data=False, seed=0, stage=0):
         """blocks_*: list of 0-based index lists (generate_free_blocks / generate_all_blocks)."""
@@ -221,6 +228,22 @@ class Engine:
         self._ck(lib.smcb200_stage(self.h, C.byref(cfg), C.byref(state), ptr(sched), 0 if sched is None else len(sched),
                                    ptr(inc), ptr(nw), C.byref(res)))
         return res, inc, nw
+
+    def run_stages(self, cfg: StageConfig, state: StageState, schedule, i_first, n_stages, inc_hist=None, normw_hist=None):
+        """Up to n_stages consecutive stages of the recursion in ONE call (smcb200_run_stages): stage k is the reference's loop
+        index i = i_first + k.  inc_hist / normw_hist: optional float64 arrays of shape (n_stages, shard length), C order
+        (row k = the w_matrix / W_matrix column of stage k); pinned memory keeps their streaming asynchronous.
+        Returns the list of StageResult of the completed stages."""
+        sched = _f64(schedule)
+        for b in (inc_hist, normw_hist):
+            assert b is None or (b.dtype == np.float64 and b.shape == (n_stages, self.count) and b.flags.c_contiguous)
+        results = (StageResult * int(n_stages))()
+        n_done = C.c_int32(0)
+        st = lib.smcb200_run_stages(self.h, C.byref(cfg), C.byref(state), ptr(sched), len(sched), int(i_first), int(n_stages),
+                                    ptr(inc_hist), ptr(normw_hist), self.count, results, C.byref(n_done))
+        self.last_results = [results[k] for k in range(n_done.value)]
+        self._ck(st)
+        return self.last_results
 
     def stage_host(self, particles, cfg: StageConfig, state: StageState, schedule=None):
         """One stage on a host-resident cloud (Fortran-ordered, updated in place)."""
@@ -248,6 +271,12 @@ class Engine:
         ms = C.c_float()
         self._ck(lib.smcb200_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def fp64_peak(self, iters=2048):
+        """Measured FP64 FMA throughput of this GPU in TFLOP/s (denominator of the FP64 roofline)."""
+        out = C.c_double()
+        self._ck(lib.smcb200_fp64_peak(self.h, int(iters), C.byref(out)))
+        return out.value
 
     def debug_math(self, op, x, seed=0):
         x = _f64(x)

@@ -88,12 +88,12 @@ def main():
     cl = j["cloud"]
     w, W = j["w"], j["W"]
     n_stage = w.shape[1]
-    # keep every stage's ESS/schedule (small) but only a subset of full weight columns
-    keep = sorted(set([1, 2, 3, 4, 5, 10, 20, 33, 47, 60, 75, 90, 105, 118, 119]))  # 0-based stage columns n (n>=1)
+    # every one of the 119 correction stages: W[:, n-1], w[:, n] -> W[:, n] (float64, 5000 x 120 each; savez_compressed)
+    keep = list(range(1, n_stage))
     save("correction_history.npz",
          ESS=cl["ESS"], tempering_schedule=cl["tempering_schedule"], resamples=cl["resamples"],
          n_parts=w.shape[0], n_stage=n_stage, c=cl["c"], accept=cl["accept"],
-         stages=np.array(keep), W_prev=W[:, [k - 1 for k in keep]], w_inc=w[:, keep], W_new=W[:, keep],
+         stages=np.array(keep), w=w, W=W,
          final_particles=cl["particles"][::10].copy(),       # thinned: statistical anchor only
          final_mean=np.average(cl["particles"][:, :9], axis=0, weights=cl["particles"][:, -1]),
          sumsq_W=np.sum(W.astype(np.float64) ** 2, axis=0))

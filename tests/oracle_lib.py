@@ -15,7 +15,7 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("smc_oracle.c", "as_model.c")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("smc_oracle.c", "as_model.c", "normal_table.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"], env={**os.environ, "CC": "gcc"})
     return _SO
@@ -64,6 +64,7 @@ def lib():
         "orc_gather": (None, [f64p, f64p, i64, C.c_int, i64p]),
         "orc_update_c": (d, [d, d, d]),
         "orc_moments": (None, [f64p, i64, C.c_int, f64p, f64p]),
+        "orc_moments_shifted": (None, [f64p, i64, C.c_int, f64p, f64p, f64p]),
         "orc_mean_accept": (d, [f64p, i64, C.c_int]),
         "orc_cholesky": (C.c_int, [f64p, C.c_int, f64p]),
         "orc_model_create": (vp, [C.c_int]), "orc_model_free": (None, [vp]),

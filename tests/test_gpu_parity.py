@@ -505,7 +505,117 @@ def test_stage_trajectory_adaptive_bitexact(eng):
     assert 0.0 < phi <= 1.0
 
 
-# ---- full-size (BASELINE config C2) property tests: the oracle is too slow there ------------------
+def test_moments_onepass_bitexact(eng):
+    """The fused stage's one-pass moments (shift = particle 0): bit-identical to the oracle's restatement of the same sums,
+    equal to the reference's two-pass weighted_mean / weighted_cov (src/particle.jl:481-532) to rounding -- also for a cloud
+    whose mean is 1e4 standard deviations away from the origin (where an unshifted one-pass formula would lose 8 digits)."""
+    for N, d, offset in ((5000, 9, 0.0), (4096, 20, 0.0), (70001, 2, 0.0), (3000, 5, 0.0), (12289, 7, 1e4), (6000, 20, -3e3)):
+        rng = np.random.default_rng(N + d)
+        P = rand_cloud(rng, N, d)
+        P[:, :d] += offset
+        P[:, d + 4] *= N / P[:, d + 4].sum()
+        params, lk, _ = W.linear_gaussian(d=d, T=32)
+        eng.cloud_create(N, d)
+        eng.set_model(M.make_spec(params, lk))
+        eng.upload(P)
+        mean, cov = eng.moments_onepass()
+        omean, ocov = np.zeros(d), np.zeros((d, d))
+        O.lib().orc_moments_shifted(O.cloud_f(P), N, d, np.ascontiguousarray(P[0, :d]), omean, ocov)
+        assert np.array_equal(mean, omean) and np.array_equal(cov, ocov), (N, d)
+        m2, c2 = eng.moments()                                          # two-pass form
+        scale = np.sqrt(np.outer(np.diag(c2), np.diag(c2)))
+        assert np.max(np.abs(mean - m2) / np.sqrt(np.diag(c2))) < 1e-10
+        assert np.max(np.abs(cov - c2) / scale) < 1e-10
+        assert np.array_equal(eng.download(), P)                       # the cloud itself is untouched
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_run_stages_matches_the_oracle_trajectory(eng, adaptive):
+    """smcb200_run_stages: the whole recursion in one call (no host in the loop on a fixed schedule) gives the per-stage
+    results, the w / W history columns and the final cloud of the oracle's stage-by-stage loop, bit for bit."""
+    from smc_jl_b200._lib import StageConfig, StageState
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters(prior_para=10.0)
+    spec = M.make_spec(params, M.LinearEquationsLogLik(data, X))
+    N, d = 6000, 9
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(21))
+    n_phi = 30
+    sched = (np.arange(n_phi) / (n_phi - 1.0)) ** 2.1
+    eng.upload(P0)
+    state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2, resampled_last_period=0)
+    cfg = StageConfig(phi_n1=0.0, phi_n=0.0, threshold_ratio=0.5, target=0.25, alpha=0.9, tempering_target=0.9,
+                      n_mh_steps=2, n_blocks=2, resample_method=0, adaptive=int(adaptive), seed=99, stage=0)
+    n_max = n_phi - 1 if not adaptive else 200
+    inc_h, nw_h = np.zeros((n_max, N)), np.zeros((n_max, N))
+    results = eng.run_stages(cfg, state, sched, 2, n_max, inc_hist=inc_h, normw_hist=nw_h)
+    assert results[-1].phi_n == 1.0
+    if not adaptive:
+        assert len(results) == n_phi - 1
+    got = eng.download()
+    # oracle, one stage at a time
+    io = O.StageIO(threshold_ratio=0.5, target=0.25, alpha=0.9, tempering_target=0.9, pw=0.0, log_prob_old_data=0.0,
+                   n_mh_steps=2, n_blocks=2, resample_method=0, adaptive=int(adaptive), has_old=0, nthreads=0, seed=99, c=0.5,
+                   accept=0.25, ess_prev=float(N), resampled_last=0, j=2, phi_prop=0.0)
+    mod = O.Model(spec)
+    buf = O.cloud_f(P0)
+    scratch = np.zeros_like(buf)
+    phi_prev, n_res = 0.0, 0
+    for k, res in enumerate(results):
+        io.phi_n1, io.phi_n, io.stage = phi_prev, float(sched[min(k + 1, n_phi - 1)]), k + 2
+        oinc, onw = np.zeros(N), np.zeros(N)
+        assert O.lib().orc_stage(mod.h, buf, scratch, N, np.ascontiguousarray(sched), n_phi, C.byref(io),
+                                 oinc.ctypes.data_as(C.c_void_p), onw.ctypes.data_as(C.c_void_p), None, None) == 0
+        assert (res.phi_n, res.ess, res.sum_weights, res.c, res.accept, res.resampled) == \
+               (io.phi_out, io.ess, io.sum_w, io.c, io.accept, io.resampled), k
+        assert np.array_equal(inc_h[k], oinc) and np.array_equal(nw_h[k], onw), k
+        phi_prev = io.phi_out
+        n_res += io.resampled
+    assert n_res >= 2 and phi_prev == 1.0
+    assert np.array_equal(got, O.cloud_m(buf, N, d))
+    assert (state.c, state.accept, state.ess_prev) == (io.c, io.accept, io.ess)
+
+
+def test_full_size_c2_bitexact_against_the_oracle(eng):
+    """BASELINE config C2 at its FULL size (d = 20, N = 2^20, n_mh_steps = 3): the first stages of the real schedule,
+    including one that resamples, against the CPU oracle -- identical ESS / c / accept, identical clouds
+    (np.array_equal on all 2^20 x 25 doubles), hence posterior mean / std far inside the 1e-6 relative target."""
+    from smc_jl_b200._lib import StageConfig, StageState
+    params, lk, _ = W.linear_gaussian(d=20, T=256)
+    spec = M.make_spec(params, lk)
+    N, d = 1 << 20, 20
+    P0 = _evaluated_cloud(eng, spec, params, N, np.random.default_rng(11))
+    mod = O.Model(spec)
+    buf = O.cloud_f(P0)
+    scratch = np.zeros_like(buf)
+    sched = ((np.arange(300)) / 299.0) ** 2.1
+    thr = 0.9                                                      # resample early (the reference default 0.5 needs more stages)
+    state = StageState(c=0.5, accept=0.25, ess_prev=float(N), phi_prop=0.0, j=2, resampled_last_period=0)
+    io = O.StageIO(threshold_ratio=thr, target=0.25, alpha=1.0, tempering_target=0.95, pw=0.0, log_prob_old_data=0.0,
+                   n_mh_steps=3, n_blocks=1, resample_method=0, adaptive=0, has_old=0, nthreads=0, seed=1793, c=0.5, accept=0.25,
+                   ess_prev=float(N), resampled_last=0, j=2, phi_prop=0.0)
+    eng.upload(P0)
+    resamples = 0
+    for s in range(8):
+        cfg = StageConfig(phi_n1=float(sched[s]), phi_n=float(sched[s + 1]), threshold_ratio=thr, target=0.25, alpha=1.0,
+                          tempering_target=0.95, n_mh_steps=3, n_blocks=1, resample_method=0, seed=1793, stage=s + 2)
+        res, _, _ = eng.stage(cfg, state)
+        io.phi_n1, io.phi_n, io.stage = float(sched[s]), float(sched[s + 1]), s + 2
+        assert O.lib().orc_stage(mod.h, buf, scratch, N, sched, 300, C.byref(io), None, None, None, None) == 0
+        assert (res.ess, res.c, res.accept, res.resampled) == (io.ess, io.c, io.accept, io.resampled), s
+        resamples += res.resampled
+        if resamples >= 1 and s >= 2:
+            break
+    assert resamples >= 1
+    got, want = eng.download(), O.cloud_m(buf, N, d)
+    assert np.array_equal(got, want)
+    w = got[:, -1]
+    gm, wm = np.average(got[:, :d], axis=0, weights=w), np.average(want[:, :d], axis=0, weights=want[:, -1])
+    gs = np.sqrt(np.average((got[:, :d] - gm) ** 2, axis=0, weights=w))
+    ws = np.sqrt(np.average((want[:, :d] - wm) ** 2, axis=0, weights=want[:, -1]))
+    assert np.max(np.abs(gm - wm) / np.abs(wm)) <= 1e-6 and np.max(np.abs(gs - ws) / ws) <= 1e-6    # north_star tolerance
+
+
+# ---- full-size (BASELINE config C2) size-independent properties ------------------
 def test_full_size_properties(eng):
     from smc_jl_b200._lib import StageConfig, StageState
     params, lk, _ = W.linear_gaussian(d=20, T=256)
