@@ -215,8 +215,9 @@ static inline double normal_icdf(uint32_t r)
     uint32_t v = (r << 1) | 1u;
     float f = (float)v;                     /* round to nearest even */
     uint32_t fb; memcpy(&fb, &f, 4);
-    const float *c = ORC_NORMAL_TAB + 4 * ((fb >> 20) - (127u << 3));
-    uint32_t xb = (fb & 0x000fffffu) | 0x3f800000u;
+    const int SH = 23 - SMC_NORMAL_TABLE_LOG2SUB;
+    const float *c = ORC_NORMAL_TAB + 4 * ((fb >> SH) - (127u << SMC_NORMAL_TABLE_LOG2SUB));
+    uint32_t xb = (fb & ((1u << SH) - 1u)) | 0x3f800000u;
     float x; memcpy(&x, &xb, 4);
     float z = __builtin_fmaf(__builtin_fmaf(__builtin_fmaf(c[3], x, c[2]), x, c[1]), x, c[0]);
     uint32_t zb; memcpy(&zb, &z, 4);
@@ -671,11 +672,15 @@ ORC_API void orc_moments_shifted(const double *cloud, i64 N, int d, const double
     free(tl); free(sums);
 }
 
-/* canonical mean of the accept column (update_acceptance_rate!, particle.jl:466-468): tiles of 128 consecutive particles
- * (one per lane), adjacent-pair tree over the lanes, then over tiles -- the order the mutation kernel's epilogue produces */
-ORC_API double orc_mean_accept(const double *cloud, i64 N, int d)
+/* mean of the accept column (update_acceptance_rate!, particle.jl:466-468).  Every entry is (integer count) / n_free, so
+ * the engine sums the integer counts exactly (order-free) and divides once: mean = (sum_i count_i / n_free) / N -- equal to
+ * the reference's floating-point mean of the column up to rounding. */
+ORC_API double orc_mean_accept(const double *cloud, i64 N, int d, int n_free)
 {
-    return orc_canon_sum_generic(COL(cloud, N, C_ACCEPT(d)), N, 128, 1) / (double)N;
+    const double *a = COL(cloud, N, C_ACCEPT(d));
+    long long tot = 0;
+    for (i64 i = 0; i < N; ++i) tot += llround(a[i] * (double)n_free);
+    return ((double)tot / (double)n_free) / (double)N;
 }
 
 /* Lower Cholesky, row by row; returns 0 or (1 + failing row) if not positive definite
@@ -1336,7 +1341,7 @@ ORC_API int orc_stage(const orc_model *m, double *cloud, double *scratch /* N*(d
     orc_mutate(m, pr, cloud, N, 0, phi_n, io->phi_n1, io->alpha, io->n_mh_steps, n_free, io->has_old, io->seed,
                io->stage, io->nthreads);
     orc_proposal_free(pr);
-    io->accept = orc_mean_accept(cloud, N, d);
+    io->accept = orc_mean_accept(cloud, N, d, n_free);
     io->ess_prev = io->ess;
     io->status = 0;
     return 0;

@@ -40,7 +40,6 @@ enum {
     SC_COUNT = 32
 };
 constexpr int CK = 3;                  // trial phi per sweep of the cooperative adaptive-phi solve: depth-2 bisection tree
-constexpr int ACC_TILE = 128;          // accept-column sum: one 128-particle tile per lane tree (R = 1), then the tile tree
 
 constexpr int ESS_K = 15;   // trial phi per pass of the adaptive-phi solve: the 15 nodes of a depth-4 bisection tree
 struct PhiState {           // adaptive-phi state machine, lives in device memory
@@ -104,18 +103,19 @@ struct MutArgs {
     const double* scal;        // SC_* scalars: phi_n = scal[SC_PHI_N], the kernel returns at once when scal[SC_STATUS] != 0,
                                // rows are read from `alt_in` when scal[SC_RESAMPLE] != 0 (the stage resampled into it)
     const double* alt_in;
-    // accept-column sum (update_acceptance_rate!, particle.jl:466-468) fused into the epilogue
-    double* acc_partials;      // [P_acc] tile sums (entries >= number of tiles stay zero)
-    int acc_P;
-    unsigned* acc_counter;
-    double* acc_out;           // shard-local root
+    // persistent warps: 32-particle work items handed out by a device counter
+    unsigned* work_counter;
+    // mean of the accept column (update_acceptance_rate!, particle.jl:466-468) fused into the kernel: exact integer total
+    unsigned long long* acc_total;
+    unsigned* acc_counter;     // block ticket (the last block finalises)
+    double* acc_out;           // sum of the accept column (global)
     double* acc_mean_out;      // nullable: global sum / n_global -> scal[SC_ACCEPT]
     double n_global;
     PeerCtx pc;                // cross-GPU exchange of the shard roots inside the kernel's last block
 };
 struct Ctx;
 struct KernelEntry {            // one likelihood functor's kernels + the constant-memory uploaders of its translation unit
-    int kind, neq, k, stride, coef, sig, d;
+    int kind, neq, k, stride, coef, sig, d, minb;
     void (*mut[2][3][2])(double*, int64_t, int64_t, MutArgs);   // [has_old][0 blocks / 1 single block / 2 single full block][mixture]
     const void* mut_fn(int has_old, int blk, int mix) const { return (const void*)mut[has_old][blk][mix]; }
     void (*eval)(double*, int64_t, int);
@@ -155,7 +155,7 @@ struct Ctx {
     double* hist_scr = nullptr;    // [HIST_RING][2][N] incremental / normalised weight columns of recent stages
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t hist_ready[8]{}, hist_copied[8]{};
-    double* acc_partials = nullptr; int acc_P = 0;   // accept-column tile sums
+    unsigned long long* acc_total = nullptr;         // accept-column integer total of the running mutation kernel
     double* m1p_partials = nullptr; size_t m1p_len = 0; int m1p_P = 0;   // one-pass moments: [1 + d + E][P_chunks]
     double* m1p_sums = nullptr;    // [1 + d + E] shard-local roots, then global
     int coop_blocks_per_sm = 0;    // occupancy of k_correct_coop (queried once)

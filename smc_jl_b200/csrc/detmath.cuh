@@ -252,7 +252,7 @@ static constexpr float normal_tab_host[4 * NORMAL_TAB_ROWS] = {SMC_NORMAL_TABLE_
 static __device__ __align__(16) const float normal_tab_dev[4 * NORMAL_TAB_ROWS] = {SMC_NORMAL_TABLE_VALUES};
 #endif
 // tab: [NORMAL_TAB_ROWS] rows of (b0, b1, b2, b3); 16-byte aligned (shared memory inside the mutation kernel)
-SMC_HD double normal_icdf(uint32_t r, const float4* tab)
+SMC_HD float normal_icdf_f(uint32_t r, const float4* tab)
 {
     const uint32_t v = (r << 1) | 1u;
 #if defined(__CUDA_ARCH__)
@@ -261,11 +261,13 @@ SMC_HD double normal_icdf(uint32_t r, const float4* tab)
     const float f = (float)v;
 #endif
     const uint32_t fb = float_to_bits(f);
-    const float4 c = tab[(fb >> 20) - (127u << 3)];
-    const float x = bits_to_float((fb & 0x000fffffu) | 0x3f800000u);
+    constexpr int SH = 23 - SMC_NORMAL_TABLE_LOG2SUB;
+    const float4 c = tab[(fb >> SH) - (127u << SMC_NORMAL_TABLE_LOG2SUB)];
+    const float x = bits_to_float((fb & ((1u << SH) - 1u)) | 0x3f800000u);
     const float z = fmaf(fmaf(fmaf(c.w, x, c.z), x, c.y), x, c.x);
-    return (double)bits_to_float(float_to_bits(z) ^ (r & 0x80000000u));
+    return bits_to_float(float_to_bits(z) ^ (r & 0x80000000u));
 }
+SMC_HD double normal_icdf(uint32_t r, const float4* tab) { return (double)normal_icdf_f(r, tab); }
 SMC_HD void normal_quad(u32x4 r, const float4* tab, double& z0, double& z1, double& z2, double& z3)
 {
     z0 = normal_icdf(r.x, tab); z1 = normal_icdf(r.y, tab); z2 = normal_icdf(r.z, tab); z3 = normal_icdf(r.w, tab);

@@ -89,8 +89,8 @@ void free_cloud(Ctx* c)
     cudaFree(c->cloud[0]); cudaFree(c->cloud[1]); cudaFree(c->tmp); cudaFree(c->rmax); cudaFree(c->idx);
     cudaFree(c->partials); cudaFree(c->mpartials); cudaFree(c->ess_partials); c->ess_partials = nullptr; cudaFree(c->scan_blocktot); cudaFree(c->scan_blockoff); cudaFree(c->scan_levels);
     cudaFree(c->scan_bmax); cudaFree(c->msum); cudaFree(c->csum);
-    cudaFree(c->hist_scr); cudaFree(c->acc_partials); cudaFree(c->m1p_partials); cudaFree(c->m1p_sums); cudaFree(c->coop_partials);
-    c->hist_scr = c->acc_partials = c->m1p_partials = c->m1p_sums = c->coop_partials = nullptr;
+    cudaFree(c->hist_scr); cudaFree(c->m1p_partials); cudaFree(c->m1p_sums); cudaFree(c->coop_partials);
+    c->hist_scr = c->m1p_partials = c->m1p_sums = c->coop_partials = nullptr;
     for (int b = 0; b < 3; ++b)
         for (int r = 0; r < 16; ++r)
             if (c->ipc_open[b][r]) { cudaIpcCloseMemHandle(c->ipc_open[b][r]); c->ipc_open[b][r] = nullptr; }
@@ -107,7 +107,6 @@ struct Tiles { int ntiles, P; };
 Tiles weight_tiles(int64_t n) { int nt = (int)((n + W_TILE - 1) / W_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles moment_tiles(int64_t n) { int nt = (int)((n + M_TILE - 1) / M_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
-Tiles accept_tiles(int64_t n) { int nt = (int)((n + ACC_TILE - 1) / ACC_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 
 // cooperative grid of k_correct_coop for this shard: block b owns tpb consecutive tiles (tpb a power of two)
 struct CoopGeom { int grid, tpb, Pb; };
@@ -647,6 +646,8 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
         ok = ok && cudaEventCreateWithFlags(&c->hist_copied[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->acc_total, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(c->acc_total, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mb_epoch_dev, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(c->mb_epoch_dev, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mb_err, sizeof(int)) == cudaSuccess;
@@ -679,7 +680,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
-    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total);
     cudaFreeHost(c->h_summary);
     for (int i = 0; i < HIST_RING; ++i) {
         if (c->hist_ready[i]) cudaEventDestroy(c->hist_ready[i]);
@@ -767,10 +768,6 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMemset(c->cloud[0], 0, sizeof(double) * cols * c->N));
     // fused-stage buffers: weight-history ring, accept-column tile sums, one-pass moment partials, cooperative-grid partials
     SMC_CUDA(c, cudaMalloc(&c->hist_scr, sizeof(double) * (size_t)HIST_RING * 2 * c->N));
-    const Tiles ta = accept_tiles(c->N);
-    c->acc_P = ta.P;
-    SMC_CUDA(c, cudaMalloc(&c->acc_partials, sizeof(double) * ta.P));
-    SMC_CUDA(c, cudaMemset(c->acc_partials, 0, sizeof(double) * ta.P));
     const size_t nq1 = (size_t)1 + n_para + E;
     c->m1p_P = tch.P; c->m1p_len = nq1 * tch.P;
     SMC_CUDA(c, cudaMalloc(&c->m1p_partials, sizeof(double) * c->m1p_len));

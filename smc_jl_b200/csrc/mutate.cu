@@ -98,11 +98,14 @@ int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has
     a.seed = seed; a.stage = stage;
     a.scal = fused ? ctx->scal : nullptr;
     a.alt_in = ctx->cloud[ctx->cur ^ 1];
-    a.acc_partials = ctx->acc_partials; a.acc_P = ctx->acc_P; a.acc_counter = ctx->counters + 5;
+    a.work_counter = ctx->counters + 7; a.acc_total = ctx->acc_total; a.acc_counter = ctx->counters + 5;
     a.acc_out = ctx->scal + SC_ACC; a.acc_mean_out = ctx->scal + SC_ACCEPT; a.n_global = (double)ctx->N_global;
     a.pc = peer_ctx(ctx);
     const bool single = (a.n_blocks == 1);
-    const unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
+    // persistent blocks: as many as stay resident (the kernel's launch bound), never more than there is work
+    unsigned grid = (unsigned)((ctx->N + MUT_THREADS - 1) / MUT_THREADS);
+    const unsigned resident = (unsigned)(e->minb * (ctx->sm_count > 0 ? ctx->sm_count : 1));
+    if (grid > resident) grid = resident;
     const size_t smem = sizeof(double) * 2 * (size_t)e->d * MUT_THREADS;
     // one block that holds every parameter (none fixed): compile-time membership mask
     const bool full = single && ctx->n_free == e->d;      // (a single block always holds all free parameters)

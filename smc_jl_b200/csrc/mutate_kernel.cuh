@@ -22,12 +22,32 @@
 #include "reduce.cuh"
 #include "aslik.cuh"
 
+#ifndef SMC_NORM_BATCH
+#define SMC_NORM_BATCH 1
+#endif
+#ifndef SMC_F2D_INT
+#define SMC_F2D_INT 0
+#endif
+
 namespace smc {
 namespace {
 
 __constant__ MutConst c_mut;
 __constant__ LikSlot c_lik[2];
 __constant__ PriorConst c_pri;
+
+// binary32 -> binary64 of a proposal normal (zero or normal, never subnormal / inf / nan): exact either way; the integer
+// form keeps the conversion off the XU pipe
+__device__ __forceinline__ double f2d(float z)
+{
+#if SMC_F2D_INT
+    const uint32_t zb = __float_as_uint(z), mag = zb & 0x7fffffffu;
+    const uint32_t hi = (mag ? (mag >> 3) + 0x38000000u : 0u) | (zb & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(zb << 29));
+#else
+    return (double)z;
+#endif
+}
 
 // ---- priors (ModelConstructors.prior: sum over free parameters) ------------------
 // Families other than Normal sit behind a call so that the unrolled per-parameter code stays small
@@ -186,18 +206,27 @@ __global__ void __launch_bounds__(MUT_THREADS, LIK::MINB)
 k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
 {
     constexpr int D = LIK::D;
-    static_assert(MUT_THREADS == ACC_TILE, "the accept-column sum is defined on 128-particle tiles");
     extern __shared__ double sm_state[];
-    __shared__ float4 sm_tab[NORMAL_TAB_ROWS];     // inverse-normal-CDF table (4.2 KB; random per-lane rows)
-    __shared__ double sm_red[MUT_THREADS / 32];
+    __shared__ float4 sm_tab[NORMAL_TAB_ROWS];     // inverse-normal-CDF table (random per-lane rows)
+    const float4* NTAB = sm_tab;
     __shared__ bool sm_last;
     if (a.scal && a.scal[SC_STATUS] != 0.0) return;   // the stage was poisoned (NaN ESS / non-PD covariance): leave the cloud alone
     if (c_mut.status != 0) return;
     for (int k = threadIdx.x; k < NORMAL_TAB_ROWS; k += MUT_THREADS) sm_tab[k] = reinterpret_cast<const float4*>(normal_tab_dev)[k];
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * MUT_THREADS + threadIdx.x;
+    // Persistent warps: every warp fetches 32-particle work items from a global counter until the cloud is exhausted, so
+    // the table above is loaded once per block, there is no block barrier in the loop and the SMs stay evenly loaded.
+    const unsigned n_items = (unsigned)((N + 31) / 32);
+    const int lane = threadIdx.x & 31;
+    unsigned next_item = 0u;
+    if (lane == 0) next_item = atomicAdd(a.work_counter, 1u);
+    for (;;) {
+    const unsigned item = __shfl_sync(0xffffffffu, next_item, 0);
+    if (item >= n_items) break;
+    if (lane == 0) next_item = atomicAdd(a.work_counter, 1u);      // the next item's ticket travels while this one is processed
+    const int64_t i = (int64_t)item * 32 + lane;
     const bool live = i < N;
-    double accept = 0.0;
+    int acc_cnt = 0;
     if (live) {
         const double* src = (a.scal && a.scal[SC_RESAMPLE] != 0.0) ? a.alt_in : cloud;
         double* buf0 = sm_state + threadIdx.x;
@@ -235,6 +264,38 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
                 // s = (c L) z (every s[r] sums over ascending columns j, the oracle's order), so the normals never
                 // leave registers.  The mixture path also parks them in the candidate buffer (component 2 needs z_k).
                 constexpr int NQUAD = (D + 3) / 4;
+#if SMC_NORM_BATCH
+                // phase-batched: every Philox block of the step first (independent chains), then all table rows and
+                // polynomials, then the mat-vec -- the long-latency operations (IMAD chains, uint->float conversions,
+                // table loads) of different normals overlap instead of sitting in front of each column's DFMAs
+                float zf[4 * NQUAD];
+                {
+                    uint32_t rw[4 * NQUAD];
+#pragma unroll
+                    for (int q = 0; q < NQUAD; ++q) {
+                        if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
+                            const u32x4 r = rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL);
+                            rw[4 * q] = r.x; rw[4 * q + 1] = r.y; rw[4 * q + 2] = r.z; rw[4 * q + 3] = r.w;
+                        } else {
+                            rw[4 * q] = 0u; rw[4 * q + 1] = 0u; rw[4 * q + 2] = 0u; rw[4 * q + 3] = 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4 * NQUAD; ++j) zf[j] = (j < D) ? normal_icdf_f(rw[j], NTAB) : 0.0f;
+                }
+                double s[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) s[k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const double zj = f2d(zf[j]);
+                    if (MIX) cand[j * MUT_THREADS] = zj;
+                    if (BLK == 2 || ((mask >> j) & 1u)) {
+#pragma unroll
+                        for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], zj, s[r]);
+                    }
+                }
+#else
                 double s[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) s[k] = 0.0;
@@ -242,7 +303,7 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
                 for (int q = 0; q < NQUAD; ++q) {
                     if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
                         double z[4];
-                        normal_quad(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), sm_tab, z[0], z[1], z[2], z[3]);
+                        normal_quad(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), NTAB, z[0], z[1], z[2], z[3]);
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             const int j = 4 * q + jj;
@@ -256,6 +317,7 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
                         }
                     }
                 }
+#endif
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const double t = cur[k * MUT_THREADS];
@@ -311,7 +373,7 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
                 if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
                     flipped = !flipped;
                     like = ln; lpri = pn; lprev = lo;
-                    accept += (double)c_mut.bsize[b];
+                    acc_cnt += c_mut.bsize[b];
                 }
             }
         }
@@ -321,35 +383,36 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
         cloud[col_off(N, D) + i] = like;
         cloud[col_off(N, D + 1) + i] = lpri;
         cloud[col_off(N, D + 2) + i] = lprev;
-        accept = accept / (double)a.n_free;                            // particle.jl:410-418
-        cloud[col_off(N, D + 3) + i] = accept;
+        cloud[col_off(N, D + 3) + i] = (double)acc_cnt / (double)a.n_free;   // particle.jl:410-418
     }
-    // sum of the accept column (update_acceptance_rate!, particle.jl:466-468): this block is one 128-particle tile of
-    // the canonical order (adjacent-pair tree over the lanes, then over the tiles); the last block to finish reduces
-    // the tile sums
-    if (!a.acc_partials) return;
-    double v = warp_tree(accept);
-    if ((threadIdx.x & 31) == 0) sm_red[threadIdx.x >> 5] = v;
+    // mean of the accept column (update_acceptance_rate!, particle.jl:466-468): the per-particle counts are integers, so
+    // their sum is exact and order-free -- one warp reduction and one atomic per work item
+    const int wsum = __reduce_add_sync(0xffffffffu, live ? acc_cnt : 0);
+    if (lane == 0 && wsum) atomicAdd(a.acc_total, (unsigned long long)wsum);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        v = (sm_red[0] + sm_red[1]) + (sm_red[2] + sm_red[3]);
-        __stcg(a.acc_partials + blockIdx.x, v);
         __threadfence();
         const unsigned t = atomicInc(a.acc_counter, gridDim.x - 1);
         sm_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!sm_last) return;
+    // last block: every work item is done.  accept sum = total / n_free (global after the cross-GPU exchange)
     __threadfence();
-    const double root = tiles_tree_block<MUT_THREADS>(a.acc_partials, a.acc_P, sm_red);
     __shared__ double sm_x[2];
-    if (threadIdx.x == 0) { sm_x[0] = root; sm_x[1] = root; }
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = *reinterpret_cast<volatile unsigned long long*>(a.acc_total);
+        sm_x[0] = (double)tot; sm_x[1] = (double)tot;
+        *a.acc_total = 0ull; *a.work_counter = 0u;          // ready for the next launch
+    }
     __syncthreads();
-    if (a.pc.world > 1) peer_exchange_block(a.pc, sm_x, 1, 1, sm_x + 1);     // fixed rank-order tree over the shard roots
+    if (a.pc.world > 1) peer_exchange_block(a.pc, sm_x, 1, 1, sm_x + 1);     // integer-valued doubles: exact in any order
     __syncthreads();
     if (threadIdx.x == 0) {
-        *a.acc_out = sm_x[1];
-        if (a.acc_mean_out) *a.acc_mean_out = sm_x[1] / a.n_global;
+        const double sum = sm_x[1] / (double)a.n_free;
+        *a.acc_out = sum;
+        if (a.acc_mean_out) *a.acc_mean_out = sum / a.n_global;
     }
 }
 
@@ -492,6 +555,7 @@ static KernelEntry make_entry()
     KernelEntry e;
     e.kind = LIK::KIND;
     e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
+    e.minb = LIK::MINB;
     e.mut[0][0][0] = k_mutate<LIK, false, 0, false>;
     e.mut[0][1][0] = k_mutate<LIK, false, 1, false>;
     e.mut[0][2][0] = k_mutate<LIK, false, 2, false>;

@@ -2,7 +2,7 @@
 //   k_correct_coop    ONE cooperative launch for solve_adaptive_phi (src/helpers.jl:9-56) + correction + ESS +
 //                     the resample decision (src/smc_main.jl:386-435); every decision is left in device scalars
 //   k_moments1p<D>    weighted mean / covariance in ONE pass over the cloud (src/particle.jl:481-532): a chunk's
-//                     columns arrive by bulk asynchronous copies (cp.async.bulk + mbarrier), eight warps share the
+//                     columns arrive by bulk asynchronous copies (cp.async.bulk + mbarrier), four warps share the
 //                     lower triangle
 //   k_moments_finish  tile trees of the one-pass sums; its last block exchanges them across GPUs, updates the step
 //                     size (src/smc_main.jl:453-455) and factors the proposal covariance (src/mutation.jl:81) with
@@ -361,17 +361,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         : "memory");
 }
 
-// One row group of the lower triangle over one chunk.  The two halves of the chunk are consumed as they arrive; each
-// half is centred in place (x <- x - x0, all threads) before the accumulation, so every warp reads ready differences.
-// Every thread of the block must call this (block barriers inside).
+// One row group of the lower triangle over one chunk.  The two halves of the chunk are consumed as they arrive.
+// Every thread of the block must call this (block barrier inside).
 template <int D, int GRP>
-__device__ __forceinline__ void m1p_group(double* __restrict__ xs /* smem [D+1][M2_CH] */, int64_t N, int64_t c0, int lane,
+__device__ __forceinline__ void m1p_group(const double* __restrict__ xs /* smem [D+1][M2_CH] */, int64_t N, int64_t c0, int lane,
                                           const double* __restrict__ shift, uint64_t* bars, bool bulk, double* __restrict__ red)
 {
     constexpr int A0 = m1p_rowb<D>(GRP), A1 = m1p_rowb<D>(GRP + 1);
     constexpr int NR = (A1 > A0) ? (A1 - A0) : 1;
     constexpr int NC = (A1 > 0) ? A1 : 1;
-    constexpr int NT = 32 * M1P_G, HALF = M2_CH / 2;
+    constexpr int HALF = M2_CH / 2;
     double acc[NR][NC], m1[NR];
 #pragma unroll
     for (int a = 0; a < NR; ++a) {
@@ -380,14 +379,12 @@ __device__ __forceinline__ void m1p_group(double* __restrict__ xs /* smem [D+1][
         for (int b = 0; b < NC; ++b) acc[a][b] = 0.0;
     }
     double sw = 0.0;
+    double mu[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) mu[k] = (k < A1) ? shift[k] : 0.0;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         if (bulk) mbar_wait(bars + half, 0u);
-        for (int idx = threadIdx.x; idx < D * HALF; idx += NT) {
-            const int k = idx / HALF, p = idx % HALF;
-            xs[k * M2_CH + half * HALF + p] = xs[k * M2_CH + half * HALF + p] - shift[k];
-        }
-        __syncthreads();
 #pragma unroll 2
         for (int r = half * (HALF / 32); r < (half + 1) * (HALF / 32); ++r) {
             const int64_t i = c0 + (int64_t)r * 32 + lane;
@@ -397,7 +394,7 @@ __device__ __forceinline__ void m1p_group(double* __restrict__ xs /* smem [D+1][
                 if (A1 > A0) {
                     double dx[NC];
 #pragma unroll
-                    for (int k = 0; k < A1; ++k) dx[k] = xs[k * M2_CH + r * 32 + lane];
+                    for (int k = 0; k < A1; ++k) dx[k] = xs[k * M2_CH + r * 32 + lane] - mu[k];
 #pragma unroll
                     for (int a = A0; a < A1; ++a) {
                         m1[a - A0] = fma(wi, dx[a], m1[a - A0]);

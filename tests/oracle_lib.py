@@ -65,7 +65,7 @@ def lib():
         "orc_update_c": (d, [d, d, d]),
         "orc_moments": (None, [f64p, i64, C.c_int, f64p, f64p]),
         "orc_moments_shifted": (None, [f64p, i64, C.c_int, f64p, f64p, f64p]),
-        "orc_mean_accept": (d, [f64p, i64, C.c_int]),
+        "orc_mean_accept": (d, [f64p, i64, C.c_int, C.c_int]),
         "orc_cholesky": (C.c_int, [f64p, C.c_int, f64p]),
         "orc_model_create": (vp, [C.c_int]), "orc_model_free": (None, [vp]),
         "orc_model_set_params": (C.c_int, [vp, i32p, f64p, f64p, i32p, f64p, f64p]),

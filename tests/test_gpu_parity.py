@@ -266,7 +266,7 @@ def _mutation_case(eng, spec, P, blocks, phi_n, phi_n1, c, n_mh, has_old, seed, 
     L.orc_mutate(mod.h, pr, buf, N, 0, phi_n, phi_n1, alpha, n_mh, len(free), int(has_old), seed, stage, 0)
     L.orc_proposal_free(pr)
     want = O.cloud_m(buf, N, d)
-    oacc = L.orc_mean_accept(buf, N, d)
+    oacc = L.orc_mean_accept(buf, N, d, len(free))
     return got, want, acc, oacc
 
 

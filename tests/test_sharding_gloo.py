@@ -80,9 +80,10 @@ def _worker(rank, world, port, N, d, ret):
         L.orc_mutate(mod.h, pr, whole, N, 0, phi_n, phi_n1, 1.0, 2, d, 0, 99, 7, 1)
         L.orc_proposal_free(pr)
         ok = ok and np.array_equal(O.cloud_m(shard_buf, count, d), O.cloud_m(whole, N, d)[first:first + count])
-        # accept mean through per-shard canonical sums
-        acc = float(combine_ranks(allgather(L.orc_canon_sum(np.ascontiguousarray(O.cloud_m(shard_buf, count, d)[:, d + 3]), count)))[0]) / N
-        ok = ok and acc == L.orc_mean_accept(whole, N, d)
+        # accept mean: the shards' exact integer totals (accept column = count / n_free), combined across ranks
+        tot = np.rint(O.cloud_m(shard_buf, count, d)[:, d + 3] * d).sum()
+        acc = (float(combine_ranks(allgather(float(tot)))[0]) / d) / N
+        ok = ok and acc == L.orc_mean_accept(whole, N, d, d)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
