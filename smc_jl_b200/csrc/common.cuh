@@ -39,7 +39,6 @@ enum {
     SC_EVALS = 16, SC_SWEEPS = 17,
     SC_COUNT = 32
 };
-constexpr int CK = 3;                  // trial phi per sweep of the cooperative adaptive-phi solve: depth-2 bisection tree
 
 constexpr int ESS_K = 15;   // trial phi per pass of the adaptive-phi solve: the 15 nodes of a depth-4 bisection tree
 struct PhiState {           // adaptive-phi state machine, lives in device memory
@@ -158,9 +157,10 @@ struct Ctx {
     unsigned long long* acc_total = nullptr;         // accept-column integer total of the running mutation kernel
     double* m1p_partials = nullptr; size_t m1p_len = 0; int m1p_P = 0;   // one-pass moments: [1 + d + E][P_chunks]
     double* m1p_sums = nullptr;    // [1 + d + E] shard-local roots, then global
-    int coop_blocks_per_sm = 0;    // occupancy of k_correct_coop (queried once)
+    int coop_blocks_per_sm[3] = {0, 0, 0};    // occupancy of k_correct_coop<3 / 7 / 15> (queried once)
     int sm_count = 0;
     double* coop_partials = nullptr; size_t coop_partials_len = 0;
+    double* coop_gsum = nullptr; unsigned long long* coop_gflag = nullptr; unsigned long long coop_gen = 0;
     double* h_summary = nullptr;   // pinned ring of stage summaries [SUMMARY_RING][SC_COUNT]
     double* rmax = nullptr;        // N   running max of the cumsum
     int64_t* idx = nullptr;        // N

@@ -108,19 +108,18 @@ Tiles weight_tiles(int64_t n) { int nt = (int)((n + W_TILE - 1) / W_TILE); if (n
 Tiles moment_tiles(int64_t n) { int nt = (int)((n + M_TILE - 1) / M_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 
-// cooperative grid of k_correct_coop for this shard: block b owns tpb consecutive tiles (tpb a power of two)
-struct CoopGeom { int grid, tpb, Pb; };
-CoopGeom coop_geom(const Ctx* c, int64_t n)
+// trial phi per sweep of the adaptive solve: a sweep costs one grid barrier + K exp per particle, so small clouds take
+// wider sweeps (the result does not depend on K)
+int coop_k(int64_t n) { return (n >= ((int64_t)1 << 20)) ? 3 : 7; }
+const void* coop_kernel(int64_t n) { return coop_k(n) == 3 ? (const void*)k_correct_coop<3> : (const void*)k_correct_coop<7>; }
+// cooperative grid of k_correct_coop for this shard: at most one block per SM (a short grid barrier), never more blocks
+// than pairs of tiles
+int coop_grid(const Ctx* c, int64_t n)
 {
     const Tiles t = weight_tiles(n);
-    const int cap = (c->coop_blocks_per_sm > 0 ? c->coop_blocks_per_sm : 1) * (c->sm_count > 0 ? c->sm_count : 1);
-    int tpb = 1;
-    while ((t.ntiles + tpb - 1) / tpb > cap) tpb *= 2;
-    CoopGeom g;
-    g.tpb = tpb;
-    g.grid = (t.ntiles + tpb - 1) / tpb;
-    g.Pb = (t.P >= tpb) ? t.P / tpb : 1;
-    return g;
+    int g = (t.ntiles + COOP_GROUPS - 1) / COOP_GROUPS;
+    const int cap = c->sm_count > 0 ? c->sm_count : 1;
+    return g > cap ? cap : g;
 }
 
 int sync(Ctx* c)
@@ -146,13 +145,13 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
 {
     const int d = c->d;
     double* cl = c->cloud[c->cur];
-    const CoopGeom g = coop_geom(c, c->N);
+    const Tiles tw = weight_tiles(c->N);
     CoopArgs a;
     std::memset(&a, 0, sizeof(a));
     a.ll = cl + col_off(c->N, d); a.old = cl + col_off(c->N, d + 2); a.w = cl + col_off(c->N, d + 4);
     a.inc_out = L.inc_dev; a.normw_out = L.normw_dev;
     a.N = c->N; a.n_global = (double)c->N_global;
-    a.ntiles = weight_tiles(c->N).ntiles; a.tpb = g.tpb; a.Pb = g.Pb;
+    a.ntiles = tw.ntiles; a.P = tw.P;
     a.corr.phi_n1 = L.phi_n1; a.corr.phi_n = L.phi_n; a.corr.pw = L.pw; a.corr.lpod = L.lpod;
     a.corr.mode = (L.pw == 0.0) ? 0 : (L.pw == 1.0 ? 1 : 2);
     a.corr.log_1m_pw = (a.corr.mode == 2) ? det_log(1.0 - L.pw) : 0.0;
@@ -161,9 +160,10 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
     a.sched = L.sched_dev; a.n_phi = L.n_phi; a.tempering_target = L.tempering_target;
     a.c_in = L.c_in; a.accept_in = L.accept_in; a.ess_prev_in = L.ess_prev_in; a.phi_prop_in = L.phi_prop_in; a.j_in = L.j_in;
     a.resampled_last_in = L.resampled_last_in;
-    a.partials = c->coop_partials; a.scal = c->scal; a.st = c->phi_state; a.pc = peer_ctx(c);
+    a.partials = c->coop_partials; a.scal = c->scal; a.pc = peer_ctx(c);
+    a.gsum = c->coop_gsum; a.gflag = c->coop_gflag; a.gen = ++c->coop_gen;
     void* args[] = {&a};
-    SMC_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_correct_coop, dim3(g.grid), dim3(256), args, 0, c->stream));
+    SMC_CUDA(c, cudaLaunchCooperativeKernel(coop_kernel(c->N), dim3(coop_grid(c, c->N)), dim3(COOP_NT), args, 0, c->stream));
     c->launches += 1;
     return SMCB200_OK;
 }
@@ -646,6 +646,9 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
         ok = ok && cudaEventCreateWithFlags(&c->hist_copied[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->coop_gsum, sizeof(double) * 2 * COOP_NQMAX) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->coop_gflag, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(c->coop_gflag, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->acc_total, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(c->acc_total, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mb_epoch_dev, sizeof(unsigned long long)) == cudaSuccess;
@@ -656,8 +659,9 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
         int coop = 0;
         ok = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && coop != 0;
         ok = ok && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm, k_correct_coop, 256, 0) == cudaSuccess;
-        ok = ok && c->coop_blocks_per_sm >= 1;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm[0], k_correct_coop<3>, COOP_NT, 0) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm[1], k_correct_coop<7>, COOP_NT, 0) == cudaSuccess;
+        ok = ok && c->coop_blocks_per_sm[0] >= 1 && c->coop_blocks_per_sm[1] >= 1;
     }
     ok = ok && cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
@@ -680,7 +684,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
-    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total); cudaFree(c->coop_gsum); cudaFree(c->coop_gflag);
     cudaFreeHost(c->h_summary);
     for (int i = 0; i < HIST_RING; ++i) {
         if (c->hist_ready[i]) cudaEventDestroy(c->hist_ready[i]);
@@ -773,8 +777,7 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMalloc(&c->m1p_partials, sizeof(double) * c->m1p_len));
     SMC_CUDA(c, cudaMemset(c->m1p_partials, 0, sizeof(double) * c->m1p_len));
     SMC_CUDA(c, cudaMalloc(&c->m1p_sums, sizeof(double) * 2 * (1 + DMAX + PACKMAX)));
-    const CoopGeom cgm = coop_geom(c, c->N);
-    c->coop_partials_len = (size_t)((2 * CK > 3) ? 2 * CK : 3) * cgm.Pb;
+    c->coop_partials_len = (size_t)2 * COOP_NQMAX * tw.P;
     SMC_CUDA(c, cudaMalloc(&c->coop_partials, sizeof(double) * c->coop_partials_len));
     SMC_CUDA(c, cudaMemset(c->coop_partials, 0, sizeof(double) * c->coop_partials_len));
     c->cur = 0;

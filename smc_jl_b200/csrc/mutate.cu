@@ -116,8 +116,14 @@ int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has
     if (!seen) {
         if (smem > 48 * 1024)
             SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // the chain state lives in shared memory: ask for the largest carve-out so that LIK::MINB blocks stay resident
-        SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // the chain state lives in shared memory: ask for just enough carve-out to keep LIK::MINB blocks resident and leave
+        // the rest of the 256 KB to L1 (the Kalman-filter functor keeps a few spilled registers there)
+        cudaFuncAttributes fa;
+        SMC_CUDA(ctx, cudaFuncGetAttributes(&fa, kern));
+        const size_t need = (size_t)e->minb * (smem + fa.sharedSizeBytes + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        SMC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         configured.push_back((const void*)kern);
     }
     kern<<<grid, MUT_THREADS, smem, ctx->stream>>>(ctx->cloud[ctx->cur], ctx->N, ctx->index0, a);

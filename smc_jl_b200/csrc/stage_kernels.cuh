@@ -91,11 +91,13 @@ __device__ inline void phi_transition(PhiState* st, const double* __restrict__ s
 
 // =================================================================================================
 // k_correct_coop: one cooperative launch per stage for everything up to the resample decision.
-// Block b owns the `tpb` (power of two) consecutive 1024-element tiles [b tpb, (b+1) tpb) of this shard, so its partial
-// is a subtree of the canonical tile tree; block 0 finishes the tree (one warp per quantity), exchanges the shard
-// roots with the other GPUs in place (NVLink mailboxes) and publishes the result between two grid barriers.
-//   adaptive: sweeps of CK trial phi (compute_ESS, helpers.jl:173-181) drive the bisection state machine until the
-//             bracket is exhausted -- the three columns stay in L1/L2, there is no host poll and no extra launch;
+// The shard's 1024-element tiles are dealt round-robin to the 256-thread groups of at most one 512-thread block per SM;
+// every reduction stores the tiles' sums, crosses ONE grid barrier, and then every block finishes the canonical
+// adjacent-pair tile tree itself, so all blocks agree bit for bit and run identical copies of the bisection state
+// machine; on several GPUs block 0 exchanges the shard roots in place (NVLink mailboxes) and publishes the global sums.
+//   adaptive: sweeps of K trial phi (compute_ESS, helpers.jl:173-181; K = 3, 7 or 15 by cloud size: each sweep costs one
+//             grid barrier plus K exp per particle) drive the bisection state machine until the bracket is exhausted --
+//             the three columns stay in L1/L2, there is no host poll and no extra launch;
 //   pass A:   w~ = w * inc, S = sum w~                      (smc_main.jl:401-413, particle.jl:250-259)
 //   pass B:   W = (w~ N) / S, Q = sum W^2, sum W, sum W/N   (particle.jl:362-369, smc_main.jl:427)
 //   decision: ESS = N^2 / Q, resample iff ESS < threshold_ratio N (smc_main.jl:435); NaN ESS poisons the stage.
@@ -104,135 +106,305 @@ struct CoopArgs {
     const double* ll; const double* old; double* w;   // loglh, old_loglh, weight columns of this shard
     double* inc_out; double* normw_out;               // nullable: w_matrix / W_matrix columns of this stage
     int64_t N; double n_global;
-    int ntiles, tpb, Pb;
+    int ntiles, P;                                    // tiles of this shard; P = next power of two (tile-tree width)
     CorrArgs corr;
     double threshold_ratio;
     int adaptive, solve_only, use_carry;
     const double* sched; int n_phi; double tempering_target;
     double c_in, accept_in, ess_prev_in, phi_prop_in; long long j_in; int resampled_last_in;
-    double* partials;                                 // [max(2 CK, 3)][Pb], entries >= gridDim.x stay zero
+    double* partials;                                 // [2][NQMAX][P] (two alternating regions), entries >= ntiles stay zero
     double* scal;
-    PhiState* st;
+    // multi-GPU: block 0 crosses the GPUs and publishes the global sums to the other blocks of its grid
     PeerCtx pc;
+    double* gsum;                                     // [2][NQMAX]
+    unsigned long long* gflag;                        // monotone: (launch generation << 20) | reduction step
+    unsigned long long gen;
+};
+constexpr int COOP_NT = 512;                         // threads per block: two 1024-element tiles in flight per block
+constexpr int COOP_GROUPS = COOP_NT / W_LANES;
+constexpr int COOP_KMAX = 7;
+constexpr int COOP_NQMAX = 2 * COOP_KMAX;
+
+// per-tile lane sums of the three reductions (functors: nvcc's front end aborts on the equivalent lambdas inside a
+// template kernel); t = thread index inside the tile's 256-thread group
+template <int K>
+struct SweepSums {                 // S_k = sum x, Q_k = sum x^2 with x = w inc(phi_k), k < K   (compute_ESS, helpers.jl:173-181)
+    static constexpr int NLOAD = 3 * W_R;
+    const CoopArgs& a; const double* phi; double phi_n1;
+    __device__ __forceinline__ void load(int64_t tile, int t, double (&b)[NLOAD]) const
+    {
+        const int64_t base = tile * W_TILE + t;
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) {
+            const int64_t i = base + (int64_t)r * W_LANES;
+            const bool in = i < a.N;
+            b[3 * r] = in ? __ldg(a.ll + i) : 0.0; b[3 * r + 1] = in ? __ldg(a.old + i) : 0.0; b[3 * r + 2] = in ? a.w[i] : 0.0;
+        }
+    }
+    __device__ __forceinline__ void compute(int64_t tile, int t, const double (&b)[NLOAD], double (&v)[2 * K]) const
+    {
+#pragma unroll
+        for (int q = 0; q < 2 * K; ++q) v[q] = 0.0;
+        const int64_t base = tile * W_TILE + t;
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) {
+            const int64_t i = base + (int64_t)r * W_LANES;
+            if (i < a.N) {
+                const double l = b[3 * r], o = b[3 * r + 1], wi = b[3 * r + 2];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
+                    v[k] = v[k] + x;
+                    v[K + k] = v[K + k] + x * x;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) { v[k] = v[k] + 0.0; v[K + k] = v[K + k] + 0.0 * 0.0; }
+            }
+        }
+    }
+};
+struct PassASums {                 // w~ = w inc, S = sum w~   (smc_main.jl:401-413, particle.jl:250-259)
+    static constexpr int NLOAD = 1;
+    const CoopArgs& a; double phi_n;
+    __device__ __forceinline__ void load(int64_t, int, double (&)[NLOAD]) const {}
+    __device__ __forceinline__ void compute(int64_t tile, int t, const double (&)[NLOAD], double (&v)[1]) const
+    {
+        const int64_t base = tile * W_TILE + t;
+        double x[W_R];
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) {
+            const int64_t i = base + (int64_t)r * W_LANES;
+            x[r] = 0.0;
+            if (i < a.N) {
+                const double inc = inc_weight(__ldg(a.ll + i), __ldg(a.old + i), a.corr, phi_n);
+                x[r] = a.w[i] * inc;
+                a.w[i] = x[r];
+                if (a.inc_out) a.inc_out[i] = inc;
+            }
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) acc = acc + x[r];
+        v[0] = acc;
+    }
+};
+struct PassBSums {                 // W = (w~ N) / S, Q = sum W^2, sum W, sum W / N   (particle.jl:362-369, smc_main.jl:427,438)
+    static constexpr int NLOAD = 1;
+    const CoopArgs& a; double S;
+    __device__ __forceinline__ void load(int64_t, int, double (&)[NLOAD]) const {}
+    __device__ __forceinline__ void compute(int64_t tile, int t, const double (&)[NLOAD], double (&v)[3]) const
+    {
+        const int64_t base = tile * W_TILE + t;
+        double x[W_R], y[W_R];
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) {
+            const int64_t i = base + (int64_t)r * W_LANES;
+            x[r] = 0.0; y[r] = 0.0;
+            if (i < a.N) {
+                x[r] = (a.w[i] * a.n_global) / S;
+                y[r] = x[r] / a.n_global;                 // normalized_weights / n_parts, smc_main.jl:438
+                a.w[i] = x[r];
+                if (a.normw_out) a.normw_out[i] = x[r];
+            }
+        }
+        double q = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < W_R; ++r) { q = q + x[r] * x[r]; s2 = s2 + x[r]; s3 = s3 + y[r]; }
+        v[0] = q; v[1] = s2; v[2] = s3;
+    }
 };
 
-// sums of NQ per-thread quantities over this block's tiles in the canonical order: `lane_sums(t, v)` gives the thread's
-// lane sums of tile t; returns (thread q < NQ) the block's subtree sum of quantity q
+constexpr int COOP_RMAX = 8;                         // rounds whose warp sums are parked before the single block barrier
+struct CoopSmem {
+    double warp[COOP_RMAX][COOP_GROUPS][COOP_NQMAX][8];     // per-tile warp sums
+    double seg[COOP_NQMAX][COOP_NT / 32];        // per-warp segment roots of the tile tree
+    double res[COOP_NQMAX], tmp[COOP_NQMAX];
+};
+
+// tile sums of NQ quantities in the canonical order (lane l of a tile adds its 4 elements, adjacent-pair tree over the
+// 256 lanes): each 256-thread group of the block takes one tile per round (tiles are dealt round-robin over the grid)
+// and stores the tile's sums for the grid-wide tree
 template <int NQ, class F>
-__device__ __forceinline__ double coop_block_sums(const CoopArgs& a, double (*sm)[8], F lane_sums)
+__device__ __forceinline__ void coop_tile_sums(const CoopArgs& a, CoopSmem& sm, const F& f, double* region)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double stack[12];
-    int sp = 0;
-    for (int tt = 0; tt < a.tpb; ++tt) {
-        const int64_t tile = (int64_t)blockIdx.x * a.tpb + tt;
-        double v[NQ];
-        lane_sums(tile, v);
-        __syncthreads();                 // protects sm against the previous round's readers
+    const int tid = threadIdx.x, g = tid / W_LANES, t = tid % W_LANES, lane = tid & 31, warp = t >> 5;
+    const int per_round = gridDim.x * COOP_GROUPS;
+    const int rounds = (a.ntiles + per_round - 1) / per_round;
+    for (int r0 = 0; r0 < rounds; r0 += COOP_RMAX) {
+        const int r1 = (r0 + COOP_RMAX < rounds) ? r0 + COOP_RMAX : rounds;
+        __syncthreads();                 // protects sm.warp against the previous reduction's readers
+        double nxt[F::NLOAD];
+        {
+            const int64_t tile = ((int64_t)r0 * COOP_GROUPS + g) * gridDim.x + blockIdx.x;
+            if (tile < a.ntiles) f.load(tile, t, nxt);
+        }
+        for (int r = r0; r < r1; ++r) {
+            const int64_t tile = ((int64_t)r * COOP_GROUPS + g) * gridDim.x + blockIdx.x;
+            double cur[F::NLOAD];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const double s = warp_tree(v[q]);
-            if (lane == 0) sm[q][warp] = s;
+            for (int k = 0; k < F::NLOAD; ++k) cur[k] = nxt[k];
+            const int64_t tile_n = ((int64_t)(r + 1) * COOP_GROUPS + g) * gridDim.x + blockIdx.x;
+            if (r + 1 < r1 && tile_n < a.ntiles) f.load(tile_n, t, nxt);     // the next round's columns travel during this round
+            double v[NQ];
+            if (tile < a.ntiles) f.compute(tile, t, cur, v);
+            else {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) v[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double s = warp_tree(v[q]);
+                if (lane == 0) sm.warp[r - r0][g][q][warp] = s;
+            }
         }
         __syncthreads();
-        if (tid < NQ) {
-            const double* r = sm[tid];
-            double x = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-            int k = tt;
-            while (k & 1) { x = stack[--sp] + x; k >>= 1; }
-            stack[sp++] = x;
+        for (int e = tid; e < (r1 - r0) * COOP_GROUPS * NQ; e += COOP_NT) {
+            const int q = e % NQ, gg = (e / NQ) % COOP_GROUPS, rr = e / (NQ * COOP_GROUPS);
+            const int64_t tile = ((int64_t)(r0 + rr) * COOP_GROUPS + gg) * gridDim.x + blockIdx.x;
+            if (tile < a.ntiles) {
+                const double* w8 = sm.warp[rr][gg][q];
+                __stcg(region + (size_t)q * a.P + tile, ((w8[0] + w8[1]) + (w8[2] + w8[3])) + ((w8[4] + w8[5]) + (w8[6] + w8[7])));
+            }
         }
     }
-    return (tid < NQ) ? stack[0] : 0.0;
 }
 
-// block 0: finish the tile tree of NQ quantities (one warp per quantity), cross the GPUs, leave the results in res[]
-// (shared memory, valid for every thread of block 0 after the call)
-template <int NQ>
-__device__ __forceinline__ void coop_root(const CoopArgs& a, double* res /* smem [NQ] */, double* tmp /* smem [NQ] */)
+// thread tid's contiguous slice of the P tile sums of quantity q (M = P / COOP_NT of them), reduced in tree order
+template <int M>
+__device__ __forceinline__ double coop_slice(const double* q_part, int tid)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = warp; q < NQ; q += 8) {
-        const double r = tiles_tree_warp(a.partials + (size_t)q * a.Pb, a.Pb);
-        if (lane == 0) tmp[q] = r;
+    double v[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) v[k] = __ldcg(q_part + (size_t)tid * M + k);
+#pragma unroll
+    for (int sft = 1; sft < M; sft <<= 1)
+#pragma unroll
+        for (int k = 0; k + sft < M; k += 2 * sft) v[k] = v[k] + v[k + sft];
+    return v[0];
+}
+
+// One grid-wide reduction of NQ quantities with ONE grid barrier: the blocks store their tile sums, the grid synchronises
+// (at most one block per SM takes part, which keeps the barrier short), and then EVERY block finishes the adjacent-pair
+// tile tree itself from L2 (thread slices -> 16 warp trees -> one warp), so all blocks hold the same bits without a second
+// barrier.  The two partial regions alternate with `step`: a block can only run two reductions ahead of the slowest reader
+// after passing the barrier in between.  Multi-GPU: block 0 alone crosses the GPUs (NVLink mailboxes) and publishes the
+// global sums behind a flag.  Result: sm.res[0 .. NQ).
+template <int NQ, class F>
+__device__ __forceinline__ void coop_allreduce(const CoopArgs& a, cg::grid_group& grid, CoopSmem& sm, const F& f, int& step)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* region = a.partials + (size_t)(step & 1) * COOP_NQMAX * a.P;
+    coop_tile_sums<NQ>(a, sm, f, region);
+    __threadfence();
+    grid.sync();
+    if (a.pc.world == 1 || blockIdx.x == 0) {
+        const int P = a.P;
+        double x[NQ];                       // all loads first (independent L2 round trips), then the trees
+        if (P <= COOP_NT) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[q] = (tid < P) ? __ldcg(region + (size_t)q * P + tid) : 0.0;
+        } else if (P == 2 * COOP_NT) {
+            double v[NQ][2];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) { v[q][0] = __ldcg(region + (size_t)q * P + 2 * tid); v[q][1] = __ldcg(region + (size_t)q * P + 2 * tid + 1); }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[q] = v[q][0] + v[q][1];
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double* qp = region + (size_t)q * P;
+                if (P == 4 * COOP_NT) x[q] = coop_slice<4>(qp, tid);
+                else if (P == 8 * COOP_NT) x[q] = coop_slice<8>(qp, tid);
+                else x[q] = tree_run(qp + (size_t)tid * (P / COOP_NT), P / COOP_NT);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double r = warp_tree(x[q]);
+            if (lane == 0) sm.seg[q][warp] = r;
+        }
+        __syncthreads();
+        if (warp < NQ) {
+            double x = (lane < COOP_NT / 32) ? sm.seg[warp][lane] : 0.0;
+            x = warp_tree(x);
+            if (lane == 0) sm.tmp[warp] = x;
+        }
+        __syncthreads();
+    }
+    if (a.pc.world == 1) {
+        if (tid < NQ) sm.res[tid] = sm.tmp[tid];
+    } else {
+        double* g = a.gsum + (size_t)(step & 1) * COOP_NQMAX;
+        const unsigned long long want = (a.gen << 20) | (unsigned long long)(step + 1);
+        if (blockIdx.x == 0) {
+            peer_exchange_block(a.pc, sm.tmp, NQ, 1, sm.res);
+            if (tid < NQ) __stcg(g + tid, sm.res[tid]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.gflag) = want;
+        } else {
+            if (tid == 0) {
+                while (*reinterpret_cast<volatile unsigned long long*>(a.gflag) < want) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid < NQ) sm.res[tid] = __ldcg(g + tid);
+        }
     }
     __syncthreads();
-    if (a.pc.world > 1) peer_exchange_block(a.pc, tmp, NQ, 1, res);
-    else if ((int)threadIdx.x < NQ) res[threadIdx.x] = tmp[threadIdx.x];
-    __syncthreads();
+    ++step;
 }
 
-__global__ void __launch_bounds__(256) k_correct_coop(CoopArgs a)
+template <int K>
+__device__ __forceinline__ void coop_solve(const CoopArgs& a, cg::grid_group& grid, CoopSmem& sm, PhiState& st, int& step, int& sweeps,
+                                           double phi_n1)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        st.ess_bar = a.resampled_last_in ? a.tempering_target * a.n_global : a.tempering_target * a.ess_prev_in;   // helpers.jl:14-20
+        st.phi_prop = a.phi_prop_in; st.phi_cur = a.phi_prop_in; st.phi_n1 = phi_n1; st.phi_n = 0.0;
+        st.j = a.j_in; st.n_phi = a.n_phi; st.phase = 0; st.done = 0; st.evals = 0; st.g_last = 0.0;
+        st.lo = 0.0; st.hi = 0.0;
+        phi_fill_walk_k<K>(&st, a.sched);
+    }
+    __syncthreads();
+    while (!st.done) {                       // block-uniform and grid-uniform: every block runs the same state machine
+        double phi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) phi[k] = st.trial[k];
+        const SweepSums<K> f{a, phi, phi_n1};
+        coop_allreduce<2 * K>(a, grid, sm, f, step);
+        if (tid == 0) phi_transition<K>(&st, a.sched, sm.res);
+        ++sweeps;
+        __syncthreads();
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(COOP_NT, 1) k_correct_coop(CoopArgs a)
 {
     cg::grid_group grid = cg::this_grid();
-    constexpr int NQMAX = (2 * CK > 3) ? 2 * CK : 3;
-    __shared__ double sm[NQMAX][8];
-    __shared__ double res[NQMAX], tmpq[NQMAX];
+    __shared__ CoopSmem sm;
+    __shared__ PhiState st;                     // every block runs its own copy of the bisection state machine
     const int tid = threadIdx.x;
     const bool lead = (blockIdx.x == 0 && tid == 0);
     double* scal = a.scal;
-    PhiState* st = a.st;
     double phi_n = a.corr.phi_n;
     const double phi_n1 = a.corr.phi_n1;
+    int step = 0;
 
     if (lead) {
         if (!a.use_carry) { scal[SC_C] = a.c_in; scal[SC_ACCEPT] = a.accept_in; scal[SC_STATUS] = 0.0; }
         scal[SC_EVALS] = 0.0; scal[SC_SWEEPS] = 0.0;
     }
-    // ---- solve_adaptive_phi -------------------------------------------------------------------------
+    // ---- solve_adaptive_phi ---------------------------------------------------------------------------
     if (a.adaptive) {
-        if (lead) {
-            st->ess_bar = a.resampled_last_in ? a.tempering_target * a.n_global : a.tempering_target * a.ess_prev_in;   // helpers.jl:14-20
-            st->phi_prop = a.phi_prop_in; st->phi_cur = a.phi_prop_in; st->phi_n1 = phi_n1; st->phi_n = 0.0;
-            st->j = a.j_in; st->n_phi = a.n_phi; st->phase = 0; st->done = 0; st->evals = 0; st->g_last = 0.0;
-            st->lo = 0.0; st->hi = 0.0;
-            phi_fill_walk_k<CK>(st, a.sched);
-            __threadfence();
-        }
-        grid.sync();
         int sweeps = 0;
-        for (;;) {
-            if (*reinterpret_cast<volatile int*>(&st->done)) break;         // grid-uniform: written before the last barrier
-            double phi[CK];
-#pragma unroll
-            for (int k = 0; k < CK; ++k) phi[k] = __ldcg(&st->trial[k]);
-            const double part = coop_block_sums<2 * CK>(a, sm, [&](int64_t tile, double (&v)[2 * CK]) {
-#pragma unroll
-                for (int q = 0; q < 2 * CK; ++q) v[q] = 0.0;
-                const int64_t base = tile * W_TILE + tid;
-#pragma unroll
-                for (int r = 0; r < W_R; ++r) {
-                    const int64_t i = base + (int64_t)r * W_LANES;
-                    if (i < a.N) {
-                        const double l = __ldg(a.ll + i), o = __ldg(a.old + i), wi = a.w[i];
-#pragma unroll
-                        for (int k = 0; k < CK; ++k) {
-                            const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
-                            v[k] = v[k] + x;
-                            v[CK + k] = v[CK + k] + x * x;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < CK; ++k) { v[k] = v[k] + 0.0; v[CK + k] = v[CK + k] + 0.0 * 0.0; }
-                    }
-                }
-            });
-            if (tid < 2 * CK) __stcg(a.partials + (size_t)tid * a.Pb + blockIdx.x, part);
-            __threadfence();
-            grid.sync();
-            if (blockIdx.x == 0) {
-                coop_root<2 * CK>(a, res, tmpq);
-                if (tid == 0) {
-                    phi_transition<CK>(st, a.sched, res);
-                    __threadfence();
-                }
-            }
-            ++sweeps;
-            grid.sync();
-        }
-        phi_n = __ldcg(&st->phi_n);
+        coop_solve<K>(a, grid, sm, st, step, sweeps, phi_n1);
+        phi_n = st.phi_n;
         if (lead) {
-            scal[SC_J] = (double)st->j; scal[SC_PHI_PROP] = st->phi_prop; scal[SC_EVALS] = (double)st->evals;
+            scal[SC_J] = (double)st.j; scal[SC_PHI_PROP] = st.phi_prop; scal[SC_EVALS] = (double)st.evals;
             scal[SC_SWEEPS] = (double)sweeps;
         }
     }
@@ -241,70 +413,23 @@ __global__ void __launch_bounds__(256) k_correct_coop(CoopArgs a)
 
     // ---- pass A: incremental weights, unnormalised weights, S ------------------------------------------
     {
-        const double part = coop_block_sums<1>(a, sm, [&](int64_t tile, double (&v)[1]) {
-            const int64_t base = tile * W_TILE + tid;
-            double x[W_R];
-#pragma unroll
-            for (int r = 0; r < W_R; ++r) {
-                const int64_t i = base + (int64_t)r * W_LANES;
-                x[r] = 0.0;
-                if (i < a.N) {
-                    const double inc = inc_weight(__ldg(a.ll + i), __ldg(a.old + i), a.corr, phi_n);
-                    x[r] = a.w[i] * inc;
-                    a.w[i] = x[r];
-                    if (a.inc_out) a.inc_out[i] = inc;
-                }
-            }
-            double acc = 0.0;
-#pragma unroll
-            for (int r = 0; r < W_R; ++r) acc = acc + x[r];
-            v[0] = acc;
-        });
-        if (tid == 0) __stcg(a.partials + blockIdx.x, part);
-        __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) {
-            coop_root<1>(a, res, tmpq);
-            if (tid == 0) { scal[SC_S] = res[0]; __threadfence(); }
-        }
-        grid.sync();
+        const PassASums f{a, phi_n};
+        coop_allreduce<1>(a, grid, sm, f, step);
     }
+    const double S = sm.res[0];
+    __syncthreads();
     // ---- pass B: normalised weights, Q = sum W^2, sum W, sum W / n_parts ----------------------------------
     {
-        const double S = __ldcg(scal + SC_S);
-        const double part = coop_block_sums<3>(a, sm, [&](int64_t tile, double (&v)[3]) {
-            const int64_t base = tile * W_TILE + tid;
-            double x[W_R], y[W_R];
-#pragma unroll
-            for (int r = 0; r < W_R; ++r) {
-                const int64_t i = base + (int64_t)r * W_LANES;
-                x[r] = 0.0; y[r] = 0.0;
-                if (i < a.N) {
-                    x[r] = (a.w[i] * a.n_global) / S;
-                    y[r] = x[r] / a.n_global;                 // normalized_weights / n_parts, smc_main.jl:438
-                    a.w[i] = x[r];
-                    if (a.normw_out) a.normw_out[i] = x[r];
-                }
-            }
-            double q = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int r = 0; r < W_R; ++r) { q = q + x[r] * x[r]; s2 = s2 + x[r]; s3 = s3 + y[r]; }
-            v[0] = q; v[1] = s2; v[2] = s3;
-        });
-        if (tid < 3) __stcg(a.partials + (size_t)tid * a.Pb + blockIdx.x, part);
-        __threadfence();
-        grid.sync();
-        if (blockIdx.x == 0) {
-            coop_root<3>(a, res, tmpq);
-            if (tid == 0) {
-                const double n = a.n_global;
-                const double ess = (n * n) / res[0];                            // smc_main.jl:427
-                scal[SC_Q] = res[0]; scal[SC_S2] = res[1]; scal[SC_SRES] = res[2];
-                scal[SC_ESS] = ess;
-                const bool nan = (ess != ess);                                  // check_nan_ess, helpers.jl:270-305
-                if (nan) scal[SC_STATUS] = (double)SMCB200_ERR_NAN_ESS;
-                scal[SC_RESAMPLE] = (!nan && scal[SC_STATUS] == 0.0 && ess < a.threshold_ratio * n) ? 1.0 : 0.0;   // smc_main.jl:435
-            }
+        const PassBSums f{a, S};
+        coop_allreduce<3>(a, grid, sm, f, step);
+        if (lead) {
+            const double n = a.n_global;
+            const double ess = (n * n) / sm.res[0];                         // smc_main.jl:427
+            scal[SC_S] = S; scal[SC_Q] = sm.res[0]; scal[SC_S2] = sm.res[1]; scal[SC_SRES] = sm.res[2];
+            scal[SC_ESS] = ess;
+            const bool nan = (ess != ess);                                  // check_nan_ess, helpers.jl:270-305
+            if (nan) scal[SC_STATUS] = (double)SMCB200_ERR_NAN_ESS;
+            scal[SC_RESAMPLE] = (!nan && scal[SC_STATUS] == 0.0 && ess < a.threshold_ratio * n) ? 1.0 : 0.0;   // smc_main.jl:435
         }
     }
 }
