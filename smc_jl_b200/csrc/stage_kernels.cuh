@@ -345,7 +345,10 @@ __device__ __forceinline__ void coop_allreduce(const CoopArgs& a, cg::grid_group
             if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.gflag) = want;
         } else {
             if (tid == 0) {
-                while (*reinterpret_cast<volatile unsigned long long*>(a.gflag) < want) { }
+                const long long t0 = clock64();
+                while (*reinterpret_cast<volatile unsigned long long*>(a.gflag) < want) {
+                    if (clock64() - t0 > 400000000000ll) { *a.pc.err = 1; break; }      // block 0 is stuck behind a dead peer
+                }
                 __threadfence();
             }
             __syncthreads();

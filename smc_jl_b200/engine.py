@@ -52,6 +52,7 @@ class Engine:
             self.h = None
             raise RuntimeError("smcb200_create(device=%d) failed: %s -- a CUDA GPU is required, there is no CPU "
                                "fallback" % (device, lib.smcb200_status_string(st).decode()))
+        self.device = int(device)
         self.n_parts = 0
         self.n_para = 0
         self.spec = None

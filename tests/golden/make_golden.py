@@ -98,6 +98,23 @@ def main():
          final_mean=np.average(cl["particles"][:, :9], axis=0, weights=cl["particles"][:, -1]),
          sumsq_W=np.sum(W.astype(np.float64) ** 2, axis=0))
 
+    # --- file-format golden: every metadata byte of the reference's JLD2 output (everything except the three big
+    #     Float64 payloads), so that smc_jl_b200/jld2.py can be checked byte for byte without the reference tree -------------
+    raw = open(R + "smc_cloud_fix=true_version=150.jld2", "rb").read()
+    n, ncol, nst = cl["particles"].shape[0], cl["particles"].shape[1], w.shape[1]
+    p0 = 512 + 4742 + 87                        # first byte of the particle payload (cloud object at 4623, array header 87 bytes)
+    p1 = p0 + n * ncol * 8
+    links = j._obj(j.root)["links"]
+    w0 = 512 + links["w"] + 87
+    w1 = w0 + n * nst * 8
+    W0 = 512 + links["W"] + 87
+    W1 = W0 + n * nst * 8
+    save("jld2_structure.npz", head=np.frombuffer(raw[:p0], np.uint8), mid=np.frombuffer(raw[p1:w0], np.uint8),
+         whdr=np.frombuffer(raw[w1:W0], np.uint8), tail=np.frombuffer(raw[W1:], np.uint8), shape=np.array([n, ncol, nst]),
+         tempering_schedule=cl["tempering_schedule"], ESS=cl["ESS"],
+         scalars=np.array([cl["stage_index"], cl["n_Φ"], cl["resamples"]]), fscalars=np.array([cl["c"], cl["accept"], cl["total_sampling_time"]]),
+         file_size=len(raw))
+
     # --- mutation golden ---------------------------------------------------------------
     j = JLD2(R + "mutation_inputs.jld2")
     o = JLD2(R + "mutation_outputs_version=150.jld2")

@@ -87,6 +87,21 @@ def main():
         m1, c1 = single.moments()
         m2, c2 = shard.moments()
         assert np.array_equal(m1, m2) and np.array_equal(c1, c2)
+        if name != "linreg20" or phi_prev < 1.0:
+            # the rest of the recursion in ONE call per engine (smcb200_run_stages: no host in the loop on a fixed schedule)
+            i_first = n_stage + 2
+            n_left = len(sched) - i_first + 1
+            if n_left > 0 and phi_prev < 1.0:
+                cfg = StageConfig(phi_n1=phi_prev, phi_n=0.0, threshold_ratio=0.5, target=0.25, alpha=kw.get("alpha", 1.0), tempering_target=0.8,
+                                  n_mh_steps=kw["n_mh_steps"], n_blocks=kw["n_blocks"], resample_method=0, adaptive=kw["adaptive"], seed=1793, stage=0)
+                h1, h2 = np.zeros((n_left, N)), np.zeros((n_left, hi - lo))
+                q1 = single.run_stages(cfg, s1, sched, i_first, n_left, normw_hist=h1)
+                q2 = shard.run_stages(cfg, s2, sched, i_first, n_left, normw_hist=h2)
+                assert len(q1) == len(q2) and all((a.phi_n, a.ess, a.c, a.accept, a.resampled) == (b.phi_n, b.ess, b.c, b.accept, b.resampled)
+                                                  for a, b in zip(q1, q2)), name
+                assert np.array_equal(h1[:len(q1), lo:hi], h2[:len(q2)])
+                assert np.array_equal(single.download()[lo:hi], shard.download()), "%s: run_stages differs on the sharded engine" % name
+                nres += sum(a.resampled for a in q1)
         assert nres >= (2 if name != "an_schorfheide_mixture" else 1), nres
         single.close(); shard.close()
         dist.barrier()

@@ -1,4 +1,5 @@
-"""Host-side sharding geometry of the multi-GPU engine (mirrors smcb200_cloud_create / k_combine_ranks).
+"""TEST MIRROR of the multi-GPU engine's sharding geometry (smcb200_cloud_create) and cross-rank tree (peer_exchange_block);
+used by tests/test_sharding_gloo.py only -- the product computes both inside libsmcb200.
 
 Particles are split into contiguous ranges of the zero-padded power-of-two index space so that every
 canonical reduction tree is shard-aligned: per-rank roots combined by an adjacent-pair tree in rank order

@@ -142,17 +142,23 @@ def test_bridge_with_prior_mixing(golden):
     assert len(c3) == 2048 and np.all(np.abs(wmean(c3) - truth) < 0.5)
 
 
-def test_checkpoint_and_resume_is_bit_exact(tmp_path):
+@pytest.mark.parametrize("ext", [".jld2", ".npz"])
+def test_checkpoint_and_resume_is_bit_exact(tmp_path, ext):
     """save_intermediate / continue_intermediate (smc_main.jl:334-361,499-507): a run resumed from the stage-10
-    checkpoint ends in exactly the cloud, ESS history and weight history of the uninterrupted run."""
+    checkpoint ends in exactly the cloud, ESS history and weight history of the uninterrupted run.  `.jld2`: the reference's
+    own containers (JLD2 `cloud` / `w` / `W` / `j` with the SMC.Cloud type tag, HDF5 `smcparams`)."""
     from smc_jl_b200 import smc
     from smc_jl_b200.driver import load_cloud
     params, lk, _ = W.linear_gaussian(d=8, T=64, prior_sd=2.0)
     kw = dict(verbose="none", n_parts=3000, n_Φ=25, n_mh_steps=2, n_blocks=2, α=0.9, seed=21)
-    base = str(tmp_path / "run.npz")
-    full, w_full, W_full = smc(lk, params, None, savepath=base, particle_store_path=str(tmp_path / "p.npz"),
+    base = str(tmp_path / ("run" + ext))
+    store = str(tmp_path / ("p" + (".h5" if ext == ".jld2" else ".npz")))
+    full, w_full, W_full = smc(lk, params, None, savepath=base, particle_store_path=store,
                                save_intermediate=True, intermediate_stage_increment=10, **kw)
-    ck = str(tmp_path / "run_stage=10.npz")
+    if ext == ".jld2":
+        from smc_jl_b200.jld2 import read_h5_matrix
+        assert np.array_equal(read_h5_matrix(store, "smcparams"), full.particles[:, :8])
+    ck = str(tmp_path / ("run_stage=10" + ext))
     cloud10, w10, W10, j10 = load_cloud(ck)
     assert cloud10.stage_index == 10 and w10.shape == (3000, 10) and len(cloud10.ESS) == 10
     res, w_res, W_res = smc(lk, params, None, testing=True, continue_intermediate=True, loadpath=ck, **kw)
@@ -196,6 +202,34 @@ def test_errors_mirror_the_reference():
     fixed = [M.parameter(p.key, 1.0, fixed=True) for p in params]
     with pytest.raises((AssertionError, ValueError), match="fixed"):
         smc(lk, fixed, None, testing=True, verbose="none")
+
+
+def test_sharded_smc_matches_the_single_gpu_run(tmp_path):
+    """`smc(...; n_gpus = 2)` (the reference's `parallel = true`): one process per GPU, the bridge initialisation of a tempered
+    update, the whole recursion and the output files on a sharded engine -- the same cloud, history and files as on one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from smc_jl_b200 import smc
+    from smc_jl_b200.driver import load_cloud
+    data, X = W.synthetic_three_equation(T=100)
+    params = W.three_equation_parameters(prior_para=10.0)
+    old, new = M.LinearEquationsLogLik(data[:, :50], X), M.LinearEquationsLogLik(data, X)
+    kw = dict(verbose="none", testing=True, n_Φ=40, n_mh_steps=2, n_blocks=3, α=0.9, seed=5)
+    c_old, _, _ = smc(old, params, None, n_parts=9000, **kw)
+    kw2 = dict(kw, n_parts=16384, old_data=data[:, :50], old_cloud=c_old, old_loglikelihood=old, tempered_update_prior_weight=0.25,
+               testing=False)
+    one = smc(new, params, None, savepath=str(tmp_path / "one.jld2"), particle_store_path=str(tmp_path / "one.h5"), **kw2)
+    two = smc(new, params, None, n_gpus=2, savepath=str(tmp_path / "two.jld2"), particle_store_path=str(tmp_path / "two.h5"), **kw2)
+    assert np.array_equal(one[0].particles, two[0].particles) and np.array_equal(one[0].ESS, two[0].ESS)
+    assert np.array_equal(one[1], two[1]) and np.array_equal(one[2], two[2]) and one[0].resamples == two[0].resamples
+    assert open(str(tmp_path / "one.h5"), "rb").read() == open(str(tmp_path / "two.h5"), "rb").read()
+    assert np.array_equal(load_cloud(str(tmp_path / "two.jld2"))[0].particles, one[0].particles)
+    # adaptive schedule on the sharded engine
+    kw3 = dict(verbose="none", testing=True, n_parts=8192, use_fixed_schedule=False, tempering_target=0.9, n_Φ=40, seed=9)
+    a1 = smc(new, params, None, **kw3)
+    a2 = smc(new, params, None, n_gpus=2, **kw3)
+    assert np.array_equal(a1[0].particles, a2[0].particles) and np.array_equal(a1[0].tempering_schedule, a2[0].tempering_schedule)
 
 
 def test_multi_gpu_sharding_is_bit_invariant():

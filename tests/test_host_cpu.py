@@ -184,23 +184,6 @@ def test_oracle_initial_draw_distributions():
     assert np.array_equal(O.cloud_m(buf2, 500, 8), P[1000:1500])
 
 
-def test_checkpoint_file_round_trip(tmp_path):
-    """The .npz checkpoint container of the smc() driver (keys of src/smc_main.jl:499-507: cloud fields, w, W, j)."""
-    from smc_jl_b200.cloud import Cloud
-    from smc_jl_b200.driver import _save_checkpoint, load_cloud
-    rng = np.random.default_rng(0)
-    c = Cloud(np.asfortranarray(rng.normal(size=(50, 8))), tempering_schedule=np.linspace(0, 1, 7), ESS=np.array([50.0, 31.5]),
-              stage_index=2, n_Φ=7, resamples=1, c=0.42, accept=0.3, total_sampling_time=1.5)
-    w, W = rng.uniform(size=(50, 2)), rng.uniform(size=(50, 2))
-    path = str(tmp_path / "ck.npz")
-    _save_checkpoint(path, c, w, W, 5)
-    c2, w2, W2, j2 = load_cloud(path)
-    assert np.array_equal(c2.particles, c.particles) and c2.particles.flags.f_contiguous
-    assert np.array_equal(c2.ESS, c.ESS) and np.array_equal(c2.tempering_schedule, c.tempering_schedule)
-    assert (c2.stage_index, c2.n_Φ, c2.resamples, c2.c, c2.accept, c2.total_sampling_time, j2) == (2, 7, 1, 0.42, 0.3, 1.5, 5)
-    assert np.array_equal(w2, w) and np.array_equal(W2, W)
-
-
 def test_as_prototype_agrees_with_oracle(golden):
     """tools/as_reduced_prototype.py (numpy, generic matrix algebra) and oracle/as_model.c (fixed operation order,
     L D L' innovations) are two independent restatements of the same reduced An-Schorfheide solution + Kalman filter."""

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 import oracle_lib as O
 from smc_jl_b200 import model as M
 from smc_jl_b200 import workloads as W
-from smc_jl_b200.sharding import combine_ranks, shard_range
+from sharding_mirror import combine_ranks, shard_range
 
 
 def test_shard_geometry():
@@ -96,6 +96,39 @@ def test_two_rank_shards_match_single_process(N):
     ret = ctx.Manager().dict()
     port = 29600 + (N % 97)
     procs = [ctx.Process(target=_worker, args=(r, world, port, N, 4, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(0) is True and ret.get(1) is True
+
+
+def _gather_worker(rank, world, port, tmpdir, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smc_jl_b200.driver import _Group
+        grp = _Group(rank, world, dist, tmpdir if rank == 0 else None)
+        first, count, _ = shard_range(20000, world, rank)
+        full = np.arange(20000 * 3, dtype=np.float64).reshape(20000, 3)
+        ok = True
+        for tag in ("particles", "w"):                                     # two gathers in a row reuse the directory
+            got = grp.gather_rows(full[first:first + count] + (tag == "w"), tag)
+            ok = ok and ((got is None) if rank else np.array_equal(got, full + (tag == "w")))
+        ok = ok and not [f for f in os.listdir(tmpdir) if f.endswith("_%d.npy" % rank)]   # shard files are removed
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_smc_result_gathering(tmp_path):
+    """Host side of `smc(...; n_gpus = G)`: every rank's rows of the cloud / history reach rank 0 in rank order."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, 29731, str(tmp_path), ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
