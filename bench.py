@@ -542,6 +542,8 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         try:
+            if args.no_cpu:
+                raise RuntimeError("skipped (--no-cpu)")
             n_cpu = n_global if (wl.name in ("c2", "c4") and world == 1) else min(n_global, 1 << 16 if wl.name in ("c3", "c5") else N_FULL)
             orc = OracleRun(wl, n_cpu, os.cpu_count() or 1)
             for _ in range(2):
@@ -608,6 +610,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-match", action="store_true", help="skip the ess_match leg (developer runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (developer runs)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

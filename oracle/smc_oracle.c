@@ -626,15 +626,16 @@ ORC_API void orc_moments(const double *cloud, i64 N, int d, double *mean, double
  *   Sw = sum w,  m_k = sum w (x_k - x0_k),  C_ab = sum (w (x_a - x0_a)) (x_b - x0_b)
  *   mean_k = x0_k + m_k / Sw,  cov_ab = C_ab / Sw - (m_a / Sw)(m_b / Sw)
  * Equal to orc_moments (the reference's two-pass form, src/particle.jl:481-532) up to rounding (~1e-15 relative).
- * Canonical order of every sum: chunks of M2_CH consecutive particles, lane l accumulates particles l, l + 32, ...
- * sequentially, adjacent-pair tree over the 32 lanes, then over chunks (zero padded to a power of two). */
+ * Canonical order of every sum (the engine runs them as one FP64 tensor-core SYRK, whose accumulator is a sequential fma
+ * chain over the particles): sub-chunks of M1P_SC consecutive particles accumulated one particle after the other in
+ * ascending order, then the adjacent-pair tree over sub-chunks (zero padded to a power of two). */
+#define M1P_SC 256
 ORC_API void orc_moments_shifted(const double *cloud, i64 N, int d, const double *shift, double *mean, double *cov)
 {
     const double *w = COL(cloud, N, C_WEIGHT(d));
-    i64 nch = (N + M2_CH - 1) / M2_CH;
+    i64 nch = (N + M1P_SC - 1) / M1P_SC;
     i64 Pc = next_pow2(nch < 1 ? 1 : nch);
     double *tl = (double *)calloc((size_t)Pc, sizeof(double));
-    double lane[M_LANES];
     int E = d * (d + 1) / 2, nq = 1 + d + E;
     double *sums = (double *)malloc(sizeof(double) * (size_t)nq);
     for (int q = 0; q < nq; ++q) {
@@ -644,19 +645,14 @@ ORC_API void orc_moments_shifted(const double *cloud, i64 N, int d, const double
         const double *xa = COL(cloud, N, a), *xb = COL(cloud, N, b);
         memset(tl, 0, sizeof(double) * (size_t)Pc);
         for (i64 c = 0; c < nch; ++c) {
-            for (int l = 0; l < M_LANES; ++l) {
-                double acc = 0.0;
-                for (int r = 0; r < M2_CH / M_LANES; ++r) {
-                    i64 i = c * M2_CH + (i64)r * M_LANES + l;
-                    if (i < N) {
-                        if (q == 0) acc = acc + w[i];
-                        else if (q <= d) acc = FMA(w[i], xa[i] - shift[a], acc);
-                        else acc = FMA(w[i] * (xa[i] - shift[a]), xb[i] - shift[b], acc);
-                    }
-                }
-                lane[l] = acc;
+            double acc = 0.0;
+            i64 i1 = (c + 1) * M1P_SC < N ? (c + 1) * M1P_SC : N;
+            for (i64 i = c * M1P_SC; i < i1; ++i) {
+                if (q == 0) acc = acc + w[i];
+                else if (q <= d) acc = FMA(w[i], xa[i] - shift[a], acc);
+                else acc = FMA(w[i] * (xa[i] - shift[a]), xb[i] - shift[b], acc);
             }
-            tl[c] = tree_inplace(lane, M_LANES);
+            tl[c] = acc;
         }
         sums[q] = tree_inplace(tl, Pc);
     }

@@ -15,6 +15,7 @@ namespace smc {
 constexpr int W_LANES = 256, W_R = 4, W_TILE = W_LANES * W_R;      // weight-type sums
 constexpr int M_LANES = 32, M_R = 64, M_TILE = M_LANES * M_R;      // moment-type sums (pass 1)
 constexpr int M2_CH = 512;                                         // scatter-matrix chunk (sequential fma)
+constexpr int M1P_SC = 256;                                        // one-pass moments: sub-chunk accumulated by one warp (sequential fma)
 constexpr int LEAF = 16;                                           // cumsum leaf (sequential)
 constexpr int SCAN_THREADS = 256, SCAN_TILE = SCAN_THREADS * LEAF; // cumsum block tile
 

@@ -107,18 +107,23 @@ struct Tiles { int ntiles, P; };
 Tiles weight_tiles(int64_t n) { int nt = (int)((n + W_TILE - 1) / W_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles moment_tiles(int64_t n) { int nt = (int)((n + M_TILE - 1) / M_TILE); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
 Tiles chunk_tiles(int64_t n) { int nt = (int)((n + M2_CH - 1) / M2_CH); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }
+Tiles unit_tiles(int64_t n) { const int64_t u = (int64_t)M1P_SC * M1P_WARPS; int nt = (int)((n + u - 1) / u); if (nt < 1) nt = 1; return {nt, (int)next_pow2(nt)}; }   // blocks of the one-pass moments
 
 // trial phi per sweep of the adaptive solve: a sweep costs one grid barrier + K exp per particle, so small clouds take
 // wider sweeps (the result does not depend on K)
 int coop_k(int64_t n) { return (n >= ((int64_t)1 << 20)) ? 3 : 7; }
-const void* coop_kernel(int64_t n) { return coop_k(n) == 3 ? (const void*)k_correct_coop<3> : (const void*)k_correct_coop<7>; }
+// variant index: 0 = K 3, 1 = K 7, 2 = fixed schedule (no solve code)
+int coop_variant(int64_t n, bool adaptive) { return !adaptive ? 2 : (coop_k(n) == 3 ? 0 : 1); }
+const void* coop_kernel(int v) { return v == 0 ? (const void*)k_correct_coop<3> : v == 1 ? (const void*)k_correct_coop<7> : (const void*)k_correct_coop<0>; }
 // cooperative grid of k_correct_coop for this shard: at most one block per SM (a short grid barrier), never more blocks
 // than pairs of tiles
-int coop_grid(const Ctx* c, int64_t n)
+int coop_grid(const Ctx* c, int64_t n, int variant)
 {
     const Tiles t = weight_tiles(n);
     int g = (t.ntiles + COOP_GROUPS - 1) / COOP_GROUPS;
-    const int cap = c->sm_count > 0 ? c->sm_count : 1;
+    int per_sm = c->coop_blocks_per_sm[variant];
+    if (per_sm > 2) per_sm = 2;                       // a short grid barrier matters more than a third block
+    const int cap = (c->sm_count > 0 ? c->sm_count : 1) * (per_sm > 0 ? per_sm : 1);
     return g > cap ? cap : g;
 }
 
@@ -163,7 +168,8 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
     a.partials = c->coop_partials; a.scal = c->scal; a.pc = peer_ctx(c);
     a.gsum = c->coop_gsum; a.gflag = c->coop_gflag; a.gen = ++c->coop_gen;
     void* args[] = {&a};
-    SMC_CUDA(c, cudaLaunchCooperativeKernel(coop_kernel(c->N), dim3(coop_grid(c, c->N)), dim3(COOP_NT), args, 0, c->stream));
+    const int variant = coop_variant(c->N, L.adaptive != 0);
+    SMC_CUDA(c, cudaLaunchCooperativeKernel(coop_kernel(variant), dim3(coop_grid(c, c->N, variant)), dim3(COOP_NT), args, 0, c->stream));
     c->launches += 1;
     return SMCB200_OK;
 }
@@ -381,19 +387,10 @@ int launch_moments(Ctx* c)
 }
 
 // ---- one-pass moments + step size + proposal factor (the fused stage) ---------------------------------------------
-template <int D>
-int launch_m1p(Ctx* c, const double* x0, const double* x1, const double* wcol, const double* shift, int64_t stride, const Tiles& t)
+template <int NT>
+int launch_mma(Ctx* c, unsigned grid, const double* x0, const double* x1, const double* wcol, const double* shift, int64_t stride, int P)
 {
-    constexpr size_t stage = (size_t)(D + 1) * M2_CH, red = (size_t)(1 + D + D * (D + 1) / 2) * 33;
-    constexpr size_t smem = sizeof(double) * (stage > red ? stage : red);
-    static bool configured = false;
-    if (!configured) {
-        if (smem > 48 * 1024)
-            SMC_CUDA(c, cudaFuncSetAttribute(k_moments1p<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMC_CUDA(c, cudaFuncSetAttribute(k_moments1p<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
-    k_moments1p<D><<<t.ntiles, 32 * M1P_G, smem, c->stream>>>(x0, x1, wcol, c->N, c->scal, shift, stride, c->m1p_partials, t.P);
+    k_moments_mma<NT><<<grid, 32 * M1P_WARPS, 0, c->stream>>>(x0, x1, wcol, c->N, c->d, c->scal, shift, stride, c->m1p_partials, P);
     return SMCB200_OK;
 }
 
@@ -406,26 +403,17 @@ int launch_moments_prepare(Ctx* c, const BlockSpec& bs, double target)
     // shift = parameter vector of global particle 0 in the (pre-selection) current buffer of rank 0
     const double* shift = (c->world > 1) ? c->shift_base[c->cur] : x0;
     const int64_t stride = (c->world > 1) ? c->n_rank0 : c->N;
-    const Tiles t = chunk_tiles(c->N);
+    const Tiles t = unit_tiles(c->N);
     const int E = d * (d + 1) / 2, nq = 1 + d + E;
+    const unsigned grid = (unsigned)t.ntiles;
     int st = SMCB200_OK;
-    switch (d) {
-    case 2: st = launch_m1p<2>(c, x0, x1, wcol, shift, stride, t); break;
-    case 3: st = launch_m1p<3>(c, x0, x1, wcol, shift, stride, t); break;
-    case 4: st = launch_m1p<4>(c, x0, x1, wcol, shift, stride, t); break;
-    case 5: st = launch_m1p<5>(c, x0, x1, wcol, shift, stride, t); break;
-    case 6: st = launch_m1p<6>(c, x0, x1, wcol, shift, stride, t); break;
-    case 8: st = launch_m1p<8>(c, x0, x1, wcol, shift, stride, t); break;
-    case 9: st = launch_m1p<9>(c, x0, x1, wcol, shift, stride, t); break;
-    case 10: st = launch_m1p<10>(c, x0, x1, wcol, shift, stride, t); break;
-    case 12: st = launch_m1p<12>(c, x0, x1, wcol, shift, stride, t); break;
-    case 16: st = launch_m1p<16>(c, x0, x1, wcol, shift, stride, t); break;
-    case 20: st = launch_m1p<20>(c, x0, x1, wcol, shift, stride, t); break;
-    case 24: st = launch_m1p<24>(c, x0, x1, wcol, shift, stride, t); break;
-    case 32: st = launch_m1p<32>(c, x0, x1, wcol, shift, stride, t); break;
-    default:
-        k_moments1p_generic<<<t.ntiles, 128, 0, c->stream>>>(x0, x1, wcol, c->N, d, c->scal, shift, stride, c->m1p_partials, t.P);
-        break;
+    switch ((d + 1 + 7) / 8) {      // tiles of 8 variables holding d parameters + the constant
+    case 1: st = launch_mma<1>(c, grid, x0, x1, wcol, shift, stride, t.P); break;
+    case 2: st = launch_mma<2>(c, grid, x0, x1, wcol, shift, stride, t.P); break;
+    case 3: st = launch_mma<3>(c, grid, x0, x1, wcol, shift, stride, t.P); break;
+    case 4: st = launch_mma<4>(c, grid, x0, x1, wcol, shift, stride, t.P); break;
+    case 5: st = launch_mma<5>(c, grid, x0, x1, wcol, shift, stride, t.P); break;
+    default: return fail(c, SMCB200_ERR_UNSUPPORTED, "one-pass moments support n_para <= 39");
     }
     if (st) return st;
     k_moments_finish<<<nq, 256, 0, c->stream>>>(c->m1p_partials, t.P, nq, c->m1p_sums, c->m1p_sums + (1 + DMAX + PACKMAX), c->counters + 6,
@@ -661,7 +649,8 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
         ok = ok && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm[0], k_correct_coop<3>, COOP_NT, 0) == cudaSuccess;
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm[1], k_correct_coop<7>, COOP_NT, 0) == cudaSuccess;
-        ok = ok && c->coop_blocks_per_sm[0] >= 1 && c->coop_blocks_per_sm[1] >= 1;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->coop_blocks_per_sm[2], k_correct_coop<0>, COOP_NT, 0) == cudaSuccess;
+        ok = ok && c->coop_blocks_per_sm[0] >= 1 && c->coop_blocks_per_sm[1] >= 1 && c->coop_blocks_per_sm[2] >= 1;
     }
     ok = ok && cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM) == cudaSuccess;
@@ -756,7 +745,7 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     const Tiles tw = weight_tiles(c->N), tm = moment_tiles(c->N);
     const int E = n_para * (n_para + 1) / 2;
     const size_t len = (size_t)6 * tw.P;
-    const Tiles tch = chunk_tiles(c->N);
+    const Tiles tch = chunk_tiles(c->N), tun = unit_tiles(c->N);
     size_t lm = (size_t)(n_para + 1) * tm.P;
     if ((size_t)E * tch.P > lm) lm = (size_t)E * tch.P;
     c->partials_len_m = lm;
@@ -773,7 +762,7 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     // fused-stage buffers: weight-history ring, accept-column tile sums, one-pass moment partials, cooperative-grid partials
     SMC_CUDA(c, cudaMalloc(&c->hist_scr, sizeof(double) * (size_t)HIST_RING * 2 * c->N));
     const size_t nq1 = (size_t)1 + n_para + E;
-    c->m1p_P = tch.P; c->m1p_len = nq1 * tch.P;
+    c->m1p_P = tun.P; c->m1p_len = nq1 * tun.P;
     SMC_CUDA(c, cudaMalloc(&c->m1p_partials, sizeof(double) * c->m1p_len));
     SMC_CUDA(c, cudaMemset(c->m1p_partials, 0, sizeof(double) * c->m1p_len));
     SMC_CUDA(c, cudaMalloc(&c->m1p_sums, sizeof(double) * 2 * (1 + DMAX + PACKMAX)));

@@ -201,6 +201,158 @@ __device__ __forceinline__ double mvn_quad(int b, uint32_t mask, double (&v)[D])
 
 // MIX = (alpha < 1): the three-component mixture proposal of mvnormal_mixture_draw (helpers.jl:87-100) and
 // the proposal densities of compute_proposal_densities (helpers.jl:128-164).
+
+// scalars of one chain (loglh, logprior, old_loglh of the current state) + the outcome of the last step
+struct ChainScal { double like, lpri, lprev; int accepted; };
+
+// ONE Metropolis-Hastings step of one block of parameters (mutation.jl:75-134).  SMC_STEP_CALL = 1 compiles it as a real
+// call: as straight-line code outside the kernel's loops ptxas rotates the uniform registers that carry the factor
+// entries into the DFMAs (LDCU.128 several columns ahead) instead of funnelling a whole mat-vec through one uniform
+// register quad.  Measured on B200 (tools/operand_probe.cu, profiles/r02_operand_probe.txt): the mat-vec alone gains
+// (25.6 -> 29.1 TFLOP/s at 20 warps/SM), the kernel does not (0.290 -> 0.309 ms: the call's spills and the lost
+// overlap across steps cost more), so the step stays inlined.
+#ifndef SMC_STEP_CALL
+#define SMC_STEP_CALL 0
+#endif
+#if SMC_STEP_CALL
+#define SMC_STEP_ATTR __noinline__
+#else
+#define SMC_STEP_ATTR __forceinline__
+#endif
+template <class LIK, bool HAS_OLD, int BLK, bool MIX>
+__device__ SMC_STEP_ATTR ChainScal mh_step(const double* cur, double* cand, const float4* NTAB, uint64_t seed, uint32_t gp, uint32_t stage,
+                                           uint32_t sb, int b, double phi, double omphi, double alpha, ChainScal ch)
+{
+    constexpr int D = LIK::D;
+    constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
+    const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
+    // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
+    const u32x4 r4 = rng4(seed, gp, stage, sb, PURP_STEP);
+    const double step_prob = u01(r4.x, r4.y);
+    int comp = 1;
+    if (MIX) {
+        const double u_mix = u01(r4.z, r4.w);
+        comp = (u_mix < alpha) ? 1 : ((u_mix < alpha + (1.0 - alpha) / 2.0) ? 2 : 3);
+    }
+    // (1) + (2): one Philox block gives the four normals of parameters 4q .. 4q+3 (table-driven inverse
+    // CDF, normal_icdf); each normal is consumed at once by its column of the proposal increment
+    // s = (c L) z (every s[r] sums over ascending columns j, the oracle's order), so the normals never
+    // leave registers.  The mixture path also parks them in the candidate buffer (component 2 needs z_k).
+    constexpr int NQUAD = (D + 3) / 4;
+#if SMC_NORM_BATCH
+    // phase-batched: every Philox block of the step first (independent chains), then all table rows and
+    // polynomials, then the mat-vec -- the long-latency operations (IMAD chains, uint->float conversions,
+    // table loads) of different normals overlap instead of sitting in front of each column's DFMAs
+    float zf[4 * NQUAD];
+    {
+        uint32_t rw[4 * NQUAD];
+#pragma unroll
+        for (int q = 0; q < NQUAD; ++q) {
+            if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
+                const u32x4 r = rng4(seed, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL);
+                rw[4 * q] = r.x; rw[4 * q + 1] = r.y; rw[4 * q + 2] = r.z; rw[4 * q + 3] = r.w;
+            } else {
+                rw[4 * q] = 0u; rw[4 * q + 1] = 0u; rw[4 * q + 2] = 0u; rw[4 * q + 3] = 0u;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4 * NQUAD; ++j) zf[j] = (j < D) ? normal_icdf_f(rw[j], NTAB) : 0.0f;
+    }
+    double s[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) s[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double zj = f2d(zf[j]);
+        if (MIX) cand[j * MUT_THREADS] = zj;
+        if (BLK == 2 || ((mask >> j) & 1u)) {
+#pragma unroll
+            for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], zj, s[r]);
+        }
+    }
+#else
+    double s[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) s[k] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQUAD; ++q) {
+        if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
+            double z[4];
+            normal_quad(rng4(seed, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), NTAB, z[0], z[1], z[2], z[3]);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * q + jj;
+                if (j < D) {
+                    if (MIX) cand[j * MUT_THREADS] = z[jj];
+                    if (BLK == 2 || ((mask >> j) & 1u)) {
+#pragma unroll
+                        for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], z[jj], s[r]);
+                    }
+                }
+            }
+        }
+    }
+#endif
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const double t = cur[k * MUT_THREADS];
+        if (MIX) {
+            // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
+            const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
+            const double base = (comp == 3) ? c_mut.mu[k] : t;
+            s[k] = ((mask >> k) & 1u) ? base + inc : t;
+        } else {
+            s[k] = (BLK == 2 || ((mask >> k) & 1u)) ? t + s[k] : t;          // s is now theta'
+        }
+        cand[k * MUT_THREADS] = s[k];
+    }
+    const bool ok = in_bounds<D>(s);
+    double pn = logprior<D>(s);
+    double ln = LIK::template ll<0>(s);
+    if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
+    double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
+    if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
+    // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
+    double qdiff = 0.0;
+    if (MIX) {
+        // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
+        // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
+        // fma chains, so one evaluation serves both.
+        const double lognorm = c_mut.lognorm[b];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
+        double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if ((mask >> k) & 1u) {
+                const double zs = s[k] * c_mut.isd[b][k];
+                ind = (ind * c_mut.isdn[b][k]) * det_exp(-0.5 * (zs * zs));
+            }
+        const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+        for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+        const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+#pragma unroll
+        for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
+        const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
+        const double w2 = (1.0 - alpha) / 2.0;
+        double q0 = alpha * e_sym, q1 = alpha * e_sym;
+        q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
+        q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
+        q0 = det_log(q0); q1 = det_log(q1);
+        if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
+        qdiff = q0 - q1;
+    }
+    const double eta = det_exp(((phi * (ln - ch.like) + omphi * (lo - ch.lprev)) + (pn - ch.lpri)) + qdiff);
+    ch.accepted = 0;
+    if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
+        ch.like = ln; ch.lpri = pn; ch.lprev = lo;
+        ch.accepted = 1;
+    }
+    return ch;
+}
+
 template <class LIK, bool HAS_OLD, int BLK, bool MIX>
 __global__ void __launch_bounds__(MUT_THREADS, LIK::MINB)
 k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
@@ -233,146 +385,27 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
         double* buf1 = sm_state + D * MUT_THREADS + threadIdx.x;
 #pragma unroll
         for (int k = 0; k < D; ++k) buf0[k * MUT_THREADS] = src[col_off(N, k) + i];
-        double like = src[col_off(N, D) + i];
-        double lpri = src[col_off(N, D + 1) + i];
-        double lprev = src[col_off(N, D + 2) + i];
+        ChainScal ch;
+        ch.like = src[col_off(N, D) + i];
+        ch.lpri = src[col_off(N, D + 1) + i];
+        ch.lprev = src[col_off(N, D + 2) + i];
+        ch.accepted = 0;
         bool flipped = false;
         const uint32_t gp = (uint32_t)(index0 + i);
         const double phi = a.scal ? a.scal[SC_PHI_N] : a.phi_n;
         const double omphi = 1.0 - phi;
         constexpr bool SINGLE = BLK != 0;
-        constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
         const int nb = SINGLE ? 1 : a.n_blocks;
 
         for (int step = 0; step < a.n_mh_steps; ++step) {
             for (int bb = 0; bb < nb; ++bb) {
                 const int b = SINGLE ? 0 : bb;
                 const uint32_t sb = (uint32_t)(step * nb + b);
-                const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
                 const double* cur = flipped ? buf1 : buf0;
                 double* cand = flipped ? buf0 : buf1;
-                // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
-                const u32x4 r4 = rng4(a.seed, gp, a.stage, sb, PURP_STEP);
-                const double step_prob = u01(r4.x, r4.y);
-                int comp = 1;
-                if (MIX) {
-                    const double u_mix = u01(r4.z, r4.w);
-                    comp = (u_mix < a.alpha) ? 1 : ((u_mix < a.alpha + (1.0 - a.alpha) / 2.0) ? 2 : 3);
-                }
-                // (1) + (2): one Philox block gives the four normals of parameters 4q .. 4q+3 (table-driven inverse
-                // CDF, normal_icdf); each normal is consumed at once by its column of the proposal increment
-                // s = (c L) z (every s[r] sums over ascending columns j, the oracle's order), so the normals never
-                // leave registers.  The mixture path also parks them in the candidate buffer (component 2 needs z_k).
-                constexpr int NQUAD = (D + 3) / 4;
-#if SMC_NORM_BATCH
-                // phase-batched: every Philox block of the step first (independent chains), then all table rows and
-                // polynomials, then the mat-vec -- the long-latency operations (IMAD chains, uint->float conversions,
-                // table loads) of different normals overlap instead of sitting in front of each column's DFMAs
-                float zf[4 * NQUAD];
-                {
-                    uint32_t rw[4 * NQUAD];
-#pragma unroll
-                    for (int q = 0; q < NQUAD; ++q) {
-                        if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
-                            const u32x4 r = rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL);
-                            rw[4 * q] = r.x; rw[4 * q + 1] = r.y; rw[4 * q + 2] = r.z; rw[4 * q + 3] = r.w;
-                        } else {
-                            rw[4 * q] = 0u; rw[4 * q + 1] = 0u; rw[4 * q + 2] = 0u; rw[4 * q + 3] = 0u;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4 * NQUAD; ++j) zf[j] = (j < D) ? normal_icdf_f(rw[j], NTAB) : 0.0f;
-                }
-                double s[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) s[k] = 0.0;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const double zj = f2d(zf[j]);
-                    if (MIX) cand[j * MUT_THREADS] = zj;
-                    if (BLK == 2 || ((mask >> j) & 1u)) {
-#pragma unroll
-                        for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], zj, s[r]);
-                    }
-                }
-#else
-                double s[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) s[k] = 0.0;
-#pragma unroll
-                for (int q = 0; q < NQUAD; ++q) {
-                    if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
-                        double z[4];
-                        normal_quad(rng4(a.seed, gp, a.stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), NTAB, z[0], z[1], z[2], z[3]);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = 4 * q + jj;
-                            if (j < D) {
-                                if (MIX) cand[j * MUT_THREADS] = z[jj];
-                                if (BLK == 2 || ((mask >> j) & 1u)) {
-#pragma unroll
-                                    for (int r = j; r < D; ++r) s[r] = fma(c_mut.L[b][lcol<D>(r, j)], z[jj], s[r]);
-                                }
-                            }
-                        }
-                    }
-                }
-#endif
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    const double t = cur[k * MUT_THREADS];
-                    if (MIX) {
-                        // component 2: theta_old + c sqrt(Sigma_ii) z_i; component 3: theta_bar + c L z
-                        const double inc = (comp == 2) ? c_mut.csd[b][k] * cand[k * MUT_THREADS] : s[k];
-                        const double base = (comp == 3) ? c_mut.mu[k] : t;
-                        s[k] = ((mask >> k) & 1u) ? base + inc : t;
-                    } else {
-                        s[k] = (BLK == 2 || ((mask >> k) & 1u)) ? t + s[k] : t;          // s is now theta'
-                    }
-                    cand[k * MUT_THREADS] = s[k];
-                }
-                const bool ok = in_bounds<D>(s);
-                double pn = logprior<D>(s);
-                double ln = LIK::template ll<0>(s);
-                if (ln == -dinf()) pn = -dinf();                       // mutation.jl:102-104
-                double lo = HAS_OLD ? LIK::template ll<1>(s) : 0.0;    // mutation.jl:106
-                if (!ok) { pn = -dinf(); ln = -dinf(); lo = -dinf(); } // ParamBoundsError, mutation.jl:112-121
-                // alpha == 1: q0 - q1 == +0 exactly (symmetric proposal), see DESIGN.md
-                double qdiff = 0.0;
-                if (MIX) {
-                    // compute_proposal_densities (helpers.jl:128-164).  The first terms of q0 and q1 are the same
-                    // number: N(theta_old; theta', c^2 Sigma) and N(theta'; theta_old, c^2 Sigma) run sign-mirrored
-                    // fma chains, so one evaluation serves both.
-                    const double lognorm = c_mut.lognorm[b];
-#pragma unroll
-                    for (int k = 0; k < D; ++k)
-                        s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - cand[k * MUT_THREADS] : 0.0;
-                    double ind = 1.0;                                   // diagonal component: variance Sigma_ii, no c
-#pragma unroll
-                    for (int k = 0; k < D; ++k)
-                        if ((mask >> k) & 1u) {
-                            const double zs = s[k] * c_mut.isd[b][k];
-                            ind = (ind * c_mut.isdn[b][k]) * det_exp(-0.5 * (zs * zs));
-                        }
-                    const double e_sym = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
-#pragma unroll
-                    for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cur[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
-                    const double e_old = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
-#pragma unroll
-                    for (int k = 0; k < D; ++k) s[k] = ((mask >> k) & 1u) ? cand[k * MUT_THREADS] - c_mut.mu[k] : 0.0;
-                    const double e_new = det_exp(-0.5 * (lognorm + mvn_quad<D>(b, mask, s)));
-                    const double w2 = (1.0 - a.alpha) / 2.0;
-                    double q0 = a.alpha * e_sym, q1 = a.alpha * e_sym;
-                    q0 = q0 + w2 * ind; q1 = q1 + w2 * ind;
-                    q0 = q0 + w2 * e_old; q1 = q1 + w2 * e_new;
-                    q0 = det_log(q0); q1 = det_log(q1);
-                    if (q0 == dinf() && q1 == dinf()) q0 = 0.0;
-                    qdiff = q0 - q1;
-                }
-                const double eta = det_exp(((phi * (ln - like) + omphi * (lo - lprev)) + (pn - lpri)) + qdiff);
-                if (step_prob < eta) {                                  // strict <, NaN rejects (mutation.jl:126)
+                ch = mh_step<LIK, HAS_OLD, BLK, MIX>(cur, cand, NTAB, a.seed, gp, a.stage, sb, b, phi, omphi, a.alpha, ch);
+                if (ch.accepted) {
                     flipped = !flipped;
-                    like = ln; lpri = pn; lprev = lo;
                     acc_cnt += c_mut.bsize[b];
                 }
             }
@@ -380,9 +413,9 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
         const double* cur = flipped ? buf1 : buf0;
 #pragma unroll
         for (int k = 0; k < D; ++k) cloud[col_off(N, k) + i] = cur[k * MUT_THREADS];
-        cloud[col_off(N, D) + i] = like;
-        cloud[col_off(N, D + 1) + i] = lpri;
-        cloud[col_off(N, D + 2) + i] = lprev;
+        cloud[col_off(N, D) + i] = ch.like;
+        cloud[col_off(N, D + 1) + i] = ch.lpri;
+        cloud[col_off(N, D + 2) + i] = ch.lprev;
         cloud[col_off(N, D + 3) + i] = (double)acc_cnt / (double)a.n_free;   // particle.jl:410-418
     }
     // mean of the accept column (update_acceptance_rate!, particle.jl:466-468): the per-particle counts are integers, so

@@ -1,9 +1,8 @@
 // stage_kernels.cuh -- the fused per-stage kernels (src/smc_main.jl:377-465 without the host in the loop):
 //   k_correct_coop    ONE cooperative launch for solve_adaptive_phi (src/helpers.jl:9-56) + correction + ESS +
 //                     the resample decision (src/smc_main.jl:386-435); every decision is left in device scalars
-//   k_moments1p<D>    weighted mean / covariance in ONE pass over the cloud (src/particle.jl:481-532): a chunk's
-//                     columns arrive by bulk asynchronous copies (cp.async.bulk + mbarrier), four warps share the
-//                     lower triangle
+//   k_moments_mma<NT> weighted mean / covariance in ONE pass over the cloud (src/particle.jl:481-532) as a weighted SYRK
+//                     on the FP64 tensor path (mma.sync.m8n8k4.f64), fragments loaded straight from the cloud's columns
 //   k_moments_finish  tile trees of the one-pass sums; its last block exchanges them across GPUs, updates the step
 //                     size (src/smc_main.jl:453-455) and factors the proposal covariance (src/mutation.jl:81) with
 //                     the whole block -> MutConst
@@ -384,8 +383,13 @@ __device__ __forceinline__ void coop_solve(const CoopArgs& a, cg::grid_group& gr
     }
 }
 
+// K = trial phi per sweep of the adaptive solve; K = 0: fixed schedule only -- a leaner kernel (no solve code, half the
+// registers) of which two blocks fit on an SM, so twice as many tiles are in flight during the two weight passes
+#ifndef SMC_COOP_MINB_ADAPTIVE
+#define SMC_COOP_MINB_ADAPTIVE 1
+#endif
 template <int K>
-__global__ void __launch_bounds__(COOP_NT, 1) k_correct_coop(CoopArgs a)
+__global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE) k_correct_coop(CoopArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ CoopSmem sm;
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(COOP_NT, 1) k_correct_coop(CoopArgs a)
         scal[SC_EVALS] = 0.0; scal[SC_SWEEPS] = 0.0;
     }
     // ---- solve_adaptive_phi ---------------------------------------------------------------------------
-    if (a.adaptive) {
+    if constexpr (K > 0) if (a.adaptive) {
         int sweeps = 0;
         coop_solve<K>(a, grid, sm, st, step, sweeps, phi_n1);
         phi_n = st.phi_n;
@@ -438,218 +442,141 @@ __global__ void __launch_bounds__(COOP_NT, 1) k_correct_coop(CoopArgs a)
 }
 
 // =================================================================================================
-// One-pass moments.  With x0 = the parameter vector of global particle 0 (any point of the cloud's support) as shift,
+// One-pass moments on the FP64 tensor path.  With x0 = the parameter vector of global particle 0 (any point of the
+// cloud's support) as shift,
 //   Sw = sum w,  m_k = sum w (x_k - x0_k),  C_ab = sum (w (x_a - x0_a)) (x_b - x0_b)
 //   mean_k = x0_k + m_k / Sw,   cov_ab = C_ab / Sw - (m_a / Sw)(m_b / Sw)
 // which is weighted_mean / weighted_cov (src/particle.jl:481-532; StatsBase.cov(..., corrected = false)) in one sweep
 // instead of two (the reference's two-pass result differs from it by rounding only: ~1e-15 relative).
-// Canonical order per quantity: inside a chunk of M2_CH = 512 consecutive particles lane l accumulates particles
-// l, l + 32, ... sequentially, then the adjacent-pair tree over the 32 lanes, then over chunks.
-// Mapping: one block of 8 warps per chunk.  The chunk's d + 1 columns (86 KB at d = 20) arrive in two halves by bulk
-// asynchronous copies (cp.async.bulk, 2 KB each, completion on one mbarrier per half), so the first half is reduced
-// while the second is still in flight and two resident blocks per SM keep ~170 KB outstanding; lane = particle and
-// warp g owns the rows [rowb(g), rowb(g+1)) of the lower triangle (~26 register accumulators at d = 20).
+// All 1 + d + d(d+1)/2 sums are the lower triangle of ONE weighted SYRK  G = sum_p (w_p y_p) y_p'  over the augmented
+// vector y = (x_0 - x0_0, ..., x_{d-1} - x0_{d-1}, 1): G_ab = C_ab, G_db = m_b, G_dd = Sw.  It runs as
+// mma.sync.m8n8k4.f64 (DMMA; measured 37 TFLOP/s on B200 against 32 for DFMA, one issue slot per 256 fma):
+// M and N index the variables in tiles of 8, K runs over the particles four at a time; the value a lane loads for
+// variable tile t -- y[8t + lane/4][p + lane%4], an 8 x 32-byte sector pattern straight from the cloud's columns -- is the
+// B fragment of column tile t and, times w_p, the A fragment of row tile t.  No shared memory, no barriers: a warp owns
+// M1P_SC consecutive particles, keeps the NT(NT+1)/2 lower tiles in registers and prefetches the next 16 particles
+// while the tensor pipe works on the current ones.  (A warp-private cp.async ring in shared memory was measured slower:
+// 8-byte LDGSTS saturate the MIO queue -- 57 vs 50 us at d = 20, N = 2^20.)
+// Canonical order per quantity (DMMA accumulates k ascending with one rounding per fma -- profiles/r01_dmma_probe.txt):
+// sequential fma chain acc <- fma(w_p y_a[p], y_b[p], acc) over the particles of a sub-chunk in ascending order, then the
+// adjacent-pair tree over sub-chunks (zero padded to a power of two).  Mirrored by orc_moments_shifted.
 // Partials layout: [1 + d + d(d+1)/2][P] with quantity 0 = Sw, 1 + k = m_k, 1 + d + a(a+1)/2 + b = C_ab.
 // =================================================================================================
-constexpr int M1P_G = 4;
-template <int D>
-__host__ __device__ constexpr int m1p_rowb(int g)
+constexpr int M1P_WARPS = 4;               // sub-chunks per block (measured at d = 20, N = 2^20: 4 warps x 4 blocks per SM 50 us; 2 x 7: 60 us; 4 x 5 at 96 registers: 56 us)
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 {
-    int a = 0;
-    while (a < D && (a * (a + 1)) / 2 * M1P_G < g * (D * (D + 1) / 2)) ++a;
-    return g >= M1P_G ? D : a;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+// one batch = M1P_KS k-steps = 16 consecutive particles: this lane's fragment elements, straight from the columns.
+// Only the last variable tile can hold the constant / the zero padding (8 (NT - 1) <= d): its lanes load nothing.
+constexpr int M1P_KS = 4;
+template <int NT>
+__device__ __forceinline__ void m1p_load(double (&xv)[M1P_KS][NT], double (&wv)[M1P_KS], const double* const (&col)[NT], const double* wcol,
+                                         int64_t p, int64_t N, bool real_last, double sh_last)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-
-// One row group of the lower triangle over one chunk.  The two halves of the chunk are consumed as they arrive.
-// Every thread of the block must call this (block barrier inside).
-template <int D, int GRP>
-__device__ __forceinline__ void m1p_group(const double* __restrict__ xs /* smem [D+1][M2_CH] */, int64_t N, int64_t c0, int lane,
-                                          const double* __restrict__ shift, uint64_t* bars, bool bulk, double* __restrict__ red)
-{
-    constexpr int A0 = m1p_rowb<D>(GRP), A1 = m1p_rowb<D>(GRP + 1);
-    constexpr int NR = (A1 > A0) ? (A1 - A0) : 1;
-    constexpr int NC = (A1 > 0) ? A1 : 1;
-    constexpr int HALF = M2_CH / 2;
-    double acc[NR][NC], m1[NR];
 #pragma unroll
-    for (int a = 0; a < NR; ++a) {
-        m1[a] = 0.0;
+    for (int s = 0; s < M1P_KS; ++s) {
+        // beyond N: weight 0 and the (finite) row of the last particle, i.e. fma(0 y_a, y_b, acc) = acc
+        const int64_t q = p + 4 * s;
+        const bool in = q < N;
+        const int64_t pc = in ? q : N - 1;
+        const double w = __ldg(wcol + pc);
+        wv[s] = in ? w : 0.0;
 #pragma unroll
-        for (int b = 0; b < NC; ++b) acc[a][b] = 0.0;
+        for (int t = 0; t < NT - 1; ++t) xv[s][t] = __ldg(col[t] + pc);
+        xv[s][NT - 1] = real_last ? __ldg(col[NT - 1] + pc) : sh_last;
     }
-    double sw = 0.0;
-    double mu[NC];
+}
+template <int NT>
+__device__ __forceinline__ void m1p_batch(double (&acc)[NT * (NT + 1) / 2][2], const double (&xv)[M1P_KS][NT], const double (&wv)[M1P_KS],
+                                          const double (&sh)[NT], bool real_last, double cst_last)
+{
 #pragma unroll
-    for (int k = 0; k < NC; ++k) mu[k] = (k < A1) ? shift[k] : 0.0;
+    for (int s = 0; s < M1P_KS; ++s) {
+        double bf[NT], af[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            bf[t] = xv[s][t] - sh[t];
+            if (t == NT - 1) bf[t] = real_last ? bf[t] : cst_last;
+            af[t] = wv[s] * bf[t];
+        }
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+            for (int tj = 0; tj <= ti; ++tj) dmma884(acc[ti * (ti + 1) / 2 + tj], af[ti], bf[tj]);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void m1p_subchunk(double (&acc)[NT * (NT + 1) / 2][2], const double* const (&col)[NT], const double* wcol, int64_t p,
+                                             int64_t N, const double (&sh)[NT], bool real_last, double cst_last)
+{
+    double xa[M1P_KS][NT], wa[M1P_KS], xb[M1P_KS][NT], wb[M1P_KS];
+    constexpr int B = 4 * M1P_KS;                       // particles per batch
+    m1p_load<NT>(xa, wa, col, wcol, p, N, real_last, sh[NT - 1]);
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        if (bulk) mbar_wait(bars + half, 0u);
-#pragma unroll 2
-        for (int r = half * (HALF / 32); r < (half + 1) * (HALF / 32); ++r) {
-            const int64_t i = c0 + (int64_t)r * 32 + lane;
-            if (i < N) {
-                const double wi = xs[D * M2_CH + r * 32 + lane];
-                if (GRP == 0) sw = sw + wi;
-                if (A1 > A0) {
-                    double dx[NC];
-#pragma unroll
-                    for (int k = 0; k < A1; ++k) dx[k] = xs[k * M2_CH + r * 32 + lane] - mu[k];
-#pragma unroll
-                    for (int a = A0; a < A1; ++a) {
-                        m1[a - A0] = fma(wi, dx[a], m1[a - A0]);
-                        const double wa = wi * dx[a];
-#pragma unroll
-                        for (int b = 0; b <= a; ++b) acc[a - A0][b] = fma(wa, dx[b], acc[a - A0][b]);
-                    }
-                }
-            }
-        }
-    }
-    // per-lane sums -> shared memory rows [quantity][lane] (row stride 33: conflict-free for the row-wise tree that
-    // follows); the rows alias the staged columns, so every warp of the block must have finished reading them
-    __syncthreads();
-    if (GRP == 0) red[lane] = sw;
-    if (A1 > A0) {
-#pragma unroll
-        for (int a = A0; a < A1; ++a) {
-            red[(1 + a) * 33 + lane] = m1[a - A0];
-#pragma unroll
-            for (int b = 0; b <= a; ++b) red[(1 + D + a * (a + 1) / 2 + b) * 33 + lane] = acc[a - A0][b];
-        }
+    for (int it = 0; it < M1P_SC / (2 * B); ++it) {     // two batches per trip: the register sets swap roles, no copies
+        m1p_load<NT>(xb, wb, col, wcol, p + B, N, real_last, sh[NT - 1]);
+        m1p_batch<NT>(acc, xa, wa, sh, real_last, cst_last);
+        m1p_load<NT>(xa, wa, col, wcol, p + 2 * B, N, real_last, sh[NT - 1]);      // (the last trip prefetches a clamped, unused batch)
+        m1p_batch<NT>(acc, xb, wb, sh, real_last, cst_last);
+        p += 2 * B;
     }
 }
 
 // wcol: the weight column (current buffer); x0 / x1: the parameter columns (x1 = the gather target, used when
-// scal[SC_RESAMPLE] != 0); shift_base[k * shift_stride] = parameter k of global particle 0
-template <int D>
-__global__ void __launch_bounds__(32 * M1P_G, 2)
-k_moments1p(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ wcol, int64_t N,
-            const double* __restrict__ scal, const double* __restrict__ shift_base, int64_t shift_stride,
-            double* __restrict__ partials, int P)
+// scal[SC_RESAMPLE] != 0); shift_base[k * shift_stride] = parameter k of global particle 0.  8 (NT - 1) <= d < 8 NT.
+// The warps of a block own adjacent sub-chunks and add their sums in the canonical tree order before they leave the
+// block: partials[q][block] is the tree node over M1P_WARPS M1P_SC = 1024 particles.
+template <int NT>
+__global__ void __launch_bounds__(32 * M1P_WARPS)
+k_moments_mma(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ wcol, int64_t N, int d,
+              const double* __restrict__ scal, const double* __restrict__ shift_base, int64_t shift_stride,
+              double* __restrict__ partials, int P)
 {
-    extern __shared__ __align__(16) double sm_m1[];      // [D + 1][M2_CH]: parameter columns, then the weight column
-    __shared__ double shift[D];
-    __shared__ __align__(8) uint64_t bars[2];
+    constexpr int NTILE = NT * (NT + 1) / 2;
+    constexpr int REDW = NTILE * 64 + 2;
+    __shared__ double red[M1P_WARPS * REDW];
     if (scal && scal[SC_STATUS] != 0.0) return;
     const double* __restrict__ X = (scal && scal[SC_RESAMPLE] != 0.0) ? x1 : x0;
-    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int64_t chunk = blockIdx.x;
-    const int64_t c0 = chunk * M2_CH;
-    constexpr int NT = 32 * M1P_G;
-    const bool bulk = (c0 + M2_CH <= N) && ((N & 1) == 0);     // 16-byte aligned column segments
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            mbar_init(bars, 1); mbar_init(bars + 1, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, k = lane & 3;
+    const int64_t c0 = ((int64_t)blockIdx.x * M1P_WARPS + warp) * M1P_SC;
+    double acc[NTILE][2];
+#pragma unroll
+    for (int e = 0; e < NTILE; ++e) { acc[e][0] = 0.0; acc[e][1] = 0.0; }
+    if (c0 < N) {
+        // this lane's variable in tile t: a parameter (load, subtract the shift), the constant 1, or zero padding
+        const double* col[NT];
+        double sh[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int var = 8 * t + g;
+            col[t] = X + col_off(N, var < d ? var : 0);
+            sh[t] = (var < d) ? shift_base[(size_t)var * shift_stride] : 0.0;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            constexpr unsigned HB = (M2_CH / 2) * sizeof(double);
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                mbar_expect_tx(bars + half, (unsigned)(D + 1) * HB);
-#pragma unroll 1
-                for (int k = 0; k <= D; ++k) {
-                    const double* col = (k < D) ? X + col_off(N, k) : wcol;
-                    bulk_g2s(sm_m1 + k * M2_CH + half * (M2_CH / 2), col + c0 + half * (M2_CH / 2), HB, bars + half);
-                }
-            }
-        }
-    } else {
-        for (int idx = threadIdx.x; idx < (D + 1) * M2_CH; idx += NT) {
-            const int k = idx / M2_CH, p = idx % M2_CH;
-            const int64_t i = c0 + p;
-            sm_m1[idx] = (i < N) ? ((k < D) ? X[col_off(N, k) + i] : wcol[i]) : 0.0;
-        }
+        const int var_last = 8 * (NT - 1) + g;
+        const bool real_last = var_last < d;
+        const double cst_last = (var_last == d) ? 1.0 : 0.0;
+        m1p_subchunk<NT>(acc, col, wcol, c0 + k, N, sh, real_last, cst_last);
     }
-    if (threadIdx.x < D) shift[threadIdx.x] = shift_base[(size_t)threadIdx.x * shift_stride];
-    __syncthreads();
-    double* red = sm_m1;                       // [NQ][33] per-lane sums, aliasing the staged columns once every warp is done
-    switch (g) {     // warp-uniform: each group is compiled with static row bounds (register-resident accumulators)
-    case 0: m1p_group<D, 0>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
-    case 1: m1p_group<D, 1>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
-    case 2: m1p_group<D, 2>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
-    default: m1p_group<D, 3>(sm_m1, N, c0, lane, shift, bars, bulk, red); break;
+    // C fragment: rows 8 ti + g, columns 8 tj + 2k, + 1  ->  red[warp][tile][row][column]
+#pragma unroll
+    for (int e = 0; e < NTILE; ++e) {
+        red[warp * REDW + e * 64 + g * 8 + 2 * k] = acc[e][0];
+        red[warp * REDW + e * 64 + g * 8 + 2 * k + 1] = acc[e][1];
     }
     __syncthreads();
-    // adjacent-pair tree over the 32 lanes of every quantity, one thread per quantity (registers)
-    constexpr int NQ = 1 + D + D * (D + 1) / 2;
-    for (int q = threadIdx.x; q < NQ; q += NT) {
-        double v[32];
-#pragma unroll
-        for (int l = 0; l < 32; ++l) v[l] = red[q * 33 + l];
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1)
-#pragma unroll
-            for (int l = 0; l < 32; l += 2 * sft) v[l] = v[l] + v[l + sft];
-        partials[(size_t)q * P + chunk] = v[0];
-    }
-}
-
-// any d <= DMAX (no shared-memory staging; warps over quantities); same order
-__global__ void __launch_bounds__(128)
-k_moments1p_generic(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ wcol, int64_t N, int d,
-                    const double* __restrict__ scal, const double* __restrict__ shift_base, int64_t shift_stride,
-                    double* __restrict__ partials, int P)
-{
-    if (scal && scal[SC_STATUS] != 0.0) return;
-    const double* __restrict__ X = (scal && scal[SC_RESAMPLE] != 0.0) ? x1 : x0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t chunk = blockIdx.x;
-    const int64_t c0 = chunk * M2_CH;
-    const int E = d * (d + 1) / 2, nq = 1 + d + E;
-    for (int q = warp; q < nq; q += 4) {
-        int a = 0, b = 0;
-        if (q > d) {
-            const int e = q - 1 - d;
-            while ((a + 1) * (a + 2) / 2 <= e) ++a;
-            b = e - a * (a + 1) / 2;
-        } else if (q >= 1) {
-            a = q - 1;
+    for (int idx = threadIdx.x; idx < NTILE * 64; idx += 32 * M1P_WARPS) {
+        const int e = idx >> 6, r = (idx >> 3) & 7, cc = idx & 7;
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        const int tj = e - ti * (ti + 1) / 2;
+        const int a = 8 * ti + r, b = 8 * tj + cc;
+        if (a <= d && b <= a) {
+            const int q = (a == d) ? ((b == d) ? 0 : 1 + b) : 1 + d + a * (a + 1) / 2 + b;
+            static_assert(M1P_WARPS == 4, "tree over the block's sub-chunks");
+            partials[(size_t)q * P + blockIdx.x] = (red[idx] + red[REDW + idx]) + (red[2 * REDW + idx] + red[3 * REDW + idx]);
         }
-        const double sa = shift_base[(size_t)a * shift_stride], sb = shift_base[(size_t)b * shift_stride];
-        const double* xa = X + col_off(N, a);
-        const double* xb = X + col_off(N, b);
-        double acc = 0.0;
-        for (int r = 0; r < M2_CH / 32; ++r) {
-            const int64_t i = c0 + (int64_t)r * 32 + lane;
-            if (i < N) {
-                if (q == 0) acc = acc + wcol[i];
-                else if (q <= d) acc = fma(wcol[i], xa[i] - sa, acc);
-                else acc = fma(wcol[i] * (xa[i] - sa), xb[i] - sb, acc);
-            }
-        }
-        acc = warp_tree(acc);
-        if (lane == 0) partials[(size_t)q * P + chunk] = acc;
     }
 }
 

@@ -50,6 +50,60 @@ __global__ void __launch_bounds__(128, 5) k_probe(double* out, int reps, const d
     out[(size_t)blockIdx.x * 128 + threadIdx.x] = acc;
 }
 
+// MODE 3: the same two mat-vecs as straight-line code in a real (non-inlined) function -- outside a loop ptxas rotates the
+// uniform registers of the LDCU.128 stream several loads ahead; vectors travel through shared memory
+__device__ __noinline__ void matvec_call(double* zs)
+{
+    double z[D], s[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { z[k] = zs[k * 128]; s[k] = zs[(D + k) * 128]; }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int e = half * E;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+#pragma unroll
+            for (int r = j; r < D; ++r) { s[r] = fma(c_L[e], z[j], s[r]); ++e; }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) z[k] = z[k] * 0.999 + 1e-9 * s[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) { zs[k * 128] = z[k]; zs[(D + k) * 128] = s[k]; }
+}
+__global__ void __launch_bounds__(128, 5) k_probe_call(double* out, int reps)
+{
+    extern __shared__ double sm[];
+    double* zs = sm + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { zs[k * 128] = 1.0 + 1e-3 * (threadIdx.x + k); zs[(D + k) * 128] = 0.0; }
+#pragma unroll 1
+    for (int it = 0; it < reps; ++it) matvec_call(zs);
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2 * D; ++k) acc += zs[k * 128];
+    out[(size_t)blockIdx.x * 128 + threadIdx.x] = acc;
+}
+double run_call(double* out, int blocks, int reps)
+{
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const int smem = 2 * D * 128 * sizeof(double);
+    cudaFuncSetAttribute(k_probe_call, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_probe_call<<<blocks, 128, smem>>>(out, 4);
+    float best = 1e30f;
+    for (int t = 0; t < 5; ++t) {
+        cudaEventRecord(a);
+        k_probe_call<<<blocks, 128, smem>>>(out, reps);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    const double fma_count = (double)blocks * 128 * reps * 2.0 * (E + 2.0 * D);
+    return 2.0 * fma_count / (best * 1e-3) / 1e12;
+}
+
 template <int MODE>
 double run(double* out, const double* gL, int blocks, int reps)
 {
@@ -86,6 +140,7 @@ int main()
     printf("reg  operands: %.2f TFLOP/s\n", run<0>(out, gL, blocks, reps));
     printf("ldcu operands: %.2f TFLOP/s\n", run<1>(out, gL, blocks, reps));
     printf("lds  operands: %.2f TFLOP/s\n", run<2>(out, gL, blocks, reps));
+    printf("ldcu operands, mat-vecs in a called function (rotating uniform registers): %.2f TFLOP/s\n", run_call(out, blocks, reps));
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
