@@ -99,6 +99,7 @@ struct MutArgs {
     int n_mh_steps, n_blocks, n_free;
     uint64_t seed;
     uint32_t stage;
+    uint32_t rk[20];           // Philox round keys of `seed` (k0 + r W0, k1 + r W1): the kernel xors them in as constant-bank operands
     // fused stage: device-side inputs (all nullable)
     const double* scal;        // SC_* scalars: phi_n = scal[SC_PHI_N], the kernel returns at once when scal[SC_STATUS] != 0,
                                // rows are read from `alt_in` when scal[SC_RESAMPLE] != 0 (the stage resampled into it)

@@ -80,13 +80,14 @@ SMC_HD double dnan()
 // form; scale by 2^k with at most one rounding.
 SMC_HD double det_exp(double x)
 {
-    if (x != x) return x;
-    if (x > 709.782712893384) return dinf();
-    if (x < -745.1332191019412) return 0.0;
-    const double t = fma(x, DMC(0), DMC(1));
+    // straight-line code (selects instead of early returns: independent calls interleave on the device); every finite x
+    // inside the range takes exactly the operations of the textbook form, p * 1.0 included
+    const bool over = x > 709.782712893384, under = x < -745.1332191019412;
+    const double xc = (over || under || x != x) ? 0.0 : x;
+    const double t = fma(xc, DMC(0), DMC(1));
     const double kd = t - DMC(1);
     int k = (int)kd;
-    double r = fma(-kd, DMC(2), x);
+    double r = fma(-kd, DMC(2), xc);
     r = fma(-kd, DMC(3), r);
     double p = DMC(4);
     p = fma(p, r, DMC(5));
@@ -102,9 +103,13 @@ SMC_HD double det_exp(double x)
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    if (k > 1023) { p *= 0x1p1023; k -= 1023; }
-    if (k < -1021) { p *= 0x1p-1000; k += 1000; }
-    return p * bits_to_double((uint64_t)(k + 1023) << 52);
+    const bool big = k > 1023, small = k < -1021;
+    p = p * (big ? 0x1p1023 : (small ? 0x1p-1000 : 1.0));
+    k = k - (big ? 1023 : (small ? -1000 : 0));
+    double res = p * bits_to_double((uint64_t)(k + 1023) << 52);
+    res = over ? dinf() : res;
+    res = under ? 0.0 : res;
+    return (x != x) ? x : res;
 }
 
 // log(x): fdlibm-style reduction x = 2^k (1+f), s = f/(2+f), degree-14 odd series in s.
@@ -193,6 +198,35 @@ SMC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return c;
+}
+
+// the same ten rounds with the key schedule precomputed (rk[2r] = k0 + r W0, rk[2r + 1] = k1 + r W1): bit-identical
+SMC_HD void philox_round_keys(uint64_t seed, uint32_t* rk)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+template <class KEYS>
+SMC_HD u32x4 philox4x32_10_keyed(u32x4 c, const KEYS& rk)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c.x, h0, l0);
+        mulhilo(0xCD9E8D57u, c.z, h1, l1);
+        u32x4 n;
+        n.x = h1 ^ c.y ^ rk[2 * r]; n.y = l1; n.z = h0 ^ c.w ^ rk[2 * r + 1]; n.w = l0;
+        c = n;
+    }
+    return c;
+}
+template <class KEYS>
+SMC_HD u32x4 rng4_keyed(const KEYS& rk, uint32_t particle, uint32_t stage, uint32_t slot, uint32_t purpose)
+{
+    u32x4 c; c.x = particle; c.y = stage; c.z = slot; c.w = purpose;
+    return philox4x32_10_keyed(c, rk);
 }
 
 enum : uint32_t { PURP_STEP = 1, PURP_NORMAL = 2, PURP_RESAMPLE = 3, PURP_BLOCKS = 4, PURP_INIT = 5 };

@@ -111,7 +111,7 @@ Tiles unit_tiles(int64_t n) { const int64_t u = (int64_t)M1P_SC * M1P_WARPS; int
 
 // trial phi per sweep of the adaptive solve: a sweep costs one grid barrier + K exp per particle, so small clouds take
 // wider sweeps (the result does not depend on K)
-int coop_k(int64_t n) { return (n >= ((int64_t)1 << 20)) ? 3 : 7; }
+int coop_k(int64_t n) { return (n >= ((int64_t)1 << 19)) ? 3 : 7; }     // per-sweep cost ~ 6 us + K x 3.4 us x n / 2^20 (B200): 27 sweeps of 3 beat 18 of 7 from 2^19 up
 // variant index: 0 = K 3, 1 = K 7, 2 = fixed schedule (no solve code)
 int coop_variant(int64_t n, bool adaptive) { return !adaptive ? 2 : (coop_k(n) == 3 ? 0 : 1); }
 const void* coop_kernel(int v) { return v == 0 ? (const void*)k_correct_coop<3> : v == 1 ? (const void*)k_correct_coop<7> : (const void*)k_correct_coop<0>; }

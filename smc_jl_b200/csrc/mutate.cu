@@ -8,6 +8,12 @@ void register_linreg_small(std::vector<KernelEntry>&);
 void register_linreg_mid(std::vector<KernelEntry>&);
 void register_linreg_20(std::vector<KernelEntry>&);
 void register_linreg_large(std::vector<KernelEntry>&);
+void register_linreg_fill_a(std::vector<KernelEntry>&);
+void register_linreg_fill_b(std::vector<KernelEntry>&);
+void register_linreg_fill_c(std::vector<KernelEntry>&);
+void register_linreg_fill_d(std::vector<KernelEntry>&);
+void register_linreg_fill_e(std::vector<KernelEntry>&);
+void register_linreg_fill_f(std::vector<KernelEntry>&);
 void register_equations(std::vector<KernelEntry>&);
 void register_dsge(std::vector<KernelEntry>&);
 
@@ -22,6 +28,12 @@ static const std::vector<KernelEntry>& table()
         register_linreg_small(v);
         register_linreg_mid(v);
         register_linreg_large(v);
+        register_linreg_fill_a(v);
+        register_linreg_fill_b(v);
+        register_linreg_fill_c(v);
+        register_linreg_fill_d(v);
+        register_linreg_fill_e(v);
+        register_linreg_fill_f(v);
 #endif
         return v;
     }();
@@ -96,6 +108,7 @@ int mutate_launch(Ctx* ctx, double phi_n, double alpha, int n_mh_steps, bool has
     MutArgs a;
     a.phi_n = phi_n; a.alpha = alpha; a.n_mh_steps = n_mh_steps; a.n_blocks = ctx->mutc_host->n_blocks; a.n_free = ctx->n_free;
     a.seed = seed; a.stage = stage;
+    philox_round_keys(seed, a.rk);
     a.scal = fused ? ctx->scal : nullptr;
     a.alt_in = ctx->cloud[ctx->cur ^ 1];
     a.work_counter = ctx->counters + 7; a.acc_total = ctx->acc_total; a.acc_counter = ctx->counters + 5;

@@ -220,14 +220,16 @@ struct ChainScal { double like, lpri, lprev; int accepted; };
 #define SMC_STEP_ATTR __forceinline__
 #endif
 template <class LIK, bool HAS_OLD, int BLK, bool MIX>
-__device__ SMC_STEP_ATTR ChainScal mh_step(const double* cur, double* cand, const float4* NTAB, uint64_t seed, uint32_t gp, uint32_t stage,
-                                           uint32_t sb, int b, double phi, double omphi, double alpha, ChainScal ch)
+__device__ SMC_STEP_ATTR ChainScal mh_step(const double* cur, double* cand, const float4* NTAB, const MutArgs& a, uint32_t gp,
+                                           uint32_t sb, int b, double phi, double omphi, ChainScal ch)
 {
+    const uint32_t stage = a.stage;
+    const double alpha = a.alpha;
     constexpr int D = LIK::D;
     constexpr uint32_t FULL_MASK = (D >= 32) ? 0xffffffffu : ((1u << D) - 1u);
     const uint32_t mask = (BLK == 2) ? FULL_MASK : c_mut.mask[b];
     // one Philox block per (step, block): MH uniform (mutation.jl:66,133) and the mixture component
-    const u32x4 r4 = rng4(seed, gp, stage, sb, PURP_STEP);
+    const u32x4 r4 = rng4_keyed(a.rk, gp, stage, sb, PURP_STEP);
     const double step_prob = u01(r4.x, r4.y);
     int comp = 1;
     if (MIX) {
@@ -249,7 +251,7 @@ __device__ SMC_STEP_ATTR ChainScal mh_step(const double* cur, double* cand, cons
 #pragma unroll
         for (int q = 0; q < NQUAD; ++q) {
             if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
-                const u32x4 r = rng4(seed, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL);
+                const u32x4 r = rng4_keyed(a.rk, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL);
                 rw[4 * q] = r.x; rw[4 * q + 1] = r.y; rw[4 * q + 2] = r.z; rw[4 * q + 3] = r.w;
             } else {
                 rw[4 * q] = 0u; rw[4 * q + 1] = 0u; rw[4 * q + 2] = 0u; rw[4 * q + 3] = 0u;
@@ -278,7 +280,7 @@ __device__ SMC_STEP_ATTR ChainScal mh_step(const double* cur, double* cand, cons
     for (int q = 0; q < NQUAD; ++q) {
         if (BLK == 2 || ((mask >> (4 * q)) & 15u)) {
             double z[4];
-            normal_quad(rng4(seed, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), NTAB, z[0], z[1], z[2], z[3]);
+            normal_quad(rng4_keyed(a.rk, gp, stage, (sb << 8) | (uint32_t)q, PURP_NORMAL), NTAB, z[0], z[1], z[2], z[3]);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * q + jj;
@@ -403,7 +405,7 @@ k_mutate(double* cloud, int64_t N, int64_t index0, MutArgs a)
                 const uint32_t sb = (uint32_t)(step * nb + b);
                 const double* cur = flipped ? buf1 : buf0;
                 double* cand = flipped ? buf0 : buf1;
-                ch = mh_step<LIK, HAS_OLD, BLK, MIX>(cur, cand, NTAB, a.seed, gp, a.stage, sb, b, phi, omphi, a.alpha, ch);
+                ch = mh_step<LIK, HAS_OLD, BLK, MIX>(cur, cand, NTAB, a, gp, sb, b, phi, omphi, ch);
                 if (ch.accepted) {
                     flipped = !flipped;
                     acc_cnt += c_mut.bsize[b];
@@ -608,6 +610,29 @@ static KernelEntry make_entry()
     return e;
 }
 #define LINREG(K) make_entry<GaussReg<1, K, K, 0, -1>>()
+
+// The regression sizes in between get the general kernel only (BLK = 0 handles any blocking, one block included): a third
+// of the code of a full entry, so that no K <= DMAX is refused.
+template <class LIK>
+static KernelEntry make_entry_lite()
+{
+    KernelEntry e;
+    e.kind = LIK::KIND;
+    e.neq = LIK::NEQ; e.k = LIK::K; e.stride = LIK::STRIDE; e.coef = LIK::COEF; e.sig = LIK::SIG; e.d = LIK::D;
+    e.minb = LIK::MINB;
+    for (int b = 0; b < 3; ++b) {
+        e.mut[0][b][0] = k_mutate<LIK, false, 0, false>;
+        e.mut[1][b][0] = k_mutate<LIK, true, 0, false>;
+        e.mut[0][b][1] = k_mutate<LIK, false, 0, true>;
+        e.mut[1][b][1] = k_mutate<LIK, true, 0, true>;
+    }
+    e.eval = k_evaluate<LIK>;
+    e.draw = k_initial_draw<LIK>;
+    e.upload_model = tu_upload_model;
+    e.upload_proposal = tu_upload_proposal;
+    return e;
+}
+#define LINREG_LITE(K) make_entry_lite<GaussReg<1, K, K, 0, -1>>()
 
 }  // namespace
 }  // namespace smc

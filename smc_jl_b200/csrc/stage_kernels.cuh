@@ -144,21 +144,16 @@ struct SweepSums {                 // S_k = sum x, Q_k = sum x^2 with x = w inc(
     {
 #pragma unroll
         for (int q = 0; q < 2 * K; ++q) v[q] = 0.0;
-        const int64_t base = tile * W_TILE + t;
+        // branch-free: elements past N were loaded as l = o = w = 0, i.e. x = 0 exp(0) = +0 and v + 0 = v exactly -- the
+        // W_R K exponentials of a thread are independent chains the scheduler can interleave
 #pragma unroll
         for (int r = 0; r < W_R; ++r) {
-            const int64_t i = base + (int64_t)r * W_LANES;
-            if (i < a.N) {
-                const double l = b[3 * r], o = b[3 * r + 1], wi = b[3 * r + 2];
+            const double l = b[3 * r], o = b[3 * r + 1], wi = b[3 * r + 2];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
-                    v[k] = v[k] + x;
-                    v[K + k] = v[K + k] + x * x;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < K; ++k) { v[k] = v[k] + 0.0; v[K + k] = v[K + k] + 0.0 * 0.0; }
+            for (int k = 0; k < K; ++k) {
+                const double x = wi * det_exp((phi_n1 - phi[k]) * o + (phi[k] - phi_n1) * l);
+                v[k] = v[k] + x;
+                v[K + k] = v[K + k] + x * x;
             }
         }
     }
@@ -584,7 +579,7 @@ k_moments_mma(const double* __restrict__ x0, const double* __restrict__ x1, cons
 // Same per-element arithmetic as build_mutconst() / cholesky_lower() (each L_ij is the same fma chain over k ascending).
 struct PrepSmem {
     double cov[DMAX][DMAX + 1], S[DMAX][DMAX + 1], L[DMAX][DMAX + 1];
-    double mean[DMAX], e[DMAX], logs[DMAX];
+    double mean[DMAX], e[DMAX], logs[DMAX], diag[DMAX];
     int bad;
 };
 __device__ __forceinline__ void prepare_proposal_block(PrepSmem& sm, const BlockSpec& bs, double c, MutConst* out, double* scal)
@@ -609,22 +604,23 @@ __device__ __forceinline__ void prepare_proposal_block(PrepSmem& sm, const Block
             sm.S[i][j] = (sm.cov[ai][aj] + sm.cov[aj][ai]) / 2.0;          // R_fr = (R + R') / 2, smc_main.jl:462
         }
         __syncthreads();
-        if (warp == 0) {
-            bool bad = false;
-            for (int j = 0; j < n; ++j) {
-                double sv = 0.0;
-                if (lane >= j && lane < n) {
-                    sv = sm.S[lane][j];
-                    for (int k = 0; k < j; ++k) sv = fma(-sm.L[lane][k], sm.L[j][k], sv);
-                }
-                const double sj = __shfl_sync(0xffffffffu, sv, j);
-                if (!(sj > 0.0)) { bad = true; break; }
-                const double dj = sqrt(sj);
-                if (lane == j) sm.L[j][j] = dj;
-                else if (lane > j && lane < n) sm.L[lane][j] = sv / dj;
-                __syncwarp();
+        // right-looking factorisation by the whole block: column j, then the rank-one update of the trailing block.  Every
+        // entry receives fma(-L_ik, L_jk, .) for k = 0, 1, ... in this order -- the chain of cholesky_lower(), bit for bit --
+        // but a column costs one sqrt, one division and two barriers instead of a warp-serial dot product.
+        if (tid < n) sm.diag[tid] = sm.S[tid][tid];
+        for (int j = 0; j < n; ++j) {
+            const double sjj = sm.S[j][j];
+            if (!(sjj > 0.0)) { if (tid == 0) sm.bad = 1; break; }          // block-uniform
+            const double dj = sqrt(sjj);
+            if (tid == 0) sm.L[j][j] = dj;
+            for (int i = j + 1 + tid; i < n; i += nt) sm.L[i][j] = sm.S[i][j] / dj;
+            __syncthreads();
+            const int m = n - j - 1;
+            for (int e = tid; e < m * m; e += nt) {
+                const int i = j + 1 + e / m, l = j + 1 + e % m;
+                if (l <= i) sm.S[i][l] = fma(-sm.L[i][j], sm.L[l][j], sm.S[i][l]);
             }
-            if (bad && lane == 0) sm.bad = 1;
+            __syncthreads();
         }
         __syncthreads();
         if (sm.bad) {
@@ -640,8 +636,8 @@ __device__ __forceinline__ void prepare_proposal_block(PrepSmem& sm, const Block
         }
         if (tid < n) {
             const int ai = bs.member[b][tid];
-            out->csd[b][ai] = c * sqrt(sm.S[tid][tid]);
-            const double isd = 1.0 / sqrt(sm.S[tid][tid]);
+            out->csd[b][ai] = c * sqrt(sm.diag[tid]);
+            const double isd = 1.0 / sqrt(sm.diag[tid]);
             out->isd[b][ai] = isd;
             out->isdn[b][ai] = isd * 0x1.9884533d43651p-2;
             out->rl[b][ai] = 1.0 / (c * sm.L[tid][tid]);

@@ -305,7 +305,7 @@ def W_reset(P):
     return Q
 
 
-@pytest.mark.parametrize("d,n_mh", [(20, 3), (2, 1), (8, 2)])
+@pytest.mark.parametrize("d,n_mh", [(20, 3), (2, 1), (8, 2), (7, 2), (11, 1), (31, 1)])      # 7, 11, 31: the general-kernel-only sizes
 def test_mutation_linear_gaussian_bitexact(eng, d, n_mh):
     params, lk, _ = W.linear_gaussian(d=d, T=64)
     spec = M.make_spec(params, lk)
@@ -509,7 +509,8 @@ def test_moments_onepass_bitexact(eng):
     """The fused stage's one-pass moments (shift = particle 0): bit-identical to the oracle's restatement of the same sums,
     equal to the reference's two-pass weighted_mean / weighted_cov (src/particle.jl:481-532) to rounding -- also for a cloud
     whose mean is 1e4 standard deviations away from the origin (where an unshifted one-pass formula would lose 8 digits)."""
-    for N, d, offset in ((5000, 9, 0.0), (4096, 20, 0.0), (70001, 2, 0.0), (3000, 5, 0.0), (12289, 7, 1e4), (6000, 20, -3e3)):
+    for N, d, offset in ((5000, 9, 0.0), (4096, 20, 0.0), (70001, 2, 0.0), (3000, 5, 0.0), (12289, 7, 1e4), (6000, 20, -3e3),
+                         (2500, 25, 0.0), (3001, 32, 0.0)):     # 25, 32: four and five variable tiles of the tensor-core SYRK
         rng = np.random.default_rng(N + d)
         P = rand_cloud(rng, N, d)
         P[:, :d] += offset
