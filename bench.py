@@ -252,6 +252,33 @@ class Workload:
         return float(res[-1].ess)
 
 
+def bind_near_gpu(local_rank):
+    """Pins this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned buffers of the history
+    stream are first-touched on the GPU's own NUMA node (8 ranks x 16 MB per stage otherwise cross the socket link).
+    Returns the previous affinity (restored before the CPU legs, which use every core) or None."""
+    if os.environ.get("SMCB200_NO_NUMA_BIND") or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = local_rank
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            idx = int(vis.split(",")[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus and cpus != old:
+            os.sched_setaffinity(0, cpus)
+            return old
+    except Exception:
+        pass
+    return None
+
+
 def make_engine(rank, world, local_rank, dist, torch):
     from smc_jl_b200.engine import Engine
     eng = Engine(local_rank)
@@ -442,6 +469,8 @@ def run_ours(args):
     # oracle's first-vintage run-up takes minutes at 2^20)
     n_check = n_global if wl.name in ("c2", "c4") else (1 << 16)
     match = None if args.no_match else ess_match(wl, rank, world, local_rank, dist, torch, n_check)
+    # (after the oracle leg: its OpenMP pool keeps the full CPU set)
+    old_affinity = bind_near_gpu(local_rank) if world > 1 else None
 
     eng = make_engine(rank, world, local_rank, dist, torch)
     eng.cloud_create(n_global, wl.d)
@@ -539,6 +568,8 @@ def run_ours(args):
     mut_bytes = 8.0 * (2 * wl.d + 7) * N
     achieved = mut_bytes / (mut_ms * 1e-3) / 1e9 if mut_ms > 0 else None
     out = None
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
     if rank == 0:
         cpu = None
         try:
@@ -556,7 +587,12 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
         traffic, traffic_src = ncu_traffic() if wl.name == "c2" else (None, "not captured for this config")
         d = wl.d
-        flops_step = 2.0 * (d * (d + 1)) + 2.0 * d * 5 + 60.0     # two triangular mat-vecs + prior / quadratic form / increments + exp
+        # flops per particle-MH-step of the mutation kernel.  C2: counted from the algorithm (two triangular mat-vecs + prior /
+        # quadratic form / increments + exp).  The other configs: FP64-pipe instructions per particle-step measured by ncu
+        # (profiles/r02_ncu_summary.json: fp64_pipe_pct x cycles x 592 sub-partitions / 2 / warp-steps = 771 for the 9-parameter
+        # three-block mixture kernel of C3 / C5, 64.2e3 for the 230-period Kalman filter of C4) x 1.75 flops per instruction
+        # (the fma share of the C2 kernel)
+        flops_step = {"c2": 2.0 * (d * (d + 1)) + 2.0 * d * 5 + 60.0, "c3": 1350.0, "c5": 1350.0, "c4": 112.0e3}[wl.name]
         steps_per_s_kernel = N * wl.steps_per_particle / (mut_ms * 1e-3) if mut_ms > 0 else 0.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k_done, "warmup": args.warmup,

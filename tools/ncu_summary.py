@@ -54,11 +54,30 @@ def f(row, key, default=0.0):
 
 
 def short_name(n):
-    n = n.replace("smc::<unnamed>::", "").replace("smc::", "").replace("(int)", "").replace("(bool)", "")
+    n = n.replace("smc::<unnamed>::", "").replace("smc::", "").replace("(int)", "").replace("(bool)", "").replace("unnamed>::", "")
     if n.startswith("void "):
         n = n[5:]
     cut = n.find("(")
     return n[:cut] if cut > 0 else n
+
+
+def json_summary(pairs, out_path):
+    """pairs: [(tag, report)]: per-kernel numbers of the LAST launch of every kernel in each report (the stage forced to
+    resample) -> {"kernels": {"<kernel>_<tag>": {...}}}; bench.py reads k_mutate_c2 for roofline.traffic."""
+    out = {"source": "ncu --set full --clock-control none, tools/profile_kernels.py, one launch per kernel", "kernels": {}}
+    for tag, rep in pairs:
+        for r in rows_of(rep):
+            name = short_name(r["Kernel Name"])
+            key = name.split("<")[0].replace("unnamed>::", "") + "_" + tag
+            out["kernels"][key] = {
+                "kernel": name, "time_us": f(r, "gpu__time_duration.sum"), "dram_bytes_read": f(r, "dram__bytes_read.sum"),
+                "dram_bytes_write": f(r, "dram__bytes_write.sum"), "registers": int(f(r, "launch__registers_per_thread")),
+                "warps_active_pct": f(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "issue_active_pct": f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct": f(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "warp_instructions": f(r, "smsp__inst_executed.sum"), "grid": int(f(r, "launch__grid_size")),
+                "block": int(f(r, "launch__block_size"))}
+    json.dump(out, open(out_path, "w"), indent=1)
 
 
 def main():
@@ -67,6 +86,9 @@ def main():
     alg = {}
     reports = []
     i = 0
+    if args and args[0] == "--json":          # --json out.json tag=report [tag=report ...]
+        json_summary([tuple(a.split("=", 1)) for a in args[2:]], args[1])
+        return
     while i < len(args):
         if args[i] == "--peak-gbs":
             peak = float(args[i + 1]); i += 2

@@ -8,6 +8,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > $out/${tag}_gpu_tests.log
 cat $out/${tag}_gpu_tests.log
 python bench.py > $out/${tag}_bench_c2.json 2> $out/${tag}_bench_c2.err
 for c in c3 c4 c5; do python bench.py --config $c --steps 30 > $out/${tag}_bench_$c.json 2> $out/${tag}_bench_$c.err; done
+python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-match > $out/${tag}_launches_bench.log 2>&1
 for c in c2 c3 c4; do
