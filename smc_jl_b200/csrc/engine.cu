@@ -166,7 +166,7 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
     a.c_in = L.c_in; a.accept_in = L.accept_in; a.ess_prev_in = L.ess_prev_in; a.phi_prop_in = L.phi_prop_in; a.j_in = L.j_in;
     a.resampled_last_in = L.resampled_last_in;
     a.partials = c->coop_partials; a.scal = c->scal; a.pc = peer_ctx(c);
-    a.gsum = c->coop_gsum; a.gflag = c->coop_gflag; a.gen = ++c->coop_gen;
+    a.ticket = c->coop_ticket; a.ll_step = c->coop_gflag;
     void* args[] = {&a};
     const int variant = coop_variant(c->N, L.adaptive != 0);
     SMC_CUDA(c, cudaLaunchCooperativeKernel(coop_kernel(variant), dim3(coop_grid(c, c->N, variant)), dim3(COOP_NT), args, 0, c->stream));
@@ -635,7 +635,9 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     }
     ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
     ok = ok && cudaMalloc(&c->coop_gsum, sizeof(double) * 2 * COOP_NQMAX) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->coop_gflag, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->coop_gflag, sizeof(unsigned long long)) == cudaSuccess;       // sequence number of the next cross-GPU reduction
+    ok = ok && cudaMalloc(&c->coop_ticket, sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMemset(c->coop_ticket, 0, sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMemset(c->coop_gflag, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->acc_total, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(c->acc_total, 0, sizeof(unsigned long long)) == cudaSuccess;
@@ -673,7 +675,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
-    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total); cudaFree(c->coop_gsum); cudaFree(c->coop_gflag);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total); cudaFree(c->coop_gsum); cudaFree(c->coop_gflag); cudaFree(c->coop_ticket);
     cudaFreeHost(c->h_summary);
     for (int i = 0; i < HIST_RING; ++i) {
         if (c->hist_ready[i]) cudaEventDestroy(c->hist_ready[i]);
@@ -810,7 +812,8 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
         SMC_CUDA(c, cudaMemcpy(c->peer_cnt, cnt.data(), sizeof(int64_t) * W, cudaMemcpyHostToDevice));
         // reduction mailboxes (allocated once per context, zeroed: epoch 0 = nothing published)
         if (!c->mbox) {
-            const size_t bytes = sizeof(double) * 2 * W * MB_NQ + sizeof(unsigned long long) * 2 * W;
+            const size_t bytes = sizeof(double) * 2 * W * MB_NQ + sizeof(unsigned long long) * 2 * W +
+                                 sizeof(unsigned long long) * LL_WORDS;      // value slots, flags, low-latency words
             SMC_CUDA(c, cudaMalloc(&c->mbox, bytes));
             SMC_CUDA(c, cudaMemset(c->mbox, 0, bytes));
             cudaIpcMemHandle_t mh, *mh_all_dev = nullptr, *mh_dev = nullptr;

@@ -143,6 +143,21 @@ __device__ __forceinline__ double tiles_tree_warp(const double* part, int P)
 // epoch-e flag, and a peer publishes e only after it has consumed e - 1, so two slots never collide.
 // A peer that never arrives (a crashed rank) trips a clock-based time-out instead of hanging the GPU.
 // =================================================================================================
+// Small exchanges (nq <= LL_NQ_B values, i.e. everything but the moment sums of wide models) use the low-latency form:
+// every double travels as two 8-byte words whose upper halves carry the exchange's epoch tag, so a word is either absent
+// or complete -- no system fence, no separate flag, one NVLink write latency per exchange.
+constexpr int LL_NQ_A = 32;                      // region A: the cooperative correction kernel's own sequence (stage_kernels.cuh)
+constexpr int LL_NQ_B = 256;                     // region B: exchanges numbered by pc.epoch
+__device__ __forceinline__ unsigned long long* ll_region_a(double* inbox, int world)
+{
+    return reinterpret_cast<unsigned long long*>(inbox) + (size_t)2 * world * MB_NQ + (size_t)2 * world;
+}
+__device__ __forceinline__ unsigned long long* ll_region_b(double* inbox, int world)
+{
+    return ll_region_a(inbox, world) + (size_t)2 * 16 * LL_NQ_A * 2;
+}
+constexpr size_t LL_WORDS = (size_t)2 * 16 * (LL_NQ_A + LL_NQ_B) * 2;
+
 // Called by ALL threads of ONE block (blockDim.x >= world).  local_src / dst: global or shared memory.
 __device__ __forceinline__ void peer_exchange_block(const PeerCtx& pc, const double* local_src, int nq, int combine, double* dst)
 {
@@ -153,6 +168,38 @@ __device__ __forceinline__ void peer_exchange_block(const PeerCtx& pc, const dou
     const unsigned long long epoch = s_epoch;
     const int rank = pc.rank, world = pc.world;
     const int par = (int)(epoch & 1ull);
+    if (nq <= LL_NQ_B) {
+        const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+        for (int e = threadIdx.x; e < world * nq; e += blockDim.x) {
+            const int r = e / nq, q = e % nq;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(local_src[q]);
+            volatile unsigned long long* w = ll_region_b(pc.inbox[r], world) + ((size_t)(par * 16 + rank) * LL_NQ_B + q) * 2;
+            w[0] = (bits & 0xffffffffull) | tag;
+            w[1] = (bits >> 32) | tag;
+        }
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            double v[16];
+            for (int r = 0; r < world; ++r) {
+                volatile unsigned long long* w = ll_region_b(pc.inbox[rank], world) + ((size_t)(par * 16 + r) * LL_NQ_B + q) * 2;
+                unsigned long long w0 = w[0], w1 = w[1];
+                const long long t0 = clock64();
+                while ((w0 & 0xffffffff00000000ull) != tag || (w1 & 0xffffffff00000000ull) != tag) {
+                    if (clock64() - t0 > 240000000000ll) { *pc.err = 1; break; }    // ~2 minutes: a peer died; the host reports it
+                    w0 = w[0]; w1 = w[1];
+                }
+                v[r] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            }
+            if (combine) {
+                for (int s = 1; s < world; s <<= 1)
+                    for (int i = 0; i + s < world; i += 2 * s) v[i] = v[i] + v[i + s];
+                dst[q] = v[0];
+            } else {
+                for (int r = 0; r < world; ++r) dst[(size_t)r * nq + q] = v[r];
+            }
+        }
+        __syncthreads();
+        return;
+    }
     const size_t flag_off = (size_t)2 * world * MB_NQ;               // flags follow the value slots (as doubles' worth of u64)
     for (int r = 0; r < world; ++r) {
         double* slot = pc.inbox[r] + ((size_t)par * world + rank) * MB_NQ;

@@ -115,9 +115,10 @@ struct CoopArgs {
     double* scal;
     // multi-GPU: block 0 crosses the GPUs and publishes the global sums to the other blocks of its grid
     PeerCtx pc;
-    double* gsum;                                     // [2][NQMAX]
-    unsigned long long* gflag;                        // monotone: (launch generation << 20) | reduction step
-    unsigned long long gen;
+    // Every reduction of every launch has a sequence number (ll_step, device resident, identical on all ranks); its
+    // parity selects the mailbox slot and its low 32 bits tag the words (the flag travels INSIDE each 8-byte word).
+    unsigned* ticket;                                 // block arrival counter (wraps to 0 after every reduction)
+    unsigned long long* ll_step;
 };
 constexpr int COOP_NT = 512;                         // threads per block: two 1024-element tiles in flight per block
 constexpr int COOP_GROUPS = COOP_NT / W_LANES;
@@ -214,7 +215,11 @@ struct CoopSmem {
     double warp[COOP_RMAX][COOP_GROUPS][COOP_NQMAX][8];     // per-tile warp sums
     double seg[COOP_NQMAX][COOP_NT / 32];        // per-warp segment roots of the tile tree
     double res[COOP_NQMAX], tmp[COOP_NQMAX];
+    double vals[16][COOP_NQMAX];                 // multi-GPU: every rank's shard roots
+    unsigned long long ll_base;                  // sequence number of this launch's first reduction
+    int last;
 };
+static_assert(COOP_NQMAX <= LL_NQ_A, "low-latency mailbox slot too small");
 
 // tile sums of NQ quantities in the canonical order (lane l of a tile adds its 4 elements, adjacent-pair tree over the
 // 256 lanes): each 256-thread group of the block takes one tile per round (tiles are dealt round-robin over the grid)
@@ -284,69 +289,105 @@ __device__ __forceinline__ double coop_slice(const double* q_part, int tid)
 // barrier.  The two partial regions alternate with `step`: a block can only run two reductions ahead of the slowest reader
 // after passing the barrier in between.  Multi-GPU: block 0 alone crosses the GPUs (NVLink mailboxes) and publishes the
 // global sums behind a flag.  Result: sm.res[0 .. NQ).
+// the canonical adjacent-pair tree over the P tile sums of NQ quantities by one block -> sm.tmp[0 .. NQ)
+template <int NQ>
+__device__ __forceinline__ void coop_tile_tree(const CoopArgs& a, CoopSmem& sm, const double* region)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P;
+    double x[NQ];                       // all loads first (independent L2 round trips), then the trees
+    if (P <= COOP_NT) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) x[q] = (tid < P) ? __ldcg(region + (size_t)q * P + tid) : 0.0;
+    } else if (P == 2 * COOP_NT) {
+        double v[NQ][2];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { v[q][0] = __ldcg(region + (size_t)q * P + 2 * tid); v[q][1] = __ldcg(region + (size_t)q * P + 2 * tid + 1); }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) x[q] = v[q][0] + v[q][1];
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double* qp = region + (size_t)q * P;
+            if (P == 4 * COOP_NT) x[q] = coop_slice<4>(qp, tid);
+            else if (P == 8 * COOP_NT) x[q] = coop_slice<8>(qp, tid);
+            else x[q] = tree_run(qp + (size_t)tid * (P / COOP_NT), P / COOP_NT);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const double r = warp_tree(x[q]);
+        if (lane == 0) sm.seg[q][warp] = r;
+    }
+    __syncthreads();
+    if (warp < NQ) {
+        double y = (lane < COOP_NT / 32) ? sm.seg[warp][lane] : 0.0;
+        y = warp_tree(y);
+        if (lane == 0) sm.tmp[warp] = y;
+    }
+    __syncthreads();
+}
+
+// One grid-wide reduction of NQ quantities.  The two partial regions alternate with `step`: a block can only run two
+// reductions ahead of the slowest reader.  Result: sm.res[0 .. NQ), the same bits in every block (and on every GPU).
+//   one GPU:  the blocks store their tile sums, ONE grid barrier (at most two blocks per SM take part, which keeps it
+//             short), then EVERY block finishes the adjacent-pair tile tree itself from L2 -- no second barrier.
+//   several:  no grid barrier at all.  The block that arrives last (atomic ticket) reduces the shard's tile sums and
+//             stores the shard roots straight into every rank's low-latency mailbox over NVLink: each double travels as
+//             two 8-byte words that carry the reduction's sequence tag in their upper halves, so a word is either absent
+//             or complete -- no fence, no separate flag, one NVLink write latency.  All blocks of all ranks then poll
+//             their own rank's mailbox and combine the world's roots in the fixed adjacent-pair order.
 template <int NQ, class F>
 __device__ __forceinline__ void coop_allreduce(const CoopArgs& a, cg::grid_group& grid, CoopSmem& sm, const F& f, int& step)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     double* region = a.partials + (size_t)(step & 1) * COOP_NQMAX * a.P;
     coop_tile_sums<NQ>(a, sm, f, region);
     __threadfence();
-    grid.sync();
-    if (a.pc.world == 1 || blockIdx.x == 0) {
-        const int P = a.P;
-        double x[NQ];                       // all loads first (independent L2 round trips), then the trees
-        if (P <= COOP_NT) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[q] = (tid < P) ? __ldcg(region + (size_t)q * P + tid) : 0.0;
-        } else if (P == 2 * COOP_NT) {
-            double v[NQ][2];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) { v[q][0] = __ldcg(region + (size_t)q * P + 2 * tid); v[q][1] = __ldcg(region + (size_t)q * P + 2 * tid + 1); }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[q] = v[q][0] + v[q][1];
-        } else {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double* qp = region + (size_t)q * P;
-                if (P == 4 * COOP_NT) x[q] = coop_slice<4>(qp, tid);
-                else if (P == 8 * COOP_NT) x[q] = coop_slice<8>(qp, tid);
-                else x[q] = tree_run(qp + (size_t)tid * (P / COOP_NT), P / COOP_NT);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const double r = warp_tree(x[q]);
-            if (lane == 0) sm.seg[q][warp] = r;
-        }
-        __syncthreads();
-        if (warp < NQ) {
-            double x = (lane < COOP_NT / 32) ? sm.seg[warp][lane] : 0.0;
-            x = warp_tree(x);
-            if (lane == 0) sm.tmp[warp] = x;
-        }
-        __syncthreads();
-    }
     if (a.pc.world == 1) {
+        grid.sync();
+        coop_tile_tree<NQ>(a, sm, region);
         if (tid < NQ) sm.res[tid] = sm.tmp[tid];
     } else {
-        double* g = a.gsum + (size_t)(step & 1) * COOP_NQMAX;
-        const unsigned long long want = (a.gen << 20) | (unsigned long long)(step + 1);
-        if (blockIdx.x == 0) {
-            peer_exchange_block(a.pc, sm.tmp, NQ, 1, sm.res);
-            if (tid < NQ) __stcg(g + tid, sm.res[tid]);
+        const int world = a.pc.world, rank = a.pc.rank;
+        const unsigned long long seq = sm.ll_base + (unsigned long long)step;
+        const int par = (int)(seq & 1ull);
+        const unsigned long long tag = ((seq + 1ull) & 0xffffffffull) << 32;
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicInc(a.ticket, gridDim.x - 1);
+            sm.last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (sm.last) {                                   // block-uniform
             __threadfence();
-            __syncthreads();
-            if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(a.gflag) = want;
-        } else {
-            if (tid == 0) {
-                const long long t0 = clock64();
-                while (*reinterpret_cast<volatile unsigned long long*>(a.gflag) < want) {
-                    if (clock64() - t0 > 400000000000ll) { *a.pc.err = 1; break; }      // block 0 is stuck behind a dead peer
-                }
-                __threadfence();
+            coop_tile_tree<NQ>(a, sm, region);
+            for (int e = tid; e < world * NQ; e += COOP_NT) {
+                const int r = e / NQ, q = e % NQ;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(sm.tmp[q]);
+                volatile unsigned long long* dst = ll_region_a(a.pc.inbox[r], world) + ((size_t)(par * 16 + rank) * LL_NQ_A + q) * 2;
+                dst[0] = (bits & 0xffffffffull) | tag;
+                dst[1] = (bits >> 32) | tag;
             }
-            __syncthreads();
-            if (tid < NQ) sm.res[tid] = __ldcg(g + tid);
+        }
+        if (tid < world * NQ) {
+            const int r = tid / NQ, q = tid % NQ;
+            volatile unsigned long long* src = ll_region_a(a.pc.inbox[rank], world) + ((size_t)(par * 16 + r) * LL_NQ_A + q) * 2;
+            unsigned long long w0 = src[0], w1 = src[1];
+            const long long t0 = clock64();
+            while ((w0 & 0xffffffff00000000ull) != tag || (w1 & 0xffffffff00000000ull) != tag) {
+                if (clock64() - t0 > 240000000000ll) { *a.pc.err = 1; break; }      // ~2 minutes: a rank died; the host reports it
+                w0 = src[0]; w1 = src[1];
+            }
+            sm.vals[r][q] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        }
+        __syncthreads();
+        if (tid < NQ) {
+            double v[16];
+            for (int r = 0; r < world; ++r) v[r] = sm.vals[r][tid];
+            for (int sft = 1; sft < world; sft <<= 1)
+                for (int i = 0; i + sft < world; i += 2 * sft) v[i] = v[i] + v[i + sft];
+            sm.res[tid] = v[0];
         }
     }
     __syncthreads();
@@ -395,6 +436,10 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
     double phi_n = a.corr.phi_n;
     const double phi_n1 = a.corr.phi_n1;
     int step = 0;
+    if (a.pc.world > 1) {
+        if (tid == 0) sm.ll_base = *reinterpret_cast<volatile unsigned long long*>(a.ll_step);
+        __syncthreads();
+    }
 
     if (lead) {
         if (!a.use_carry) { scal[SC_C] = a.c_in; scal[SC_ACCEPT] = a.accept_in; scal[SC_STATUS] = 0.0; }
@@ -411,7 +456,10 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
         }
     }
     if (lead) { scal[SC_PHI_N] = phi_n; scal[SC_PHI_N1] = phi_n1; }
-    if (a.solve_only) return;
+    if (a.solve_only) {
+        if (lead && a.pc.world > 1) *a.ll_step = sm.ll_base + (unsigned long long)step;     // every block read the base before its first reduction
+        return;
+    }
 
     // ---- pass A: incremental weights, unnormalised weights, S ------------------------------------------
     {
@@ -432,6 +480,7 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
             const bool nan = (ess != ess);                                  // check_nan_ess, helpers.jl:270-305
             if (nan) scal[SC_STATUS] = (double)SMCB200_ERR_NAN_ESS;
             scal[SC_RESAMPLE] = (!nan && scal[SC_STATUS] == 0.0 && ess < a.threshold_ratio * n) ? 1.0 : 0.0;   // smc_main.jl:435
+            if (a.pc.world > 1) *a.ll_step = sm.ll_base + (unsigned long long)step;
         }
     }
 }
