@@ -164,6 +164,7 @@ struct Ctx {
     double* coop_partials = nullptr; size_t coop_partials_len = 0;
     double* coop_gsum = nullptr; unsigned long long* coop_gflag = nullptr; unsigned long long coop_gen = 0;
     unsigned* coop_ticket = nullptr;
+    int coop_ll_single = 0;
     double* h_summary = nullptr;   // pinned ring of stage summaries [SUMMARY_RING][SC_COUNT]
     double* rmax = nullptr;        // N   running max of the cumsum
     int64_t* idx = nullptr;        // N

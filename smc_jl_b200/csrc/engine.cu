@@ -167,6 +167,7 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
     a.resampled_last_in = L.resampled_last_in;
     a.partials = c->coop_partials; a.scal = c->scal; a.pc = peer_ctx(c);
     a.ticket = c->coop_ticket; a.ll_step = c->coop_gflag;
+    a.ll_always = c->coop_ll_single;
     void* args[] = {&a};
     const int variant = coop_variant(c->N, L.adaptive != 0);
     SMC_CUDA(c, cudaLaunchCooperativeKernel(coop_kernel(variant), dim3(coop_grid(c, c->N, variant)), dim3(COOP_NT), args, 0, c->stream));
@@ -636,6 +637,9 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
     ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
     ok = ok && cudaMalloc(&c->coop_gsum, sizeof(double) * 2 * COOP_NQMAX) == cudaSuccess;
     ok = ok && cudaMalloc(&c->coop_gflag, sizeof(unsigned long long)) == cudaSuccess;       // sequence number of the next cross-GPU reduction
+    // developer switch.  One GPU, measured: the grid-barrier reduction (every block finishes the tile tree itself) beats the
+    // mailbox form (last block reduces, all poll) -- adaptive solve 0.399 vs 0.422 ms at N = 2^20 -- so it stays the default
+    c->coop_ll_single = std::getenv("SMCB200_COOP_MAILBOX") ? 1 : 0;
     ok = ok && cudaMalloc(&c->coop_ticket, sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMemset(c->coop_ticket, 0, sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMemset(c->coop_gflag, 0, sizeof(unsigned long long)) == cudaSuccess;
@@ -772,6 +776,14 @@ int32_t smcb200_cloud_create(smcb200_ctx* c, int64_t n_parts, int32_t n_para)
     SMC_CUDA(c, cudaMalloc(&c->coop_partials, sizeof(double) * c->coop_partials_len));
     SMC_CUDA(c, cudaMemset(c->coop_partials, 0, sizeof(double) * c->coop_partials_len));
     c->cur = 0;
+    if (c->world == 1 && !c->mbox) {
+        // one GPU: the cooperative correction kernel still reduces through the low-latency mailbox (its own)
+        const size_t bytes = sizeof(double) * 2 * MB_NQ + sizeof(unsigned long long) * 2 + sizeof(unsigned long long) * LL_WORDS;
+        SMC_CUDA(c, cudaMalloc(&c->mbox, bytes));
+        SMC_CUDA(c, cudaMemset(c->mbox, 0, bytes));
+        SMC_CUDA(c, cudaMalloc(&c->mbox_tab, sizeof(double*)));
+        SMC_CUDA(c, cudaMemcpy(c->mbox_tab, &c->mbox, sizeof(double*), cudaMemcpyHostToDevice));
+    }
     if (c->world > 1) {
         // peers' cloud buffers and running-max columns: exchange CUDA-IPC handles + shard sizes through the communicator
         NcclApi* nc = nccl_api();

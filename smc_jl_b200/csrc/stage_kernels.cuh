@@ -118,6 +118,7 @@ struct CoopArgs {
     // Every reduction of every launch has a sequence number (ll_step, device resident, identical on all ranks); its
     // parity selects the mailbox slot and its low 32 bits tag the words (the flag travels INSIDE each 8-byte word).
     unsigned* ticket;                                 // block arrival counter (wraps to 0 after every reduction)
+    int ll_always;                                    // one GPU: reduce through the (local) mailbox as well instead of a grid barrier
     unsigned long long* ll_step;
 };
 constexpr int COOP_NT = 512;                         // threads per block: two 1024-element tiles in flight per block
@@ -344,7 +345,7 @@ __device__ __forceinline__ void coop_allreduce(const CoopArgs& a, cg::grid_group
     double* region = a.partials + (size_t)(step & 1) * COOP_NQMAX * a.P;
     coop_tile_sums<NQ>(a, sm, f, region);
     __threadfence();
-    if (a.pc.world == 1) {
+    if (a.pc.world == 1 && !a.ll_always) {
         grid.sync();
         coop_tile_tree<NQ>(a, sm, region);
         if (tid < NQ) sm.res[tid] = sm.tmp[tid];
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
     double phi_n = a.corr.phi_n;
     const double phi_n1 = a.corr.phi_n1;
     int step = 0;
-    if (a.pc.world > 1) {
+    if (a.pc.world > 1 || a.ll_always) {
         if (tid == 0) sm.ll_base = *reinterpret_cast<volatile unsigned long long*>(a.ll_step);
         __syncthreads();
     }
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
     }
     if (lead) { scal[SC_PHI_N] = phi_n; scal[SC_PHI_N1] = phi_n1; }
     if (a.solve_only) {
-        if (lead && a.pc.world > 1) *a.ll_step = sm.ll_base + (unsigned long long)step;     // every block read the base before its first reduction
+        if (lead && (a.pc.world > 1 || a.ll_always)) *a.ll_step = sm.ll_base + (unsigned long long)step;     // every block read the base before its first reduction
         return;
     }
 
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(COOP_NT, (K == 0) ? 2 : SMC_COOP_MINB_ADAPTIVE
             const bool nan = (ess != ess);                                  // check_nan_ess, helpers.jl:270-305
             if (nan) scal[SC_STATUS] = (double)SMCB200_ERR_NAN_ESS;
             scal[SC_RESAMPLE] = (!nan && scal[SC_STATUS] == 0.0 && ess < a.threshold_ratio * n) ? 1.0 : 0.0;   // smc_main.jl:435
-            if (a.pc.world > 1) *a.ll_step = sm.ll_base + (unsigned long long)step;
+            if (a.pc.world > 1 || a.ll_always) *a.ll_step = sm.ll_base + (unsigned long long)step;
         }
     }
 }
