@@ -70,10 +70,24 @@ static_assert(SL_ESS + 2 * ESS_K <= SL_COUNT, "scal_loc too small");
 inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
 // cross-rank tree of nq shard-local roots (combine) or their [world][nq] layout (gather into dst): one
 // k_peer_exchange launch over the NVLink mailboxes; `flag` (device, nullable) predicates the launch
+// Launch with the programmatic-serialization attribute: the kernel (which starts with pdl_wait()) may be scheduled while
+// its predecessor in the stream drains, which hides the launch latency of the stage's chain of small dependent kernels.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int peer_exchange(Ctx* c, double* dst, const double* local_src, int nq, int combine, const double* flag = nullptr)
 {
     if (nq > MB_NQ) { c->err = "peer_exchange: too many quantities"; return SMCB200_ERR_UNSUPPORTED; }
-    k_peer_exchange<<<1, 256, 0, c->stream>>>(local_src, nq, peer_ctx(c), combine, dst, flag);
+    SMC_CUDA(c, launch_pdl(k_peer_exchange, dim3(1), dim3(256), 0, c->stream, local_src, nq, peer_ctx(c), combine, dst, flag));
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
@@ -254,16 +268,21 @@ int launch_resample_indices(Ctx* c, const double* src, int div_n, int64_t n, int
         k_colsum<<<t.ntiles, 256, 0, c->stream>>>(src, n, nd, div_n, partials, t.ntiles, t.P, counter, sres, flag);
         c->launches += 1;
     }
-    k_scan<false><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, c->scan_blocktot, nullptr,
-                                                              nullptr, nullptr, nullptr, flag);
-    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, g.nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT, flag);
-    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, g.nb, nullptr, 1, 0, c->scan_blockoff, flag);
-    k_scan<true><<<g.nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, div_n, nd, sres, n, g.B, nullptr, c->scan_blockoff, rmax,
-                                                             craw, c->scan_bmax, flag);
-    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, g.nb, flag);
+    const double* nul = nullptr;
+    double* nulw = nullptr;
+    const double* const* nultab = nullptr;
+    SMC_CUDA(c, launch_pdl(k_scan<false>, dim3(g.nb), dim3(SCAN_THREADS), SCAN_SMEM, c->stream, src, div_n, nd, (const double*)sres, n, g.B,
+                           c->scan_blocktot, nul, nulw, nulw, nulw, flag));
+    SMC_CUDA(c, launch_pdl(k_scan_upper_up, dim3(1), dim3(256), 0, c->stream, (const double*)c->scan_blocktot, g.nb, c->scan_levels,
+                           c->scal_loc + SL_SCAN_ROOT, flag));
+    SMC_CUDA(c, launch_pdl(k_scan_upper_down, dim3(1), dim3(256), 0, c->stream, (const double*)c->scan_levels, g.nb, nul, 1, 0,
+                           c->scan_blockoff, flag));
+    SMC_CUDA(c, launch_pdl(k_scan<true>, dim3(g.nb), dim3(SCAN_THREADS), SCAN_SMEM, c->stream, src, div_n, nd, (const double*)sres, n, g.B,
+                           nulw, (const double*)c->scan_blockoff, rmax, craw, c->scan_bmax, flag));
+    SMC_CUDA(c, launch_pdl(k_prefix_max, dim3(1), dim3(256), 0, c->stream, c->scan_bmax, g.nb, flag));
     const double u = systematic_offset(seed, stage, u_override);
-    k_search<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(rmax, nullptr, 0, c->scan_bmax, g.nb, g.B, n, n_out, 0, method, seed,
-                                                                     stage, u, (double)n_out, idx, flag);
+    SMC_CUDA(c, launch_pdl(k_search, dim3((unsigned)((n_out + 255) / 256)), dim3(256), 0, c->stream, (const double*)rmax, nultab, 0,
+                           (const double*)c->scan_bmax, g.nb, g.B, n, n_out, (int64_t)0, method, seed, stage, u, (double)n_out, idx, flag));
     c->launches += 6;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;
@@ -294,25 +313,28 @@ int launch_resample_cloud_sharded(Ctx* c, int method, uint64_t seed, uint32_t st
         c->launches += 1;
         st = reduce_ranks(c, c->scal + SC_SRES, c->scal_loc + SC_SRES, 1); if (st) return st;
     }
-    k_scan<false><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, c->scan_blocktot, nullptr,
-                                                            nullptr, nullptr, nullptr, flag);
-    k_scan_upper_up<<<1, 256, 0, c->stream>>>(c->scan_blocktot, nb, c->scan_levels, c->scal_loc + SL_SCAN_ROOT, flag);
+    const double* nul = nullptr;
+    double* nulw = nullptr;
+    SMC_CUDA(c, launch_pdl(k_scan<false>, dim3(nb), dim3(SCAN_THREADS), SCAN_SMEM, c->stream, src, 1, nd, (const double*)(c->scal + SC_SRES), c->N, B,
+                           c->scan_blocktot, nul, nulw, nulw, nulw, flag));
+    SMC_CUDA(c, launch_pdl(k_scan_upper_up, dim3(1), dim3(256), 0, c->stream, (const double*)c->scan_blocktot, nb, c->scan_levels,
+                           c->scal_loc + SL_SCAN_ROOT, flag));
     st = peer_exchange(c, c->gath, c->scal_loc + SL_SCAN_ROOT, 1, 0, flag); if (st) return st;
-    k_scan_upper_down<<<1, 256, 0, c->stream>>>(c->scan_levels, nb, c->gath, c->world, c->rank, c->scan_blockoff, flag);
-    k_scan<true><<<nb, SCAN_THREADS, SCAN_SMEM, c->stream>>>(src, 1, nd, c->scal + SC_SRES, c->N, B, nullptr, c->scan_blockoff,
-                                                           c->rmax, nullptr, c->scan_bmax, flag);
-    k_prefix_max<<<1, 256, 0, c->stream>>>(c->scan_bmax, nb, flag);
+    SMC_CUDA(c, launch_pdl(k_scan_upper_down, dim3(1), dim3(256), 0, c->stream, (const double*)c->scan_levels, nb, (const double*)c->gath, c->world,
+                           c->rank, c->scan_blockoff, flag));
+    SMC_CUDA(c, launch_pdl(k_scan<true>, dim3(nb), dim3(SCAN_THREADS), SCAN_SMEM, c->stream, src, 1, nd, (const double*)(c->scal + SC_SRES), c->N, B,
+                           nulw, (const double*)c->scan_blockoff, c->rmax, nulw, c->scan_bmax, flag));
+    SMC_CUDA(c, launch_pdl(k_prefix_max, dim3(1), dim3(256), 0, c->stream, c->scan_bmax, nb, flag));
     // block maxima of every shard -> [world][nb]; the maxima of the lower ranks are folded in afterwards
     st = peer_exchange(c, c->bmax_g, c->scan_bmax, nb, 0, flag); if (st) return st;
-    k_fix_rank_carry<<<1, 256, 0, c->stream>>>(c->bmax_g, nb, c->world, flag);
+    SMC_CUDA(c, launch_pdl(k_fix_rank_carry, dim3(1), dim3(256), 0, c->stream, c->bmax_g, nb, c->world, flag));
     const double u = systematic_offset(seed, stage, u_override);
-    k_search<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(nullptr, c->rmax_tab, nb, c->bmax_g, nb * c->world, B, c->N_global, c->N,
-                                                                    c->index0, method, seed, stage, u, nd, c->idx, flag);
+    SMC_CUDA(c, launch_pdl(k_search, dim3((unsigned)((c->N + 255) / 256)), dim3(256), 0, c->stream, nul, (const double* const*)c->rmax_tab, nb,
+                           (const double*)c->bmax_g, nb * c->world, B, c->N_global, c->N, c->index0, method, seed, stage, u, nd, c->idx, flag));
     double* dst = c->cloud[c->cur ^ 1];
-    k_gather_peer<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(c->peer_tab + (size_t)c->cur * c->world, c->peer_cnt, c->per, dst,
-                                                                         c->idx, c->N, d + 4,
-                                                                         fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4),
-                                                                         nw_hist, flag);
+    SMC_CUDA(c, launch_pdl(k_gather_peer, dim3((unsigned)((c->N + 255) / 256)), dim3(256), 0, c->stream,
+                           (double* const*)(c->peer_tab + (size_t)c->cur * c->world), (const int64_t*)c->peer_cnt, c->per, dst, (const int64_t*)c->idx,
+                           c->N, d + 4, fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4), nw_hist, flag));
     c->launches += 8;
     SMC_CUDA(c, cudaGetLastError());
     if (!fused) c->cur ^= 1;
@@ -333,9 +355,8 @@ int launch_resample_cloud(Ctx* c, int method, uint64_t seed, uint32_t stage, dou
     int st = launch_resample_indices(c, cl + col_off(c->N, d + 4), 1, c->N, method, seed, stage, u_override, c->rmax, nullptr,
                                      c->idx, c->partials + (size_t)3 * t.P, c->counters + 2, c->scal + SC_SRES, fused, flag);
     if (st) return st;
-    k_gather<<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(cl, dst, c->idx, c->N, d + 4,
-                                                                    fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4),
-                                                                    nw_hist, flag);
+    SMC_CUDA(c, launch_pdl(k_gather, dim3((unsigned)((c->N + 255) / 256)), dim3(256), 0, c->stream, (const double*)cl, dst,
+                           (const int64_t*)c->idx, c->N, d + 4, fused ? cl + col_off(c->N, d + 4) : dst + col_off(c->N, d + 4), nw_hist, flag));
     c->launches += 1;
     SMC_CUDA(c, cudaGetLastError());
     if (!fused) c->cur ^= 1;
@@ -391,7 +412,8 @@ int launch_moments(Ctx* c)
 template <int NT>
 int launch_mma(Ctx* c, unsigned grid, const double* x0, const double* x1, const double* wcol, const double* shift, int64_t stride, int P)
 {
-    k_moments_mma<NT><<<grid, 32 * M1P_WARPS, 0, c->stream>>>(x0, x1, wcol, c->N, c->d, c->scal, shift, stride, c->m1p_partials, P);
+    SMC_CUDA(c, launch_pdl(k_moments_mma<NT>, dim3(grid), dim3(32 * M1P_WARPS), 0, c->stream, x0, x1, wcol, c->N, c->d, (const double*)c->scal,
+                           shift, stride, c->m1p_partials, P));
     return SMCB200_OK;
 }
 
@@ -417,8 +439,8 @@ int launch_moments_prepare(Ctx* c, const BlockSpec& bs, double target)
     default: return fail(c, SMCB200_ERR_UNSUPPORTED, "one-pass moments support n_para <= 39");
     }
     if (st) return st;
-    k_moments_finish<<<nq, 256, 0, c->stream>>>(c->m1p_partials, t.P, nq, c->m1p_sums, c->m1p_sums + (1 + DMAX + PACKMAX), c->counters + 6,
-                                                peer_ctx(c), shift, stride, bs, target, c->scal, c->mutc_dev);
+    SMC_CUDA(c, launch_pdl(k_moments_finish, dim3(nq), dim3(256), 0, c->stream, (const double*)c->m1p_partials, t.P, nq, c->m1p_sums,
+                           c->m1p_sums + (1 + DMAX + PACKMAX), c->counters + 6, peer_ctx(c), shift, stride, bs, target, c->scal, c->mutc_dev));
     c->launches += 2;
     SMC_CUDA(c, cudaGetLastError());
     return SMCB200_OK;

@@ -20,6 +20,8 @@ namespace smc {
 __global__ void __launch_bounds__(256)
 k_peer_exchange(const double* __restrict__ local_src, int nq, PeerCtx pc, int combine, double* __restrict__ dst, const double* flag)
 {
+    pdl_wait();
+    pdl_trigger();
     if (flag && *flag == 0.0) return;
     peer_exchange_block(pc, local_src, nq, combine, dst);
 }
@@ -124,6 +126,8 @@ k_scan(const double* __restrict__ src, int div_n, double n_parts, const double* 
        double* __restrict__ blocktot, const double* __restrict__ blockoff, double* __restrict__ rmax,
        double* __restrict__ craw, double* __restrict__ bmax, const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double sm_dyn[];
     if (flag && *flag == 0.0) return;
     double* tile = sm_dyn;                               // [nleaf][LEAF + 1]
@@ -215,6 +219,8 @@ __global__ void __launch_bounds__(256)
 k_scan_upper_up(const double* __restrict__ blocktot, int nb, double* __restrict__ lv, double* __restrict__ root_out,
                 const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     if (flag && *flag == 0.0) return;
     int nlev = 0;
     while ((1 << nlev) < nb) ++nlev;
@@ -232,6 +238,8 @@ __global__ void __launch_bounds__(256)
 k_scan_upper_down(const double* __restrict__ lv, int nb, const double* __restrict__ rank_roots, int world, int rank,
                   double* __restrict__ blockoff, const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double off0;
     if (flag && *flag == 0.0) return;
     if (threadIdx.x == 0) {
@@ -269,6 +277,8 @@ k_scan_upper_down(const double* __restrict__ lv, int nb, const double* __restric
 __global__ void __launch_bounds__(256) k_fix_rank_carry(double* __restrict__ bmax, int nb, int world, const double* flag = nullptr)
 {
     __shared__ double carry[16];
+    pdl_wait();
+    pdl_trigger();
     if (flag && *flag == 0.0) return;
     if ((int)threadIdx.x < world) {
         double cmax = -dinf();
@@ -282,6 +292,8 @@ __global__ void __launch_bounds__(256) k_fix_rank_carry(double* __restrict__ bma
 // inclusive prefix max of the block maxima (one block of 256 threads; max is exact in any order)
 __global__ void __launch_bounds__(256) k_prefix_max(double* bmax, int nb, const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double sm[256];
     __shared__ double carry;
     if (flag && *flag == 0.0) return;
@@ -320,6 +332,8 @@ k_search(const double* __restrict__ rmax_single, const double* const* __restrict
          int64_t n_out, int64_t out0, int method, uint64_t seed, uint32_t stage, double u, double n_parts,
          int64_t* __restrict__ idx, const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_out) return;
     if (flag && *flag == 0.0) return;
@@ -366,6 +380,8 @@ __global__ void __launch_bounds__(256)
 k_gather(const double* __restrict__ src, double* __restrict__ dst, const int64_t* __restrict__ idx, int64_t N,
          int ncopy, double* __restrict__ wreset, double* __restrict__ nw_hist, const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     if (flag && *flag == 0.0) return;
@@ -390,6 +406,8 @@ k_gather_peer(double* const* __restrict__ peers, const int64_t* __restrict__ pee
               const int64_t* __restrict__ idx, int64_t N, int ncopy, double* __restrict__ wreset, double* __restrict__ nw_hist,
               const double* flag = nullptr)
 {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     if (flag && *flag == 0.0) return;

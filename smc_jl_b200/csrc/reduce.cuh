@@ -5,6 +5,12 @@
 
 namespace smc {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream drains; pdl_wait() blocks until that predecessor has completed and its writes are
+// visible (a no-op for a kernel launched the ordinary way), pdl_trigger() lets the successor's blocks be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =================================================================================================
 // canonical 256-lane block tree + last-block tile tree
 // =================================================================================================

@@ -582,6 +582,8 @@ k_moments_mma(const double* __restrict__ x0, const double* __restrict__ x1, cons
     constexpr int NTILE = NT * (NT + 1) / 2;
     constexpr int REDW = NTILE * 64 + 2;
     __shared__ double red[M1P_WARPS * REDW];
+    pdl_wait();
+    pdl_trigger();
     if (scal && scal[SC_STATUS] != 0.0) return;
     const double* __restrict__ X = (scal && scal[SC_RESAMPLE] != 0.0) ? x1 : x0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, k = lane & 3;
@@ -713,6 +715,7 @@ k_moments_finish(const double* __restrict__ partials, int P, int nq, double* __r
     __shared__ double smr[8];
     __shared__ bool is_last;
     __shared__ PrepSmem ps;
+    pdl_wait();
     if (scal[SC_STATUS] != 0.0) return;
     const double r = tiles_tree_block<256>(partials + (size_t)blockIdx.x * P, P, smr);
     if (threadIdx.x == 0) {
