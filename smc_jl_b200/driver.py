@@ -163,6 +163,41 @@ def _worker(rank, world, port, tmpdir, args, kwargs, ret):
         dist.destroy_process_group()
 
 
+def nan_ess_message(incremental_weights, normalized_weights):
+    """The assertion text of check_nan_ess (src/helpers.jl:270-305)."""
+    inc, nw = np.asarray(incremental_weights, float), np.asarray(normalized_weights, float)
+    text = "No particles have non-zero weight."
+    if np.any(np.isinf(inc)):
+        text += " Some particles have approximately infinite log-likelihoods."
+    if np.any(np.isnan(inc)):
+        text += " Some particles have approximately NaN log-likelihoods."
+    with np.errstate(all="ignore"):
+        q = float(np.sum(nw ** 2))
+    if q <= np.finfo(float).eps:
+        text += " The squared sum of the normalized weights is at machine-error."
+    if np.isnan(q):
+        text += " The squared sum of the normalized weights is returning a NaN."
+        if np.any(np.isnan(nw)):
+            text += " Part of the reason is that one of the normalized weights is a NaN"
+    return text
+
+
+def check_nan_ess(cloud, incremental_weights, normalized_weights, savepath, debug_assertion):
+    """check_nan_ess (src/helpers.jl:270-305) once the engine has reported a NaN ESS: with `debug_assertion` the incremental
+    weights, the normalised weights and the cloud go to `<savepath>_debug_assertion.jld2` (`.npz` paths: numpy container);
+    always raises the reference's AssertionError."""
+    text = nan_ess_message(incremental_weights, normalized_weights)
+    if debug_assertion:
+        if savepath.endswith(".npz"):
+            np.savez(savepath.replace(".npz", "_debug_assertion.npz"), incremental_weights=incremental_weights,
+                     normalized_weights=normalized_weights, particles=cloud.particles)
+        else:
+            from .jld2 import write_jld2
+            write_jld2(savepath.replace(".jld2", "_debug_assertion.jld2"), cloud, np.asarray(incremental_weights, float),
+                       np.asarray(normalized_weights, float), array_keys=("incremental_weights", "normalized_weights"))
+    raise AssertionError(text)
+
+
 def smc(loglikelihood, parameters, data=None, *, n_gpus=1, **kwargs):
     """See the module docstring; keyword arguments as in src/smc_main.jl:118-161 plus `seed`, `device`, `weight_history`,
     `engine` (an existing single-GPU Engine) and `n_gpus`."""
@@ -337,7 +372,21 @@ def _smc(grp, loglikelihood, parameters, data=None, *, verbose="low", testing=Fa
                               seed=seed, stage=i + 1)
             inc_h = np.zeros((n_batch, eng.count)) if weight_history else None
             nw_h = np.zeros((n_batch, eng.count)) if weight_history else None
-            results = eng.run_stages(cfg, state, schedule, i + 1, n_batch, inc_hist=inc_h, normw_hist=nw_h)
+            try:
+                results = eng.run_stages(cfg, state, schedule, i + 1, n_batch, inc_hist=inc_h, normw_hist=nw_h)
+            except AssertionError:
+                # NaN ESS (smc_main.jl:430 -> check_nan_ess): the failing stage left its normalised weights in the cloud and,
+                # when the history is on, its incremental weights in the stream
+                k_bad = len(eng.last_results)
+                nw_bad = grp.gather_rows(eng.read_column(-1)[:, None], "nan_W")
+                inc_bad = grp.gather_rows((inc_h[k_bad] if inc_h is not None and k_bad < len(inc_h) else np.full(eng.count, np.nan))[:, None],
+                                          "nan_w")
+                P_bad = grp.gather_rows(eng.download(), "nan_particles")
+                if lead:
+                    cloud.particles = np.asfortranarray(P_bad)
+                    cloud.ESS = np.array(ess_list + [np.nan])
+                    check_nan_ess(cloud, inc_bad[:, 0], nw_bad[:, 0], savepath, debug_assertion)
+                raise
             dt = (time.perf_counter() - t0) / max(len(results), 1)
             for k, res in enumerate(results):
                 i += 1

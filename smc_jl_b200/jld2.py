@@ -154,7 +154,7 @@ def gcol(objects, size=4096):
 CLOUD_FIELDS = ("particles", "tempering_schedule", "ESS", "stage_index", "n_Φ", "resamples", "c", "accept", "total_sampling_time")
 
 
-def write_jld2(path, cloud, w=None, W=None, j=None, julia_version="1.5.0"):
+def write_jld2(path, cloud, w=None, W=None, j=None, julia_version="1.5.0", array_keys=("w", "W")):
     """`jldopen(path, true, true, true, IOStream) do file; write(file, "cloud", cloud); write(file, "w", w); write(file, "W", W)
     [; write(file, "j", j)] end` (src/smc_main.jl:499-507,521-525).  `cloud` is a smc_jl_b200.cloud.Cloud."""
     blob = bytearray(48)                                   # superblock placeholder (offsets below are relative to BASE)
@@ -208,7 +208,7 @@ def write_jld2(path, cloud, w=None, W=None, j=None, julia_version="1.5.0"):
     put(scalar_object(payload, shared_dt(t2_addr), 3))
     put(part); put(sched); put(ess)
     links = [("cloud", cloud_addr)]
-    for key, arr in (("w", w), ("W", W)):
+    for key, arr in ((array_keys[0], w), (array_keys[1], W)):        # array_keys: the debug dump of check_nan_ess stores two vectors
         if arr is not None:
             a = here()
             put(array_object(a, np.asarray(arr)))

@@ -105,3 +105,28 @@ def test_driver_containers_round_trip(tmp_path):
         c2, w2, W2, j2 = load_cloud(path)
         assert np.array_equal(c2.particles, c.particles) and np.array_equal(w2, w) and np.array_equal(W2, W) and j2 == 5
         assert (c2.stage_index, c2.n_Φ, c2.resamples, c2.c, c2.accept) == (4, 7, 1, 0.37, 0.22)
+
+
+def test_check_nan_ess_message_and_debug_dump(tmp_path):
+    """check_nan_ess (src/helpers.jl:270-305): the assertion text names what went wrong, and `debug_assertion` writes
+    incremental_weights / normalized_weights / cloud to <savepath>_debug_assertion.jld2 before raising."""
+    pytest.importorskip("smc_jl_b200.driver")
+    from smc_jl_b200.driver import check_nan_ess, nan_ess_message
+    from smc_jl_b200.jld2 import read_jld2
+    inc, nw = np.zeros(6), np.full(6, np.nan)
+    assert nan_ess_message(inc, nw) == ("No particles have non-zero weight. The squared sum of the normalized weights is returning a NaN."
+                                        " Part of the reason is that one of the normalized weights is a NaN")
+    assert "infinite log-likelihoods" in nan_ess_message(np.array([np.inf, 1.0]), np.array([0.0, 0.0]))
+    assert "at machine-error" in nan_ess_message(np.array([0.0, 0.0]), np.array([0.0, 0.0]))
+    c = Cloud(np.asfortranarray(np.arange(48.0).reshape(6, 8)), tempering_schedule=np.linspace(0, 1, 3), ESS=np.array([6.0, np.nan]),
+              stage_index=2, n_Φ=3, resamples=0, c=0.5, accept=0.25, total_sampling_time=0.0)
+    save = str(tmp_path / "smc_cloud.jld2")
+    with pytest.raises(AssertionError, match="No particles have non-zero weight"):
+        check_nan_ess(c, inc, nw, save, True)
+    d = read_jld2(str(tmp_path / "smc_cloud_debug_assertion.jld2"))
+    assert set(d) == {"cloud", "incremental_weights", "normalized_weights"}
+    assert np.array_equal(d["incremental_weights"], inc) and np.all(np.isnan(d["normalized_weights"]))
+    assert np.array_equal(d["cloud"].particles, c.particles)
+    with pytest.raises(AssertionError):
+        check_nan_ess(c, inc, nw, str(tmp_path / "other.jld2"), False)
+    assert not (tmp_path / "other_debug_assertion.jld2").exists()

@@ -204,6 +204,25 @@ def test_errors_mirror_the_reference():
         smc(lk, fixed, None, testing=True, verbose="none")
 
 
+def test_nan_ess_raises_like_the_reference_and_dumps_the_debug_file(tmp_path):
+    """A likelihood so sharp that every incremental weight underflows: ESS is NaN, smc() raises check_nan_ess's assertion
+    (src/helpers.jl:270-305) and, with debug_assertion, leaves <savepath>_debug_assertion.jld2."""
+    from smc_jl_b200 import smc
+    from smc_jl_b200.jld2 import read_jld2
+    rng = np.random.default_rng(5)
+    X = np.column_stack([np.ones(40), rng.normal(size=40)])
+    y = 1e7 * (X @ np.array([1.0, 2.0]))                                     # residuals ~1e7: exp(-1e14 / 2) == 0 for every particle
+    params = [M.parameter("a", 0.0, (-1e5, 1e5), (-1e5, 1e5), None, M.Normal(0, 1)),
+              M.parameter("b", 0.0, (-1e5, 1e5), (-1e5, 1e5), None, M.Normal(0, 1))]
+    save = str(tmp_path / "smc_cloud.jld2")
+    with pytest.raises(AssertionError, match="No particles have non-zero weight"):
+        smc(M.LinearGaussianLogLik(y, X, 1.0), params, None, verbose="none", testing=True, n_parts=512, n_Φ=2, seed=1,
+            savepath=save, particle_store_path=str(tmp_path / "p.h5"), debug_assertion=True)
+    d = read_jld2(str(tmp_path / "smc_cloud_debug_assertion.jld2"))
+    assert d["cloud"].particles.shape == (512, 7) and np.all(d["incremental_weights"] == 0.0)
+    assert np.all(np.isnan(d["normalized_weights"]))
+
+
 def test_sharded_smc_matches_the_single_gpu_run(tmp_path):
     """`smc(...; n_gpus = 2)` (the reference's `parallel = true`): one process per GPU, the bridge initialisation of a tempered
     update, the whole recursion and the output files on a sharded engine -- the same cloud, history and files as on one GPU."""
