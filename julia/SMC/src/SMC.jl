@@ -202,7 +202,7 @@ function CAPMLogLik(lik_data::Matrix{Float64}, market_data::AbstractArray{Float6
 end
 # Three-equation An-Schorfheide DSGE model (examples/dsge_models/small_dsge_model.jl:35-50): replaces the closure
 #   loglik(p, d) = DSGE.likelihood(m, d; sampler = false, catch_errors = true, use_chand_recursion = true)
-# `parameters` must be DSGE.jl's AnSchorfheide ParameterVector (16 entries); data is 3 x T without missing values.
+# `parameters` must be DSGE.jl's AnSchorfheide ParameterVector (16 entries); data is 3 x T; NaN entries are missing observations (dropped from that period's update).
 struct AnSchorfheideLogLik <: DeviceLogLik         # SMCB200_LIK_AS_DSGE
     iparams::Vector{Int32}          # n_periods, n_presample
     dparams::Vector{Float64}        # vec(data): 3 x T column-major

@@ -209,6 +209,47 @@ ORC_API double orc_as_loglik(const double *th, const double *data, int T, int np
         const double n0 = (yt[0] - ((xn[SY] - xn[SYL]) + xn[SZ])) - D0;
         const double n1 = (yt[1] - 4.0 * xn[SPI]) - D1;
         const double n2 = (yt[2] - 4.0 * xn[SR]) - D2;
+        /* missing observations (NaN): DSGE.jl's filter drops those rows of the measurement equation for the period --
+         * the reduced system below (observed indices in ascending order); a period without any observation only predicts */
+        int obs[3], m = 0;
+        for (int k = 0; k < 3; ++k) if (yt[k] == yt[k]) obs[m++] = k;
+        if (m < 3) {
+            const double Ffull[3][3] = {{F00, F10, F20}, {F10, F11, F21}, {F20, F21, F22}};
+            const double nfull[3] = {n0, n1, n2};
+            double Lr[3][3] = {{0}}, dr[3] = {1, 1, 1}, rr[3] = {1, 1, 1}, wr[3] = {0, 0, 0}, vr[3] = {0, 0, 0};
+            /* F_red = L D L' by the same elimination as the full 3 x 3 case: for a < m
+             *   t_ab = F_ab - sum_{c<b} l_ac t'_bc ... written out for m <= 2 */
+            if (m >= 1) { dr[0] = Ffull[obs[0]][obs[0]]; rr[0] = 1.0 / dr[0]; wr[0] = nfull[obs[0]]; }
+            if (m == 2) {
+                const double f10 = Ffull[obs[1]][obs[0]], f11 = Ffull[obs[1]][obs[1]];
+                Lr[1][0] = f10 * rr[0];
+                dr[1] = FMA(-Lr[1][0], f10, f11); rr[1] = 1.0 / dr[1];
+                wr[1] = FMA(-Lr[1][0], wr[0], nfull[obs[1]]);
+            }
+            for (int a2 = 0; a2 < m; ++a2) { if (!(dr[a2] > 0.0)) bad = 1; vr[a2] = wr[a2] * rr[a2]; }
+            if (t >= npre) {
+                const double det = (m == 0) ? 1.0 : (m == 1 ? dr[0] : dr[0] * dr[1]);
+                const double quad = (m == 0) ? 0.0 : (m == 1 ? wr[0] * vr[0] : FMA(wr[1], vr[1], wr[0] * vr[0]));
+                ll = ll + -0.5 * (((double)m * 1.8378770664093453 + orc_log(det)) + quad);
+            }
+            double Hr[NS][2], HRr[NS][2];
+            for (int i = 0; i < NS; ++i) {
+                double xi = xn[i];
+                if (m >= 1) { Hr[i][0] = PZ[i][obs[0]]; HRr[i][0] = Hr[i][0] * rr[0]; }
+                if (m == 2) { Hr[i][1] = FMA(-Lr[1][0], Hr[i][0], PZ[i][obs[1]]); HRr[i][1] = Hr[i][1] * rr[1]; }
+                if (m >= 1) xi = FMA(Hr[i][0], vr[0], xi);
+                if (m == 2) xi = FMA(Hr[i][1], vr[1], FMA(Hr[i][0], vr[0], xn[i]));
+                x[i] = xi;
+            }
+            for (int i = 0; i < NS; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double w = Pn[i][j];
+                    if (m >= 1) w = FMA(-HRr[i][0], Hr[j][0], w);
+                    if (m == 2) w = FMA(-HRr[i][1], Hr[j][1], FMA(-HRr[i][0], Hr[j][0], Pn[i][j]));
+                    P[i][j] = w; P[j][i] = w;
+                }
+            continue;
+        }
         /* F = L D L' (unit lower L, no square roots): d_k > 0 <=> F positive definite */
         const double d0 = F00, r0 = 1.0 / d0;
         const double l10 = F10 * r0, l20 = F20 * r0;

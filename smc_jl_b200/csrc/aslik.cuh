@@ -74,7 +74,9 @@ __device__ __forceinline__ bool stable_root(double c3, double c2, double c1, dou
 }  // namespace as
 
 // theta = (tau, kappa, psi1, psi2, rA, pi*, gammaQ, rho_R, rho_g, rho_z, sigma_R, sigma_g, sigma_z, e_y, e_pi, e_R)
-__device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th)
+// NANS: the data hold missing observations (instantiated separately so that complete data run exactly the code they always did)
+template <bool NANS>
+__device__ __noinline__ double as_loglik_t(int slot, const double* __restrict__ th)
 {
     using namespace as;
     const double tau = th[0], kap = th[1], psi1 = th[2], psi2 = th[3], rA = th[4], pistar = th[5], gamQ = th[6];
@@ -204,15 +206,35 @@ __device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th
             PZ[i][1] = 4.0 * Pn[lo(i, SPI)];
             PZ[i][2] = 4.0 * Pn[lo(i, SR)];
         }
-        const double F00 = ((PZ[SY][0] - PZ[SYL][0]) + PZ[SZ][0]) + E0;
-        const double F10 = 4.0 * PZ[SPI][0];
-        const double F11 = 4.0 * PZ[SPI][1] + E1;
-        const double F20 = 4.0 * PZ[SR][0];
-        const double F21 = 4.0 * PZ[SR][1];
-        const double F22 = 4.0 * PZ[SR][2] + E2;
-        const double n0 = (y0 - ((xn[SY] - xn[SYL]) + xn[SZ])) - D0;
-        const double n1 = (y1 - 4.0 * xn[SPI]) - D1;
-        const double n2 = (y2 - 4.0 * xn[SR]) - D2;
+        double F00 = ((PZ[SY][0] - PZ[SYL][0]) + PZ[SZ][0]) + E0;
+        double F10 = 4.0 * PZ[SPI][0];
+        double F11 = 4.0 * PZ[SPI][1] + E1;
+        double F20 = 4.0 * PZ[SR][0];
+        double F21 = 4.0 * PZ[SR][1];
+        double F22 = 4.0 * PZ[SR][2] + E2;
+        double n0 = (y0 - ((xn[SY] - xn[SYL]) + xn[SZ])) - D0;
+        double n1 = (y1 - 4.0 * xn[SPI]) - D1;
+        double n2 = (y2 - 4.0 * xn[SR]) - D2;
+        // Missing observations (NaN; DSGE.jl's filter drops those rows for the period): a missing slot k becomes an inert
+        // pivot -- F_kk = 1, F_kj = 0, innovation 0, gain column 0 -- so the factorisation below passes through it with exact
+        // zeros and ones and the remaining slots see precisely the operations of the reduced system (what the oracle runs).
+        // Warp-uniform: the data are the same for every particle.
+        double nobs_c = 3.0 * 1.8378770664093453;
+        if (NANS) {
+            const bool m0 = y0 != y0, m1 = y1 != y1, m2 = y2 != y2;
+            if (m0 | m1 | m2) {
+                if (m0) { F00 = 1.0; F10 = 0.0; F20 = 0.0; n0 = 0.0; }
+                if (m1) { F11 = 1.0; F10 = 0.0; F21 = 0.0; n1 = 0.0; }
+                if (m2) { F22 = 1.0; F20 = 0.0; F21 = 0.0; n2 = 0.0; }
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    if (m0) PZ[i][0] = 0.0;
+                    if (m1) PZ[i][1] = 0.0;
+                    if (m2) PZ[i][2] = 0.0;
+                }
+                nobs_c = (double)(3 - (int)m0 - (int)m1 - (int)m2) * 1.8378770664093453;
+            }
+        }
         // F = L D L' (unit lower L): three reciprocals, no square roots; d_k > 0 <=> F positive definite
         const double d0 = F00, r0 = 1.0 / d0;
         const double l10 = F10 * r0, l20 = F20 * r0;
@@ -228,7 +250,7 @@ __device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th
         if (t >= npre) {
             const double logdet = det_log((d0 * d1) * d2);
             const double quad = fma(w2, v2, fma(w1, v1, w0 * v0));
-            ll = ll + -0.5 * ((3.0 * 1.8378770664093453 + logdet) + quad);
+            ll = ll + -0.5 * ((nobs_c + logdet) + quad);
         }
         // update: H = PZ L^{-T}; x += H D^{-1} w; P -= H D^{-1} H'
         double H[NS][3], HR[NS][3];
@@ -249,6 +271,11 @@ __device__ __noinline__ double as_loglik(int slot, const double* __restrict__ th
     if (bad) return -dinf();
     if (!(ll == ll)) return -dinf();
     return ll;
+}
+
+__device__ __forceinline__ double as_loglik(int slot, const double* __restrict__ th)
+{
+    return c_as[slot].has_nan ? as_loglik_t<true>(slot, th) : as_loglik_t<false>(slot, th);
 }
 
 struct ASLik {

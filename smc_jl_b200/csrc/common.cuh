@@ -87,6 +87,7 @@ struct LikDesc {                // host copy of a likelihood slot's shape
 struct ASConst {                // An-Schorfheide DSGE likelihood slot: 3 x T data (column-major) in global memory
     const double* data;
     int32_t T, npre;
+    int32_t has_nan, pad;        // some observation is missing (NaN): the filter masks those slots period by period
 };
 struct PeerCtx {                 // the NVLink mailboxes of this rank's communicator (world == 1: unused)
     double* const* inbox;        // device table [world]: every rank's inbox

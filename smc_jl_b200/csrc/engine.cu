@@ -969,13 +969,17 @@ int32_t smcb200_set_likelihood(smcb200_ctx* c, int32_t slot, int32_t kind, const
         if (n_ip < 2 || !ip || !dp) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "AS_DSGE needs iparams {n_periods, n_presample}");
         const int T = ip[0], npre = ip[1];
         if (T < 1 || npre < 0 || n_dp != (int64_t)3 * T) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "AS_DSGE data must be 3 x n_periods");
-        for (int64_t i = 0; i < n_dp; ++i)
-            if (!(dp[i] - dp[i] == 0.0)) return fail(c, SMCB200_ERR_UNSUPPORTED, "AS_DSGE: missing / non-finite observations are not supported");
+        int has_nan = 0;
+        for (int64_t i = 0; i < n_dp; ++i) {
+            if (dp[i] != dp[i]) { has_nan = 1; continue; }      // NaN = missing observation (dropped from that period's update)
+            if (!(dp[i] - dp[i] == 0.0)) return fail(c, SMCB200_ERR_BAD_ARGUMENT, "AS_DSGE: infinite observations");
+        }
         cudaSetDevice(c->device);
         if (c->as_data[slot]) { cudaFree(c->as_data[slot]); c->as_data[slot] = nullptr; }
         SMC_CUDA(c, cudaMalloc(&c->as_data[slot], sizeof(double) * 3 * (size_t)T));
         SMC_CUDA(c, cudaMemcpy(c->as_data[slot], dp, sizeof(double) * 3 * (size_t)T, cudaMemcpyHostToDevice));
         c->as_host[slot].data = c->as_data[slot]; c->as_host[slot].T = T; c->as_host[slot].npre = npre;
+        c->as_host[slot].has_nan = has_nan; c->as_host[slot].pad = 0;
         LikDesc L; L.kind = kind;
         c->lik[slot] = L;
         return mutate_upload_model(c);

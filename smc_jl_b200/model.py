@@ -197,7 +197,8 @@ class AnSchorfheideLogLik:
     catch_errors=true, use_chand_recursion=true)`.  `data` is 3 x T (gdp growth, inflation, nominal rate),
     the first `n_presample` periods are filtered but not scored.  The ParameterVector must be the model's
     16 parameters (tau, kappa, psi_1, psi_2, rA, pi_star, gamma_Q, rho_R, rho_g, rho_z, sigma_R, sigma_g,
-    sigma_z, e_y, e_pi, e_R).  Solved and filtered on the device (csrc/aslik.cuh)."""
+    sigma_z, e_y, e_pi, e_R).  NaN entries are missing observations (dropped from that period's update, as DSGE.jl's filter
+    does).  Solved and filtered on the device (csrc/aslik.cuh)."""
     data: np.ndarray
     n_presample: int = 2
     n_para: int = 16
@@ -207,8 +208,8 @@ class AnSchorfheideLogLik:
         self.data = np.ascontiguousarray(np.asarray(self.data, dtype=np.float64))
         if self.data.ndim != 2 or self.data.shape[0] != 3 or self.data.shape[1] < 1:
             raise ValueError("An-Schorfheide data must be 3 x T")
-        if not np.all(np.isfinite(self.data)):
-            raise ValueError("missing observations (NaN) are not supported by the device Kalman filter")
+        if np.any(np.isinf(self.data)):
+            raise ValueError("infinite observations")        # NaN = missing: the filter drops that series for the period
 
     def iparams(self):
         return np.array([self.data.shape[1], self.n_presample], dtype=np.int32)

@@ -684,6 +684,36 @@ def test_as_evaluate_golden_and_oracle(eng, golden):
         assert np.array_equal(got, O.cloud_m(buf, N, 16))
 
 
+def test_as_missing_observations_bitexact(eng, golden):
+    """NaN observations: the device filter's inert-pivot masking equals the oracle's reduced system bit for bit (evaluation and
+    a mutation with old data whose vintage also has gaps); the values differ from the complete-data ones."""
+    g = golden("as_clouds.npz")
+    data = g["data"].copy()
+    rng = np.random.default_rng(8)
+    data[0, 7] = np.nan; data[1, 13] = np.nan; data[2, 19] = np.nan
+    data[[0, 2], 40] = np.nan; data[[1, 2], 41] = np.nan; data[[0, 1], 42] = np.nan; data[:, 60] = np.nan; data[1, 1] = np.nan
+    data[rng.integers(0, 3, 25), rng.integers(70, 230, 25)] = np.nan
+    ps = W.an_schorfheide_parameters()
+    P = np.asfortranarray(g["cloud600"]).copy(order="F")
+    N = P.shape[0]
+    spec = M.make_spec(ps, M.AnSchorfheideLogLik(data))
+    eng.cloud_create(N, 16)
+    eng.set_model(spec)
+    eng.upload(W_reset(P))
+    eng.evaluate(0)
+    got = eng.download()
+    buf = O.cloud_f(W_reset(P))
+    mod = O.Model(spec)                                        # (keep the handle alive across the call)
+    O.lib().orc_evaluate(mod.h, buf, N)
+    assert np.array_equal(got, O.cloud_m(buf, N, 16))
+    assert np.all(np.isfinite(got[:, 16])) and not np.any(got[:, 16] == P[:, 16])
+    spec2 = M.make_spec(ps, M.AnSchorfheideLogLik(data), M.AnSchorfheideLogLik(data[:, :115]))
+    Q = got.copy(order="F")
+    Q[:, -1] = 1.0
+    got2, want2, acc, oacc = _mutation_case(eng, spec2, Q, [np.arange(13)], 0.6, 0.5, 0.3, 1, True, 99, 7)
+    assert np.array_equal(got2, want2) and acc == oacc and acc > 0.0
+
+
 def test_as_initialize_likelihoods_golden(eng, golden):
     """Online update: initialize_likelihoods! moves loglh (first vintage, 115 periods) to old_loglh and
     re-evaluates on the full sample; the saved cloud of the reference's second-vintage run holds both columns."""

@@ -365,3 +365,31 @@ def test_as_determinacy_and_values_against_qz_gensys(golden):
         else:
             n_indet += 1
     assert n_det > 100 and n_indet > 30
+
+
+def test_as_likelihood_with_missing_observations_against_the_dense_filter(golden):
+    """NaN observations (DSGE.jl's Kalman filter drops those rows of the measurement equation for the period): the oracle's
+    reduced-system update against a dense 8-state filter that deletes the rows -- single series missing, two missing, whole
+    periods missing, missing inside the presample."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("as_gensys", os.path.join(os.path.dirname(__file__), "..", "tools", "as_gensys_check.py"))
+    gz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gz)
+    g = golden("as_clouds.npz")
+    data = g["data"][:, :80].copy()
+    rng = np.random.default_rng(4)
+    data[0, 5] = np.nan; data[1, 9] = np.nan; data[2, 11] = np.nan             # one series missing
+    data[[0, 2], 20] = np.nan; data[[1, 2], 21] = np.nan; data[[0, 1], 22] = np.nan
+    data[:, 30] = np.nan; data[:, 31] = np.nan                                  # nothing observed
+    data[1, 0] = np.nan                                                        # inside the presample
+    data[rng.integers(0, 3, 12), rng.integers(35, 80, 12)] = np.nan
+    flat = np.ascontiguousarray(data.T).ravel()
+    base = g["cloud600"][:, :16]
+    full = np.ascontiguousarray(g["data"][:, :80].T).ravel()
+    for r in range(40):
+        th = np.ascontiguousarray(base[r * 7 % base.shape[0]])
+        ours = O.lib().orc_as_loglik(th, flat, 80, 2)
+        ref = gz.loglik8(th, data)
+        assert np.isfinite(ours) and ours == pytest.approx(ref, rel=1e-8, abs=1e-7), (r, ours, ref)
+        assert ours != O.lib().orc_as_loglik(th, full, 80, 2)                   # and the missing entries do matter

@@ -72,11 +72,15 @@ def loglik8(p, data, npre=2):
     P = sl.solve_discrete_lyapunov(T, RQR); s = np.zeros(8); ll = 0.0
     for t in range(data.shape[1]):
         s = T @ s; P = T @ P @ T.T + RQR
-        nu = data[:, t] - ZZ @ s - DD
-        F = ZZ @ P @ ZZ.T + EE
+        ok = ~np.isnan(data[:, t])                      # missing observations: drop their rows for this period (DSGE.jl's filter)
+        if not ok.any():
+            continue
+        Z, D, E = ZZ[ok], DD[ok], EE[np.ix_(ok, ok)]
+        nu = data[ok, t] - Z @ s - D
+        F = Z @ P @ Z.T + E
         Fi = np.linalg.inv(F)
         if t >= npre:
-            ll += -0.5 * (3 * np.log(2 * np.pi) + np.log(np.linalg.det(F)) + nu @ Fi @ nu)
-        K = P @ ZZ.T @ Fi
-        s = s + K @ nu; P = P - K @ ZZ @ P
+            ll += -0.5 * (ok.sum() * np.log(2 * np.pi) + np.log(np.linalg.det(F)) + nu @ Fi @ nu)
+        K = P @ Z.T @ Fi
+        s = s + K @ nu; P = P - K @ Z @ P
     return ll
