@@ -163,7 +163,7 @@ struct Ctx {
     int coop_blocks_per_sm[3] = {0, 0, 0};    // occupancy of k_correct_coop<3 / 7 / 15> (queried once)
     int sm_count = 0;
     double* coop_partials = nullptr; size_t coop_partials_len = 0;
-    double* coop_gsum = nullptr; unsigned long long* coop_gflag = nullptr; unsigned long long coop_gen = 0;
+    unsigned long long* coop_seq = nullptr;          // device: sequence number of the correction kernel's next cross-GPU reduction
     unsigned* coop_ticket = nullptr;
     int coop_ll_single = 0;
     double* h_summary = nullptr;   // pinned ring of stage summaries [SUMMARY_RING][SC_COUNT]

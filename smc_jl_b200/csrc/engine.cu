@@ -64,10 +64,9 @@ NcclApi* nccl_api()
         }                                                                                          \
     } while (0)
 
-constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_SCAN_MAX = 601, SL_ESS = 604, SL_COUNT = 640;   // slots of scal_loc
+constexpr int SL_MSUM = 16, SL_CSUM = 64, SL_SCAN_ROOT = 600, SL_ESS = 604, SL_COUNT = 640;   // slots of scal_loc
 static_assert(SL_ESS + 2 * ESS_K <= SL_COUNT, "scal_loc too small");
 // where a kernel should write shard-local roots, and the cross-rank tree that follows
-inline double* local_out(Ctx* c) { return c->world > 1 ? c->scal_loc : c->scal; }
 // cross-rank tree of nq shard-local roots (combine) or their [world][nq] layout (gather into dst): one
 // k_peer_exchange launch over the NVLink mailboxes; `flag` (device, nullable) predicates the launch
 // Launch with the programmatic-serialization attribute: the kernel (which starts with pdl_wait()) may be scheduled while
@@ -180,7 +179,7 @@ int launch_correct_coop(Ctx* c, const CorrectLaunch& L)
     a.c_in = L.c_in; a.accept_in = L.accept_in; a.ess_prev_in = L.ess_prev_in; a.phi_prop_in = L.phi_prop_in; a.j_in = L.j_in;
     a.resampled_last_in = L.resampled_last_in;
     a.partials = c->coop_partials; a.scal = c->scal; a.pc = peer_ctx(c);
-    a.ticket = c->coop_ticket; a.ll_step = c->coop_gflag;
+    a.ticket = c->coop_ticket; a.ll_step = c->coop_seq;
     a.ll_always = c->coop_ll_single;
     void* args[] = {&a};
     const int variant = coop_variant(c->N, L.adaptive != 0);
@@ -657,14 +656,13 @@ int32_t smcb200_create(smcb200_ctx** out, int32_t device)
         ok = ok && cudaEventCreateWithFlags(&c->hist_copied[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMallocHost(&c->h_summary, sizeof(double) * SC_COUNT * SUMMARY_RING) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->coop_gsum, sizeof(double) * 2 * COOP_NQMAX) == cudaSuccess;
-    ok = ok && cudaMalloc(&c->coop_gflag, sizeof(unsigned long long)) == cudaSuccess;       // sequence number of the next cross-GPU reduction
+    ok = ok && cudaMalloc(&c->coop_seq, sizeof(unsigned long long)) == cudaSuccess;       // sequence number of the next cross-GPU reduction
     // developer switch.  One GPU, measured: the grid-barrier reduction (every block finishes the tile tree itself) beats the
     // mailbox form (last block reduces, all poll) -- adaptive solve 0.399 vs 0.422 ms at N = 2^20 -- so it stays the default
     c->coop_ll_single = std::getenv("SMCB200_COOP_MAILBOX") ? 1 : 0;
     ok = ok && cudaMalloc(&c->coop_ticket, sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaMemset(c->coop_ticket, 0, sizeof(unsigned)) == cudaSuccess;
-    ok = ok && cudaMemset(c->coop_gflag, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(c->coop_seq, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->acc_total, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(c->acc_total, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&c->mb_epoch_dev, sizeof(unsigned long long)) == cudaSuccess;
@@ -701,7 +699,7 @@ int32_t smcb200_destroy(smcb200_ctx* c)
     cudaFreeHost(c->h_moments); cudaFree(c->sched_dev);
     cudaFree(c->as_data[0]); cudaFree(c->as_data[1]); cudaFree(c->ess_sq);
     for (int r = 0; r < 16; ++r) if (c->mbox_open[r]) cudaIpcCloseMemHandle(c->mbox_open[r]);
-    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total); cudaFree(c->coop_gsum); cudaFree(c->coop_gflag); cudaFree(c->coop_ticket);
+    cudaFree(c->mbox); cudaFree(c->mbox_tab); cudaFree(c->mb_err); cudaFree(c->mb_epoch_dev); cudaFree(c->acc_total); cudaFree(c->coop_seq); cudaFree(c->coop_ticket);
     cudaFreeHost(c->h_summary);
     for (int i = 0; i < HIST_RING; ++i) {
         if (c->hist_ready[i]) cudaEventDestroy(c->hist_ready[i]);

@@ -636,7 +636,7 @@ struct PrepSmem {
 };
 __device__ __forceinline__ void prepare_proposal_block(PrepSmem& sm, const BlockSpec& bs, double c, MutConst* out, double* scal)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int d = bs.d;
     if (tid == 0) { out->n_blocks = bs.n_blocks; out->status = 0; sm.bad = 0; }
     if (tid < DMAX) out->mu[tid] = (tid < d) ? sm.mean[tid] : 0.0;
