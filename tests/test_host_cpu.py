@@ -359,3 +359,57 @@ def test_incremental_weights_all_prior_weight_branches():
         np.testing.assert_allclose(oinc, inc, rtol=1e-12)
         np.testing.assert_allclose(onw, wn, rtol=1e-12)
         assert out[1] == pytest.approx(N * N / np.sum(wn ** 2), rel=1e-12) and out[2] == pytest.approx(N, rel=1e-12)
+
+
+def test_one_pass_moments_oracle_against_numpy_and_its_own_definition():
+    """orc_moments_shifted (the fused stage's weighted mean / covariance, src/particle.jl:481-532 in one pass): (i) equal to numpy's
+    weighted moments and to the oracle's two-pass form to rounding, also for a cloud 1e4 standard deviations from the origin;
+    (ii) bit-identical to a plain Python restatement of its canonical order -- per quantity a sequential fma chain over each
+    sub-chunk of 256 consecutive particles, then the adjacent-pair tree over sub-chunks -- which is the order the tensor-core
+    SYRK on the device accumulates in."""
+    from fractions import Fraction
+    L = O.lib()
+
+    def fma(a, b, c):                                  # exact: one rounding of a * b + c (float(Fraction) rounds to nearest even)
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+    for N, d, offset in ((1000, 3, 0.0), (777, 5, 1e4), (2048 + 13, 2, -3e3)):
+        rng = np.random.default_rng(N)
+        P = np.zeros((N, d + 5), order="F")
+        P[:, :d] = rng.normal(size=(N, d)) * rng.uniform(0.5, 2.0, d) + offset
+        P[:, d + 4] = rng.uniform(0.2, 2.0, N)
+        shift = np.ascontiguousarray(P[0, :d])
+        mean, cov = np.zeros(d), np.zeros((d, d))
+        L.orc_moments_shifted(O.cloud_f(P), N, d, shift, mean, cov)
+        w = P[:, d + 4]
+        m_np = np.average(P[:, :d], axis=0, weights=w)
+        c_np = np.cov(P[:, :d].T, aweights=w, bias=True).reshape(d, d)
+        sd = np.sqrt(np.diag(c_np))
+        assert np.max(np.abs(mean - m_np) / sd) < 1e-11 and np.max(np.abs(cov - c_np) / np.outer(sd, sd)) < 1e-10
+        m2, c2 = np.zeros(d), np.zeros((d, d))
+        L.orc_moments(O.cloud_f(P), N, d, m2, c2)
+        assert np.max(np.abs(mean - m2) / sd) < 1e-11 and np.max(np.abs(cov - c2) / np.outer(sd, sd)) < 1e-10
+
+        def tree(v):                                   # adjacent-pair tree, zero padded to a power of two
+            v = list(v) + [0.0] * ((1 << max(0, (len(v) - 1).bit_length())) - len(v))
+            while len(v) > 1:
+                v = [v[i] + v[i + 1] for i in range(0, len(v), 2)]
+            return v[0]
+
+        def chain(term):                               # sequential fma chain per sub-chunk of 256 particles
+            out = []
+            for c0 in range(0, N, 256):
+                acc = 0.0
+                for i in range(c0, min(c0 + 256, N)):
+                    a, b = term(i)
+                    acc = fma(a, b, acc)
+                out.append(acc)
+            return tree(out)
+
+        sw = chain(lambda i: (w[i], 1.0))
+        a_, b_ = d - 1, 0
+        mk = chain(lambda i: (w[i], P[i, a_] - shift[a_]))
+        cab = chain(lambda i: (w[i] * (P[i, a_] - shift[a_]), P[i, b_] - shift[b_]))
+        ea, eb = mk / sw, chain(lambda i: (w[i], P[i, b_] - shift[b_])) / sw
+        assert mean[a_] == shift[a_] + ea
+        assert cov[a_, b_] == fma(-ea, eb, cab / sw)
